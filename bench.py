@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — train sequences/s of the SASRec hot path on ml-1m-shaped synthetic data (BASELINE.json configs[1]:
+6040 users, 3416 items, maxlen 200, hidden 50, 2 blocks, 1 head, dropout 0.2; per-GPU batch 128 = the reference's
+ml-1m run, saved_models/ml-1m.txt/sasrec_baseline_*/params.txt), full training step = forward + loss + backward +
+deterministic sparse embedding gradient + (all-reduce) + TF-Adam.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch_size B] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job sequences/s with inputs resident in HBM (CUDA-graph replay, CUDA
+events, max over ranks, L2 flushed between timed steps); `e2e` = the same through `SASRec.train_step` with HOST
+numpy batches (pinned staging + H2D + D2H of the loss inside the timed region); `roofline` = the dominant kernel
+timed with CUDA events on the launch stream; `cpu_baseline` = the CPU oracle (PyTorch restatement of the reference
+graph, `oracle/`) on the box's host cores over a bounded sample.  `--impl reference` times that CPU arm alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2: SASRec ml-1m-shaped synthetic (6040 users, 3416 items, mean train len 163.5), maxlen=200, hidden=50, " \
+           "blocks=2, heads=1, dropout=0.2"
+USERNUM, ITEMNUM, MEAN_LEN = 6040, 3416, 163.5
+
+
+def make_args(batch_size):
+    return SimpleNamespace(hidden_units=50, maxlen=200, num_heads=1, num_blocks=2, num_context_blocks=2, max_bins=200,
+                           l2_emb=0.0, lr=1e-3, dropout_rate=0.2, seed=42, batch_size=batch_size, bin_in_hours=48,
+                           log_scale=False)
+
+
+def synth_batches(n_batches, B, T, itemnum, seed):
+    """Seeded ml-1m-shaped batches in the sampler's layout (left-padded seq/pos/neg; sampler.py:16-81): lognormal
+    lengths matched to the 163.5 mean train length (test.py:32-34), Zipf(1.0) item popularity."""
+    rng = np.random.RandomState(seed)
+    ranks = np.arange(1, itemnum + 1, dtype=np.float64)
+    prob = ranks ** -1.0
+    prob /= prob.sum()
+    out = []
+    for _ in range(n_batches):
+        seq = np.zeros((B, T), np.int32)
+        pos = np.zeros((B, T), np.int32)
+        neg = np.zeros((B, T), np.int32)
+        lens = np.clip(rng.lognormal(np.log(MEAN_LEN) - 0.32, 0.8, B), 5, 2000).astype(np.int64)
+        for b in range(B):
+            n = int(min(lens[b], T + 1))
+            items = rng.choice(itemnum, size=n, p=prob) + 1
+            k = n - 1
+            seq[b, T - k:] = items[:-1][-k:] if k else []
+            pos[b, T - k:] = items[1:][-k:] if k else []
+            neg[b, T - k:] = rng.randint(1, itemnum + 1, k)
+        out.append((seq, pos, neg))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_arm(batch_size, steps, warmup, seed=20191019):
+    """The reference's CPU path for this workload = oracle (PyTorch-CPU restatement; TF 1.15 is not installable):
+    forward + backward + TF-Adam on all host cores."""
+    from oracle import cast_oracle as O
+    args = make_args(batch_size)
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = O.init_params("sasrec", args, ITEMNUM, seed=42)
+    opt = O.TFAdam(p, lr=args.lr)
+    batches = synth_batches(2, batch_size, args.maxlen, ITEMNUM, seed)
+    gen = torch.Generator().manual_seed(1)
+
+    def drop(site, x):
+        keep = (torch.rand(x.shape, generator=gen) >= args.dropout_rate).to(x.dtype)
+        return x * keep / (1.0 - args.dropout_rate)
+
+    def step(i):
+        seq, pos, neg = batches[i % len(batches)]
+        b = {"input_seq": torch.from_numpy(seq), "pos": torch.from_numpy(pos), "neg": torch.from_numpy(neg)}
+        return O.train_step("sasrec", p, opt, args, b, drop)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    return batch_size * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch_size", type=int, default=128, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu_steps", type=int, default=8)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_profile", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(a.steps, 10)
+        v, sps, cores = cpu_reference_arm(a.batch_size, steps, min(a.warmup, 2))
+        sample = f"{steps} training steps of B={a.batch_size} sequences (fwd+bwd+TF-Adam), PyTorch-CPU oracle"
+        print(json.dumps({
+            "impl": "reference", "metric": "train_seqs_per_sec", "value": v, "unit": "seq/s", "n_gpus": a.gpus,
+            "steps": steps, "warmup": min(a.warmup, 2), "ms_per_step": sps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": a.batch_size},
+            "cpu_baseline": {"value": v, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import cast_b200
+    from cast_b200 import dist as cdist
+    rank, world, local = cdist.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    args = make_args(a.batch_size)
+    B, T, H = a.batch_size, args.maxlen, args.hidden_units
+    model = cast_b200.SASRec(USERNUM, ITEMNUM, args, device=dev, use_graph=True)
+    eng = model.engine
+    cdist.attach(eng)
+    lib = eng.lib
+    batches = synth_batches(8, B, T, ITEMNUM, seed=20191019 + 1000 * rank)
+    c = eng.ctx(B)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    # ---- (1) device-resident throughput: inputs already in HBM, graph replay, per-step CUDA events
+    dev_batches = [torch.from_numpy(np.stack([x.reshape(-1) for x in b])).to(dev) for b in batches]
+    model.train_step(None, *batches[0])  # builds buffers, captures the graph(s)
+    n0 = lib.cast_launch_count()
+    model.train_step(None, *batches[1])
+    launches_eager = lib.cast_launch_count() - n0  # 0 under graph replay
+    launches_per_step = getattr(model, "launches_per_step", None) or launches_eager
+
+    def device_step(i):
+        c.keys3.copy_(dev_batches[i % len(dev_batches)])
+        model.launch(c)
+
+    for i in range(a.warmup):
+        device_step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    for i in range(a.steps):
+        flush.zero_()
+        ev[i][0].record()
+        device_step(i)
+        ev[i][1].record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    t_dev = sum(s.elapsed_time(e) for s, e in ev) / 1e3
+    t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    t_dev = float(t.item())
+    value = world * B * a.steps / t_dev
+
+    # ---- (2) end to end through the public API with host batches
+    for i in range(3):
+        model.train_step(None, *batches[i % len(batches)])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        model.train_step(None, *batches[i % len(batches)])
+    torch.cuda.synchronize(dev)
+    t_e2e = time.perf_counter() - t0
+    t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    t_e2e = float(t.item())
+    e2e = {"value": world * B * a.steps / t_e2e, "unit": "seq/s", "h2d_bytes_per_step": 3 * B * T * 4,
+           "d2h_bytes_per_step": 12, "ms_per_step": t_e2e / a.steps * 1e3}
+
+    # ---- (3) per-kernel CUDA-event profile (eager launches on the same stream) -> dominant kernel roofline
+    roofline, kernels = None, None
+    if rank == 0 and not a.no_profile:
+        from cast_b200 import profile as cprof
+        kernels = cprof.profile_step(model, c, steps=min(a.steps, 10))
+        roofline = cprof.roofline_of_dominant(kernels, B, T, H, args, ROOT)
+
+    out = {"metric": "train_seqs_per_sec", "value": value, "unit": "seq/s", "n_gpus": world, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                      "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) between timed steps",
+                      "timing": "per-step CUDA events on the launch stream, max over ranks",
+                      "input_path": "pre-generated synthetic batches (not the reference sampler)"},
+           "e2e": e2e, "gpu_launches": int(launches_per_step) * a.steps, "launches_per_step": int(launches_per_step),
+           "clocks": clk}
+    if roofline is not None:
+        out["roofline"] = roofline
+        out["kernel_profile"] = kernels
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, sps, cores = cpu_reference_arm(B, a.cpu_steps, 1)
+        out["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": cores, "kind": "port",
+                               "sample": f"{a.cpu_steps} training steps of B={B} (fwd+bwd+TF-Adam), PyTorch-CPU oracle"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

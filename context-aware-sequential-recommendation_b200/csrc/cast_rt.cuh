@@ -1,0 +1,84 @@
+// Runtime glue shared by every kernel file: launch macro, error codes, warp reductions, the counter-based
+// dropout generator.  Compiled by nvcc for sm_100a.  (tests/emu builds the same sources with -DCAST_EMU on
+// the host to check indexing logic without a GPU; that build is test infrastructure and is never loaded by
+// the package.)
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef CAST_EMU
+#include "cuda_emu.h"
+#define CAST_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  cast_emu::launch(grid, block, smem, [=]() { kernel(__VA_ARGS__); })
+#define CAST_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(cast_emu::dyn_smem_ptr())
+#else
+#include <cuda_runtime.h>
+#define CAST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define CAST_DYN_SMEM(type, name)                                   \
+  extern __shared__ __align__(16) unsigned char name##_raw_smem[]; \
+  type* name = reinterpret_cast<type*>(name##_raw_smem)
+#endif
+
+#include "../../include/cast_b200.h"
+
+#define CAST_NEG_FILL (-4294967296.0f)  // float32(-2**32+1), modules.py:227,239
+
+namespace cast {
+
+int set_error(int code, const char* msg);
+int check_launch(const char* what);
+
+static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- counter-based dropout ------------------------------------------------------------------------------
+// keep(site, idx) = hash(seed, step, site, idx) >= thresh, thresh = floor(rate * 2^32); scale = 1/(1-rate).
+// Masks are a pure function of (seed, step, site, flat element index in the TF-shaped tensor), so the
+// backward kernels regenerate them and tests can hand the identical masks to the oracle.
+struct Drop {
+  unsigned long long key;  // mixed (seed, step, site)
+  unsigned thresh;         // 0 => dropout disabled
+  float scale;
+};
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+
+__device__ __forceinline__ Drop make_drop(float rate, unsigned long long seed, const unsigned long long* step,
+                                          int site) {
+  Drop d;
+  unsigned long long st = step ? *step : 0ull;
+  d.key = mix64(seed + st * 0x9E3779B97F4A7C15ull) ^ mix64(0xD1B54A32D192ED03ull * (unsigned long long)(site + 1));
+  d.thresh = rate > 0.f ? (unsigned)fmin(4294967295.0, floor((double)rate * 4294967296.0)) : 0u;
+  d.scale = rate > 0.f ? 1.0f / (1.0f - rate) : 1.0f;
+  return d;
+}
+
+__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  unsigned long long z = mix64(idx * 0x9E3779B97F4A7C15ull + d.key);
+  return (unsigned)(z >> 32) >= d.thresh;
+}
+
+// multiplier applied by tf.layers.dropout at element idx (0 or 1/(1-rate)); 1 when disabled
+__device__ __forceinline__ float drop_mul(const Drop& d, unsigned long long idx) {
+  if (d.thresh == 0u) return 1.0f;
+  return drop_keep(d, idx) ? d.scale : 0.0f;
+}
+
+}  // namespace cast

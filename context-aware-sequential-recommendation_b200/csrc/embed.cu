@@ -1,0 +1,190 @@
+// K1 / K11: zero-padded table gather x sqrt(H) + position row + context add -> dropout -> padding mask
+// (reference: modules.py:148-160 `embedding`, models/sasrec.py:27-62, models/cast_1.py:62-91), and the
+// element-wise backward companions (dropout/mask backward, concat+dropout for the CAST merges,
+// models/cast_4.py:111-127).  All HBM-bound: one warp per [H] row, lanes stride the row.
+#include "cast_rt.cuh"
+
+namespace cast {
+
+__global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __restrict__ table, int V, int H, long N,
+                                 int T, float scale, const float* __restrict__ pos, const float* __restrict__ add,
+                                 float rate, unsigned long long seed, const unsigned long long* step, int site,
+                                 const int* __restrict__ mask_ids, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int id = ids[row];
+  const bool live = (id > 0) && (id < V);  // row 0 is the zero pad (modules.py:154-156)
+  const float m = mask_ids ? (mask_ids[row] != 0 ? 1.f : 0.f) : 1.f;
+  const Drop d = make_drop(rate, seed, step, site);
+  const float* trow = table + (long)(live ? id : 0) * H;
+  const float* prow = pos ? pos + (long)(row % T) * H : nullptr;
+  const float* arow = add ? add + row * H : nullptr;
+  for (int c = lane; c < H; c += 32) {
+    float v = live ? trow[c] * scale : 0.f;
+    if (prow) v += prow[c];
+    if (arow) v += arow[c];
+    v *= drop_mul(d, (unsigned long long)(row * H + c));
+    v *= m;
+    out[row * H + c] = v;
+  }
+}
+
+// out_m = in * rowmask ; out_md = in * rowmask * dropout_multiplier   (either output may be null)
+__global__ void mask_dropout_kernel(const float* __restrict__ in, const int* __restrict__ mask_ids, float rate,
+                                    unsigned long long seed, const unsigned long long* step, int site, long N,
+                                    int H, float* __restrict__ out_m, float* __restrict__ out_md) {
+  const Drop d = make_drop(rate, seed, step, site);
+  const long total = N * H;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long row = i / H;
+    const float m = mask_ids ? (mask_ids[row] != 0 ? 1.f : 0.f) : 1.f;
+    const float g = in[i] * m;
+    if (out_m) out_m[i] = g;
+    if (out_md) out_md[i] = g * drop_mul(d, (unsigned long long)i);
+  }
+}
+
+// cat[n, s*H + c] = src_s[n, c] * dropA(n*wa*H + col) (s < wa) * dropB(n*k*H + col)
+struct CatSrc {
+  const float* p[4];
+};
+struct CatDst {
+  float* p[4];
+};
+
+__global__ void concat_dropout_fwd_kernel(CatSrc src, int k, int wa, long N, int H, float rateA, int siteA,
+                                          float rateB, int siteB, unsigned long long seed,
+                                          const unsigned long long* step, float* __restrict__ cat) {
+  const Drop dA = make_drop(rateA, seed, step, siteA);
+  const Drop dB = make_drop(rateB, seed, step, siteB);
+  const int W = k * H;
+  const long total = N * W;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / W;
+    const int col = (int)(i - n * W);
+    const int s = col / H;
+    float v = src.p[s][n * H + (col - s * H)];
+    if (s < wa) v *= drop_mul(dA, (unsigned long long)(n * (long)(wa * H) + col));
+    v *= drop_mul(dB, (unsigned long long)i);
+    cat[i] = v;
+  }
+}
+
+__global__ void concat_dropout_bwd_kernel(const float* __restrict__ dcat, int k, int wa, long N, int H, float rateA,
+                                          int siteA, float rateB, int siteB, unsigned long long seed,
+                                          const unsigned long long* step, CatDst dst) {
+  const Drop dA = make_drop(rateA, seed, step, siteA);
+  const Drop dB = make_drop(rateB, seed, step, siteB);
+  const int W = k * H;
+  const long total = N * W;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / W;
+    const int col = (int)(i - n * W);
+    const int s = col / H;
+    if (!dst.p[s]) continue;
+    float g = dcat[i];
+    if (s < wa) g *= drop_mul(dA, (unsigned long long)(n * (long)(wa * H) + col));
+    g *= drop_mul(dB, (unsigned long long)i);
+    dst.p[s][n * H + (col - s * H)] = g;
+  }
+}
+
+__global__ void dropout_keep_kernel(float rate, unsigned long long seed, const unsigned long long* step, int site,
+                                    long n, unsigned char* __restrict__ keep) {
+  const Drop d = make_drop(rate, seed, step, site);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    keep[i] = (d.thresh == 0u || drop_keep(d, (unsigned long long)i)) ? 1 : 0;
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                             long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = a[i] + b[i];
+}
+
+// out = dy * (act > 0 ? scale : 0)   (ReLU backward; with scale = 1/(1-rate) also dropout∘ReLU backward)
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ act, float scale,
+                                float* __restrict__ out, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = act[i] > 0.f ? dy[i] * scale : 0.f;
+}
+
+static inline int ew_grid(long total) {
+  long g = cdiv(total, 256);
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace cast
+
+using namespace cast;
+
+extern "C" int cast_embed_fwd(const int* ids, const float* table, int V, int H, long N, int T, float scale,
+                              const float* pos, const float* add, float drop_rate, unsigned long long seed,
+                              const unsigned long long* step, int site, const int* mask_ids, float* out,
+                              void* stream) {
+  if (!ids || !table || !out || H <= 0 || N < 0 || T <= 0 || V <= 0) return set_error(CAST_ERR_BAD_ARG, "embed_fwd");
+  if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "embed_fwd: drop_rate");
+  if (N == 0) return CAST_OK;
+  const int wpb = 8;
+  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, ids, table,
+              V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
+  return check_launch("embed_fwd");
+}
+
+extern "C" int cast_mask_dropout(const float* in, const int* mask_ids, float drop_rate, unsigned long long seed,
+                                 const unsigned long long* step, int site, long N, int H, float* out_masked,
+                                 float* out_masked_dropped, void* stream) {
+  if (!in || N < 0 || H <= 0) return set_error(CAST_ERR_BAD_ARG, "mask_dropout");
+  if (N == 0) return CAST_OK;
+  CAST_LAUNCH(mask_dropout_kernel, dim3(ew_grid(N * H)), dim3(256), 0, (cudaStream_t)stream, in, mask_ids,
+              drop_rate, seed, step, site, N, H, out_masked, out_masked_dropped);
+  return check_launch("mask_dropout");
+}
+
+extern "C" int cast_concat_dropout_fwd(const float* const* srcs, int k, int width_a, long N, int H, float rate_a,
+                                       int site_a, float rate_b, int site_b, unsigned long long seed,
+                                       const unsigned long long* step, float* cat, void* stream) {
+  if (!srcs || k < 1 || k > 4 || width_a < 0 || width_a > k || !cat) return set_error(CAST_ERR_BAD_ARG, "concat_fwd");
+  CatSrc s;
+  for (int i = 0; i < 4; ++i) s.p[i] = i < k ? srcs[i] : nullptr;
+  if (N == 0) return CAST_OK;
+  CAST_LAUNCH(concat_dropout_fwd_kernel, dim3(ew_grid(N * H * k)), dim3(256), 0, (cudaStream_t)stream, s, k,
+              width_a, N, H, rate_a, site_a, rate_b, site_b, seed, step, cat);
+  return check_launch("concat_dropout_fwd");
+}
+
+extern "C" int cast_concat_dropout_bwd(const float* dcat, int k, int width_a, long N, int H, float rate_a, int site_a,
+                                       float rate_b, int site_b, unsigned long long seed,
+                                       const unsigned long long* step, float* const* dsts, void* stream) {
+  if (!dsts || k < 1 || k > 4 || width_a < 0 || width_a > k || !dcat) return set_error(CAST_ERR_BAD_ARG, "concat_bwd");
+  CatDst d;
+  for (int i = 0; i < 4; ++i) d.p[i] = i < k ? dsts[i] : nullptr;
+  if (N == 0) return CAST_OK;
+  CAST_LAUNCH(concat_dropout_bwd_kernel, dim3(ew_grid(N * H * k)), dim3(256), 0, (cudaStream_t)stream, dcat, k,
+              width_a, N, H, rate_a, site_a, rate_b, site_b, seed, step, d);
+  return check_launch("concat_dropout_bwd");
+}
+
+extern "C" int cast_dropout_keep(float drop_rate, unsigned long long seed, const unsigned long long* step, int site,
+                                 long n, unsigned char* keep, void* stream) {
+  if (!keep || n < 0) return set_error(CAST_ERR_BAD_ARG, "dropout_keep");
+  if (n == 0) return CAST_OK;
+  CAST_LAUNCH(dropout_keep_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, drop_rate, seed, step,
+              site, n, keep);
+  return check_launch("dropout_keep");
+}
+
+extern "C" int cast_add(const float* a, const float* b, float* out, long n, void* stream) {
+  if (!a || !b || !out || n < 0) return set_error(CAST_ERR_BAD_ARG, "add");
+  if (n == 0) return CAST_OK;
+  CAST_LAUNCH(axpby_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, a, b, out, n);
+  return check_launch("add");
+}
+
+extern "C" int cast_relu_bwd(const float* dy, const float* act, float scale, float* out, long n, void* stream) {
+  if (!dy || !act || !out || n < 0) return set_error(CAST_ERR_BAD_ARG, "relu_bwd");
+  if (n == 0) return CAST_OK;
+  CAST_LAUNCH(relu_bwd_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, dy, act, scale, out, n);
+  return check_launch("relu_bwd");
+}

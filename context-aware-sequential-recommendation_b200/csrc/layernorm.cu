@@ -1,0 +1,198 @@
+// K2: layer normalisation exactly as modules.py:53-80 `normalize` — biased variance, eps inside the sqrt,
+// gamma * xhat + beta — forward and backward, one warp per row with shuffle reductions (H <= 1024).
+// Forward also emits the two "is this row exactly zero-sum" flags that multihead_attention derives from its
+// inputs (modules.py:222 key mask from sum_H(keys), :248 query mask from sum_H(queries)).
+// Backward: dx = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma; dgamma/dbeta are reduced in two
+// fixed-order stages (per-CTA partials, then one pass over CTAs) so results are run-to-run bit-identical.
+#include "cast_rt.cuh"
+
+namespace cast {
+
+constexpr int LN_MAXV = 32;  // values per lane -> H <= 1024
+constexpr int LN_WARPS = 8;
+constexpr int LN_ROWS_PER_CTA = 64;  // rows handled by one CTA in the backward kernel
+
+template <int NV>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, long N, int H, float eps,
+                                     float* __restrict__ y, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, float* __restrict__ xnz,
+                                     float* __restrict__ ynz) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float* xr = x + row * H;
+  float v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < H ? xr[c] : 0.f;
+    s += v[i];
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dlt = (lane + 32 * i < H) ? v[i] - mean : 0.f;
+    q += dlt * dlt;
+  }
+  q = warp_sum(q);
+  const float var = q / (float)H;
+  const float stdv = sqrtf(var + eps);  // (variance + epsilon) ** .5
+  float ys = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) {
+      const float o = gamma[c] * ((v[i] - mean) / stdv) + beta[c];
+      y[row * H + c] = o;
+      ys += o;
+    }
+  }
+  ys = warp_sum(ys);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = 1.0f / stdv;
+    if (xnz) xnz[row] = (s != 0.f) ? 1.f : 0.f;
+    if (ynz) ynz[row] = (ys != 0.f) ? 1.f : 0.f;
+  }
+}
+
+// grid = ceil(N / LN_ROWS_PER_CTA); partial[cta][0..H) = sum dy*xhat, partial[cta][H..2H) = sum dy
+template <int NV>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                     const float* __restrict__ gamma, long N, int H,
+                                     const float* __restrict__ dx_add, float* __restrict__ dx,
+                                     float* __restrict__ partial) {
+  CAST_DYN_SMEM(float, sm);  // [LN_WARPS][2H]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long row0 = (long)blockIdx.x * LN_ROWS_PER_CTA;
+  float dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = 0.f;
+  for (int r = warp; r < LN_ROWS_PER_CTA; r += LN_WARPS) {
+    const long row = row0 + r;
+    if (row >= N) break;  // warp-uniform
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float g[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      g[i] = xh[i] = 0.f;
+      if (c < H) {
+        const float d = dy[row * H + c];
+        xh[i] = (x[row * H + c] - mean) * rstd;
+        g[i] = d * gamma[c];
+        s1 += g[i];
+        s2 += g[i] * xh[i];
+        dg[i] += d * xh[i];
+        db[i] += d;
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < H) {
+        float o = rstd * (g[i] - s1 - xh[i] * s2);
+        if (dx_add) o += dx_add[row * H + c];
+        dx[row * H + c] = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) {
+      sm[warp * 2 * H + c] = dg[i];
+      sm[warp * 2 * H + H + c] = db[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < LN_WARPS; ++w) s += sm[w * 2 * H + c];
+    partial[(long)blockIdx.x * 2 * H + c] = s;
+  }
+}
+
+// out[c] = sum_{p < nparts} partial[p][c], fixed order.  Generic second stage used by LN, bias and wgrad.
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, long count,
+                                       float* __restrict__ out0, long split, float* __restrict__ out1) {
+  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c < count; c += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(long)p * count + c];
+    if (c < split)
+      out0[c] = s;
+    else
+      out1[c - split] = s;
+  }
+}
+
+int launch_reduce_partials(const float* partial, int nparts, long count, float* out0, long split, float* out1,
+                           cudaStream_t stream) {
+  long g = cdiv(count, 256);
+  if (g > 1184) g = 1184;
+  CAST_LAUNCH(reduce_partials_kernel, dim3((unsigned)g), dim3(256), 0, stream, partial, nparts, count, out0, split,
+              out1);
+  return check_launch("reduce_partials");
+}
+
+}  // namespace cast
+
+using namespace cast;
+
+extern "C" int cast_layernorm_fwd(const float* x, const float* gamma, const float* beta, long N, int H, float eps,
+                                  float* y, float* mean, float* rstd, float* xnz, float* ynz, void* stream) {
+  if (!x || !gamma || !beta || !y || H <= 0 || H > 32 * LN_MAXV || N < 0)
+    return set_error(CAST_ERR_BAD_ARG, "layernorm_fwd");
+  if (N == 0) return CAST_OK;
+#define CAST_LN_FWD(NV)                                                                                   \
+  CAST_LAUNCH(layernorm_fwd_kernel<NV>, dim3((unsigned)cdiv(N, LN_WARPS)), dim3(32 * LN_WARPS), 0,        \
+              (cudaStream_t)stream, x, gamma, beta, N, H, eps, y, mean, rstd, xnz, ynz)
+  if (H <= 64) CAST_LN_FWD(2);
+  else if (H <= 128) CAST_LN_FWD(4);
+  else if (H <= 256) CAST_LN_FWD(8);
+  else if (H <= 512) CAST_LN_FWD(16);
+  else CAST_LN_FWD(32);
+#undef CAST_LN_FWD
+  return check_launch("layernorm_fwd");
+}
+
+extern "C" size_t cast_layernorm_bwd_workspace_bytes(long N, int H) {
+  return (size_t)cdiv(N, LN_ROWS_PER_CTA) * 2 * H * sizeof(float);
+}
+
+extern "C" int cast_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                  const float* gamma, long N, int H, const float* dx_add, float* dx, float* dgamma,
+                                  float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || H <= 0 || H > 32 * LN_MAXV || N <= 0)
+    return set_error(CAST_ERR_BAD_ARG, "layernorm_bwd");
+  if (!workspace || workspace_bytes < cast_layernorm_bwd_workspace_bytes(N, H))
+    return set_error(CAST_ERR_WORKSPACE, "layernorm_bwd: workspace too small");
+  const int ncta = (int)cdiv(N, LN_ROWS_PER_CTA);
+  float* partial = static_cast<float*>(workspace);
+  const size_t smem = (size_t)LN_WARPS * 2 * H * sizeof(float);
+#define CAST_LN_BWD(NV)                                                                                         \
+  {                                                                                                             \
+    auto k = layernorm_bwd_kernel<NV>;                                                                          \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    CAST_LAUNCH(k, dim3(ncta), dim3(32 * LN_WARPS), smem, (cudaStream_t)stream, dy, x, mean, rstd, gamma, N, H, \
+                dx_add, dx, partial);                                                                           \
+  }
+  if (H <= 64) CAST_LN_BWD(2)
+  else if (H <= 128) CAST_LN_BWD(4)
+  else if (H <= 256) CAST_LN_BWD(8)
+  else if (H <= 512) CAST_LN_BWD(16)
+  else CAST_LN_BWD(32)
+#undef CAST_LN_BWD
+  int rc = check_launch("layernorm_bwd");
+  if (rc) return rc;
+  return launch_reduce_partials(partial, ncta, 2L * H, dgamma, H, dbeta, (cudaStream_t)stream);
+}

@@ -1,0 +1,211 @@
+// K7: deterministic sparse embedding gradient.  TF's autodiff of `tf.nn.embedding_lookup` sums duplicate ids
+// with unsorted_segment_sum (atomics, order not reproducible — SURVEY a9); here the (id, entry) pairs are put
+// through a stable LSD radix sort (8-bit digits, one warp per 1024-key chunk, ranks by warp match/ballot) and
+// each table row then sums its own segment in ascending entry order — no float atomics, bit-reproducible.
+// Entries enumerate up to 4 gradient sources of N positions each (item table: the input-sequence lookup x sqrt(H),
+// the positive-item lookup and the negative-item lookup, models/sasrec.py:27,89-90).
+#include "cast_rt.cuh"
+
+namespace cast {
+
+constexpr int RS_WARPS = 8;
+constexpr int RS_CHUNK = 1024;
+
+__global__ void radix_hist_kernel(const unsigned* __restrict__ keys, long n, int shift, int nchunks,
+                                  unsigned* __restrict__ hist) {
+  __shared__ unsigned cnt[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * RS_WARPS + w;
+  for (int i = lane; i < 256; i += 32) cnt[w][i] = 0u;
+  __syncwarp();
+  if (chunk < nchunks) {
+    const long beg = (long)chunk * RS_CHUNK;
+    const long end = beg + RS_CHUNK < n ? beg + RS_CHUNK : n;
+    for (long i = beg + lane; i < end; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncwarp();
+  if (chunk < nchunks)
+    for (int i = lane; i < 256; i += 32) hist[(long)i * nchunks + chunk] = cnt[w][i];
+}
+
+// exclusive scan of `total` counters in place (single CTA, fixed order)
+__global__ void radix_scan_kernel(unsigned* __restrict__ hist, long total) {
+  __shared__ unsigned sums[1024];
+  const int t = threadIdx.x;
+  const long per = (total + blockDim.x - 1) / blockDim.x;
+  const long beg = (long)t * per;
+  const long end = beg + per < total ? beg + per : total;
+  unsigned s = 0;
+  for (long i = beg; i < end; ++i) s += hist[i];
+  sums[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    unsigned run = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) {
+      const unsigned v = sums[i];
+      sums[i] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  unsigned run = sums[t];
+  for (long i = beg; i < end; ++i) {
+    const unsigned v = hist[i];
+    hist[i] = run;
+    run += v;
+  }
+}
+
+__global__ void radix_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ pay_in, long n,
+                                     int shift, int nchunks, const unsigned* __restrict__ offs,
+                                     unsigned* __restrict__ keys_out, unsigned* __restrict__ pay_out) {
+  __shared__ unsigned base[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * RS_WARPS + w;
+  if (chunk >= nchunks) return;  // warp-uniform; no block barriers below
+  for (int i = lane; i < 256; i += 32) base[w][i] = offs[(long)i * nchunks + chunk];
+  __syncwarp();
+  const long beg = (long)chunk * RS_CHUNK;
+  const long end = beg + RS_CHUNK < n ? beg + RS_CHUNK : n;
+  for (long i0 = beg; i0 < end; i0 += 32) {
+    const long i = i0 + lane;
+    const bool valid = i < end;
+    const unsigned k = valid ? keys_in[i] : 0u;
+    const unsigned dgt = valid ? ((k >> shift) & 255u) : (256u + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, dgt);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    const int leader = __ffs((int)peers) - 1;
+    unsigned b = 0u;
+    if (valid && lane == leader) {
+      b = base[w][dgt];
+      base[w][dgt] = b + (unsigned)__popc(peers);
+    }
+    b = __shfl_sync(0xffffffffu, b, leader);
+    if (valid) {
+      const unsigned p = b + (unsigned)rank;
+      keys_out[p] = k;
+      pay_out[p] = pay_in ? pay_in[i] : (unsigned)i;
+    }
+    __syncwarp();
+  }
+}
+
+struct ScatterSrc {
+  const float* rows[4];
+  const float* rowscale[4];
+  float scale[4];
+};
+
+__device__ __forceinline__ long lower_bound_u32(const unsigned* __restrict__ a, long n, unsigned key) {
+  long lo = 0, hi = n;
+  while (lo < hi) {
+    const long mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int NV>
+__global__ void segment_reduce_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay,
+                                      long total, long N, ScatterSrc src, int V, int H,
+                                      float* __restrict__ dtable) {
+  const int lane = threadIdx.x & 31;
+  const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= V) return;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  if (r > 0) {  // row 0 is the zero pad: no gradient (modules.py:154-156)
+    const long lo = lower_bound_u32(skeys, total, (unsigned)r);
+    const long hi = lower_bound_u32(skeys, total, (unsigned)r + 1u);
+    for (long e = lo; e < hi; ++e) {
+      const unsigned p = spay[e];
+      const int s = (int)(p / N);
+      const long n = (long)p - (long)s * N;
+      const float f = src.scale[s] * (src.rowscale[s] ? src.rowscale[s][n] : 1.0f);
+      const float* row = src.rows[s] + n * H;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < H) acc[i] = fmaf(row[c], f, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) dtable[r * H + c] = acc[i];
+  }
+}
+
+static inline int key_passes(int V) {
+  int bits = 1;
+  while ((1L << bits) < (long)V) ++bits;
+  return (bits + 7) / 8;
+}
+
+}  // namespace cast
+
+using namespace cast;
+
+extern "C" size_t cast_scatter_workspace_bytes(long N, int nsrc, int V) {
+  const long total = N * nsrc;
+  const long nchunks = cdiv(total, RS_CHUNK);
+  (void)V;
+  return (size_t)(4 * total + 256 * nchunks) * sizeof(unsigned) + 64;
+}
+
+extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float* const* rows,
+                                 const float* const* rowscale, const float* scale, int V, int H, float* dtable,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!keys || !rows || !scale || !dtable || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0 || H <= 0 || H > 1024)
+    return set_error(CAST_ERR_BAD_ARG, "scatter_rows");
+  const long total = N * nsrc;
+  if (total >= (1L << 32)) return set_error(CAST_ERR_UNSUPPORTED, "scatter_rows: too many entries");
+  if (!workspace || workspace_bytes < cast_scatter_workspace_bytes(N, nsrc, V))
+    return set_error(CAST_ERR_WORKSPACE, "scatter_rows: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = (int)cdiv(total, RS_CHUNK);
+  unsigned* bufK[2];
+  unsigned* bufP[2];
+  unsigned* base = static_cast<unsigned*>(workspace);
+  bufK[0] = base;
+  bufK[1] = base + total;
+  bufP[0] = base + 2 * total;
+  bufP[1] = base + 3 * total;
+  unsigned* hist = base + 4 * total;
+  const unsigned* kin = reinterpret_cast<const unsigned*>(keys);
+  const unsigned* pin = nullptr;
+  const int passes = key_passes(V);
+  const int nblk = (int)cdiv(nchunks, RS_WARPS);
+  int rc;
+  for (int p = 0; p < passes; ++p) {
+    unsigned* kout = bufK[p & 1];
+    unsigned* pout = bufP[p & 1];
+    CAST_LAUNCH(radix_hist_kernel, dim3(nblk), dim3(32 * RS_WARPS), 0, st, kin, total, 8 * p, nchunks, hist);
+    if ((rc = check_launch("radix_hist"))) return rc;
+    CAST_LAUNCH(radix_scan_kernel, dim3(1), dim3(1024), 0, st, hist, 256L * nchunks);
+    if ((rc = check_launch("radix_scan"))) return rc;
+    CAST_LAUNCH(radix_scatter_kernel, dim3(nblk), dim3(32 * RS_WARPS), 0, st, kin, pin, total, 8 * p, nchunks,
+                (const unsigned*)hist, kout, pout);
+    if ((rc = check_launch("radix_scatter"))) return rc;
+    kin = kout;
+    pin = pout;
+  }
+  ScatterSrc src;
+  for (int s = 0; s < 4; ++s) {
+    src.rows[s] = s < nsrc ? rows[s] : nullptr;
+    src.rowscale[s] = (s < nsrc && rowscale) ? rowscale[s] : nullptr;
+    src.scale[s] = s < nsrc ? scale[s] : 0.f;
+  }
+  const int wpb = 8;
+  const dim3 grid((unsigned)cdiv(V, wpb)), block(32 * wpb);
+#define CAST_SEG(NV) CAST_LAUNCH(segment_reduce_kernel<NV>, grid, block, 0, st, kin, pin, total, N, src, V, H, dtable)
+  if (H <= 64) CAST_SEG(2);
+  else if (H <= 128) CAST_SEG(4);
+  else if (H <= 256) CAST_SEG(8);
+  else if (H <= 512) CAST_SEG(16);
+  else CAST_SEG(32);
+#undef CAST_SEG
+  return check_launch("segment_reduce");
+}

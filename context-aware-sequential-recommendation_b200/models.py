@@ -1,0 +1,196 @@
+"""Model classes with the reference's interface (models/sasrec.py:5,127; models/cast_1.py:6,158 ...).
+
+    model = SASRec(usernum, itemnum, args)            # or CAST1..CAST9(usernum, itemnum, ratingnum, args)
+    auc, loss = model.train_step(u, seq, pos, neg, time_seq, hours, days)      # == sess.run([auc, loss, train_op])
+    logits, attn = model.predict(sess, u, seq, item_idx, timeseq=..., hours_seq=..., days_seq=...)
+
+`args` is the reference's argparse namespace (main.py:42-86); `sess` is accepted and ignored.  Inputs are host
+numpy int arrays as produced by the reference's sampler; results are host floats / numpy arrays.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine, MODELS
+
+
+class _Model:
+    registry_name = "sasrec"
+
+    def __init__(self, usernum, itemnum, args, *, device=None, use_graph: bool = True, _lib=None, seed=None):
+        self.usernum, self.itemnum, self.args = usernum, itemnum, args
+        self.engine = Engine(self.registry_name, usernum, itemnum, args, device=device, lib=_lib, seed=seed)
+        self.use_graph = bool(use_graph) and self.engine.device.type == "cuda"
+        self.attention_weights = None
+        self.launches_per_step = None
+        self._pinned = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _stage(self, c, seq, pos, neg, time_seq, hours, days):
+        """host -> device copies of one batch into the static input buffers (pinned staging, non-blocking)."""
+        eng = self.engine
+        B, T = c.B, eng.T
+        key = (B, "in")
+        st = self._pinned.get(key)
+        if st is None:
+            pin = eng.device.type == "cuda"
+            st = (torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin),
+                  torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin))
+            self._pinned[key] = st
+        k3, c3 = st
+        for j, a in enumerate((seq, pos, neg)):
+            if a is not None:
+                k3[j].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.int32).reshape(-1)))
+            else:
+                k3[j].zero_()
+        c.keys3.copy_(k3, non_blocking=True)
+        tables = eng.plan.tables
+        need = [("time_emb", time_seq), ("hours_emb", hours), ("days_emb", days)]
+        if any(t in tables for t, _ in need):
+            for j, (t, a) in enumerate(need):
+                if t in tables:
+                    if a is None:
+                        raise ValueError(f"model {self.registry_name} needs the {t[:-4]} sequence")
+                    c3[j].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.int32).reshape(-1)))
+            c.cids.copy_(c3, non_blocking=True)
+
+    def _capture(self, c):
+        """Capture the step as CUDA graphs: [forward+loss+backward] and [Adam]; under data parallelism the NCCL
+        all-reduce runs between the two replays (3 host launches per step instead of ~70)."""
+        eng = self.engine
+        # one eager step first (lazy CUDA init, smem attributes), with parameters / optimizer state restored after
+        saved = (eng.w.clone(), eng.m.clone(), eng.v.clone(), eng.adam_state.clone())
+        n0 = eng.lib.cast_launch_count()
+        eng.launch_train_step(c)
+        self.launches_per_step = int(eng.lib.cast_launch_count() - n0)
+        torch.cuda.synchronize(eng.device)
+        eng.w.copy_(saved[0]); eng.m.copy_(saved[1]); eng.v.copy_(saved[2]); eng.adam_state.copy_(saved[3])
+        s = torch.cuda.Stream(device=eng.device)
+        s.wait_stream(torch.cuda.current_stream(eng.device))
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g1, stream=s):
+                eng.launch_fwd_bwd(c)
+            with torch.cuda.graph(g2, stream=s):
+                eng.adam(c)
+        torch.cuda.current_stream(eng.device).wait_stream(s)
+        eng.w.copy_(saved[0]); eng.m.copy_(saved[1]); eng.v.copy_(saved[2]); eng.adam_state.copy_(saved[3])
+        c.graph = (g1, g2)
+
+    def launch(self, c):
+        """Enqueue one training step on the batch already resident in c.keys3 / c.cids."""
+        eng = self.engine
+        if self.use_graph:
+            if c.graph is None:
+                self._capture(c)
+            c.graph[0].replay()
+            if eng.grad_allreduce is not None:
+                eng.grad_allreduce(c)
+            c.graph[1].replay()
+        else:
+            eng.launch_train_step(c)
+
+    # ------------------------------------------------------------------ reference protocol
+    def train_step_async(self, u, seq, pos, neg, time_seq=None, hours=None, days=None):
+        """Enqueue one training step; returns the device tensor {sum loss terms, sum auc terms, sum istarget}."""
+        eng = self.engine
+        seq = np.asarray(seq)
+        B = seq.shape[0]
+        c = eng.ctx(B)
+        self._stage(c, seq, pos, neg, time_seq, hours, days)
+        self.launch(c)
+        return eng.sums
+
+    def train_step(self, u, seq, pos, neg, time_seq=None, hours=None, days=None):
+        """== sess.run([model.auc, model.loss, model.train_op], feed) of reference main.py:212-219."""
+        s = self.train_step_async(u, seq, pos, neg, time_seq, hours, days)
+        loss_sum, auc_sum, cnt = s[:3].tolist()
+        return auc_sum / cnt, loss_sum / cnt
+
+    def forward_eval(self, seq, time_seq=None, hours=None, days=None, want_attn=False):
+        """is_training=False forward; returns the device buffer seq_emb [B*T, H] (and fills attention weights)."""
+        eng = self.engine
+        seq = np.asarray(seq)
+        B = seq.shape[0]
+        c = eng.ctx(B)
+        self._stage(c, seq, None, None, time_seq, hours, days)
+        eng.forward(c, train=False, want_attn=want_attn)
+        return c
+
+    def predict(self, sess, u, seq, item_idx, timeseq=None, input_context_seq=None, hours_seq=None, days_seq=None):
+        """reference models/sasrec.py:127-129 / cast_3.py:191-194: returns [test_logits [B,101], attention_weights]."""
+        eng = self.engine
+        c = self.forward_eval(seq, timeseq, hours_seq, days_seq, want_attn=True)
+        B, T, H = c.B, eng.T, eng.H
+        item_idx = np.asarray(item_idx, dtype=np.int32).reshape(-1)
+        Cn = item_idx.shape[0]
+        cand = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(item_idx, (B, Cn)))).to(eng.device)
+        logits = torch.empty(B, Cn, dtype=torch.float32, device=eng.device)
+        last = c.seq_emb.view(B, T, H)[:, T - 1, :]
+        eng._call(eng.lib.cast_score_rank_cand, last.data_ptr(), T * H, eng.P["item_emb"].data_ptr(),
+                  eng.P["item_emb"].shape[0], H, B, cand.data_ptr(), Cn, logits.data_ptr(), None, None, eng._stream())
+        self.attention_weights = c.attn
+        return [logits.cpu().numpy(), c.attn.cpu().numpy()]
+
+    def score_candidates(self, seq, cand, time_seq=None, hours=None, days=None):
+        """Batched evaluation scoring: per-user candidate lists cand [U, C] (candidate 0 = target).
+        Returns (logits [U,C], count_greater [U], count_equal [U]) as numpy arrays (util.py:317-321 fused)."""
+        eng = self.engine
+        c = self.forward_eval(seq, time_seq, hours, days)
+        B, T, H = c.B, eng.T, eng.H
+        cand_t = torch.from_numpy(np.ascontiguousarray(np.asarray(cand, dtype=np.int32))).to(eng.device)
+        Cn = cand_t.shape[1]
+        logits = torch.empty(B, Cn, dtype=torch.float32, device=eng.device)
+        cgt = torch.empty(B, dtype=torch.int32, device=eng.device)
+        ceq = torch.empty(B, dtype=torch.int32, device=eng.device)
+        last = c.seq_emb.view(B, T, H)[:, T - 1, :]
+        eng._call(eng.lib.cast_score_rank_cand, last.data_ptr(), T * H, eng.P["item_emb"].data_ptr(),
+                  eng.P["item_emb"].shape[0], H, B, cand_t.data_ptr(), Cn, logits.data_ptr(), cgt.data_ptr(),
+                  ceq.data_ptr(), eng._stream())
+        return logits.cpu().numpy(), cgt.cpu().numpy(), ceq.cpu().numpy()
+
+    # parameter access by role name
+    def state_dict(self):
+        return {k: v.detach().cpu().clone() for k, v in self.engine.P.items()}
+
+    def load_state_dict(self, sd):
+        self.engine.load_parameters(sd)
+
+
+class SASRec(_Model):
+    """reference models/sasrec.py:4-129.  `static=True` => sinusoidal positions (registry name `sasrec_static`)."""
+
+    def __init__(self, usernum, itemnum, args, static=False, reuse=None, **kw):
+        self.registry_name = "sasrec_static" if static else "sasrec"
+        super().__init__(usernum, itemnum, args, **kw)
+
+
+def _make_cast(n):
+    class _CAST(_Model):
+        registry_name = f"cast_{n}"
+
+        def __init__(self, usernum, itemnum, ratingnum, args, reuse=None, **kw):
+            self.ratingnum = ratingnum
+            super().__init__(usernum, itemnum, args, **kw)
+
+    _CAST.__name__ = _CAST.__qualname__ = f"CAST{n}"
+    _CAST.__doc__ = f"reference models/cast_{n}.py (see engine.model_plan for the variant's wiring)."
+    return _CAST
+
+
+CAST1, CAST2, CAST3, CAST4, CAST5, CAST6, CAST7, CAST8, CAST9 = (_make_cast(i) for i in range(1, 10))
+
+
+def build_model(name: str, usernum, itemnum, ratingnum, args, **kw):
+    """reference main.py:121-142 dispatch."""
+    name = name.lower()
+    if name not in MODELS:
+        raise ValueError(f"provide model from {MODELS}")
+    if name == "sasrec":
+        return SASRec(usernum, itemnum, args, **kw)
+    if name == "sasrec_static":
+        return SASRec(usernum, itemnum, args, static=True, **kw)
+    return globals()["CAST" + name.split("_")[1]](usernum, itemnum, ratingnum, args, **kw)

@@ -1,0 +1,107 @@
+"""Per-kernel timing of one training step with CUDA events on the launch stream, and the roofline arithmetic for the
+dominant kernel (algorithmic FLOPs / bytes from the call's own arguments; peaks from MEASURED_PEAKS.json)."""
+from __future__ import annotations
+
+import json
+import os
+from collections import defaultdict
+
+import torch
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def _work(name, a, B, T, H, h):
+    """(flops, hbm_bytes) algorithmic work of one C-ABI call, derived from its arguments (include/cast_b200.h)."""
+    if name == "cast_gemm":
+        M, N, K = a[8], a[9], a[10]
+        return 2.0 * M * N * K, 4.0 * (M * K + K * N + M * N)
+    if name == "cast_attn_fwd":   # dense T x T: QK^T + PV  (SURVEY §8d "4TH per row")
+        return 4.0 * B * T * T * H, 4.0 * 5 * B * T * H
+    if name == "cast_attn_bwd":   # dP, dQ, dK, dV = 2x forward (algorithmic; recomputation of S not counted)
+        return 8.0 * B * T * T * H, 4.0 * 8 * B * T * H
+    if name in ("cast_layernorm_fwd",):
+        return 8.0 * a[3] * a[4], 4.0 * 2 * a[3] * a[4]
+    if name in ("cast_layernorm_bwd",):
+        return 12.0 * a[5] * a[6], 4.0 * 3 * a[5] * a[6]
+    if name == "cast_embed_fwd":
+        return 3.0 * a[4] * a[3], 4.0 * (2 * a[4] * a[3] + a[4])
+    if name == "cast_mask_dropout":
+        return 2.0 * a[6] * a[7], 4.0 * 3 * a[6] * a[7]
+    if name == "cast_adam_tf_step":
+        return 12.0 * a[4], 28.0 * a[4]
+    if name == "cast_logits_loss":
+        return 6.0 * a[4] * a[3], 4.0 * 4 * a[4] * a[3]
+    if name == "cast_scatter_rows":
+        n, nsrc, Hh, V = a[2], a[1], a[7], a[6]
+        return 2.0 * n * nsrc * Hh, 4.0 * (n * nsrc * Hh + V * Hh) + 16.0 * n * nsrc
+    if name == "cast_colsum":
+        return 1.0 * a[1] * a[2], 4.0 * a[1] * a[2]
+    return 0.0, 0.0
+
+
+def profile_step(model, c, steps=5):
+    """Runs `steps` eager training steps with every C-ABI call bracketed by CUDA events; returns a list of
+    {name, calls_per_step, ms_per_step, share, tflops, gbs} sorted by time."""
+    eng = model.engine
+    B, T, H, h = c.B, eng.T, eng.H, eng.h
+    eng.launch_train_step(c)  # warm
+    torch.cuda.synchronize(eng.device)
+    eng.timing = []
+    for _ in range(steps):
+        eng.launch_train_step(c)
+    torch.cuda.synchronize(eng.device)
+    rec, eng.timing = eng.timing, None
+    agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    for name, a, e0, e1 in rec:
+        ms = e0.elapsed_time(e1)
+        fl, by = _work(name, a, B, T, H, h)
+        r = agg[name]
+        r[0] += 1
+        r[1] += ms
+        r[2] += fl
+        r[3] += by
+    total = sum(r[1] for r in agg.values()) or 1.0
+    out = []
+    for name, (n, ms, fl, by) in agg.items():
+        out.append({"name": name, "calls_per_step": n / steps, "ms_per_step": ms / steps, "share": ms / total,
+                    "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0,
+                    "gbs": by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
+                    "flops_per_step": fl / steps, "bytes_per_step": by / steps})
+    out.sort(key=lambda r: -r["ms_per_step"])
+    return out
+
+
+def load_peaks(root):
+    p = os.path.join(root, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["source"] = "fallback"
+    return d
+
+
+COMPUTE_BOUND = ("cast_attn_fwd", "cast_attn_bwd", "cast_gemm")
+
+
+def roofline_of_dominant(kernels, B, T, H, args, root):
+    if not kernels:
+        return None
+    top = kernels[0]
+    pk = load_peaks(root)
+    if top["name"] in COMPUTE_BOUND:
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        fp32_peak = 2 * 128 * 148 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        return {"kernel": top["name"], "bound": "tensor", "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s",
+                "frac": top["tflops"] / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "share_of_step": top["share"], "ms_per_step": top["ms_per_step"],
+                "algorithmic_flops_per_step": top["flops_per_step"],
+                "pipe_used": "fp32 FFMA (fp32 parity 1e-4; tensor cores reserved for catalog scoring)",
+                "fp32_pipe_peak_tflops": fp32_peak, "frac_of_fp32_pipe": top["tflops"] / fp32_peak}
+    peak = pk["hbm_gbs"]
+    return {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": top["gbs"] / peak, "traffic": None, "peak_source": pk["source"], "share_of_step": top["share"],
+            "ms_per_step": top["ms_per_step"], "algorithmic_bytes_per_step": top["bytes_per_step"]}

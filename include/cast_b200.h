@@ -1,0 +1,154 @@
+/* cast_b200.h — C ABI of the B200-native SASRec / CAST training-and-evaluation hot path.
+ *
+ * The reference (Spijkervet/Context-Aware-Sequential-Recommendation) has no FFI layer: its arithmetic lives in
+ * TensorFlow-1.15 ops called from modules.py / models/*.py.  Each entry point below replaces the TF op group
+ * cited next to it (paths relative to the reference root).  The Python model classes of this repo
+ * (`SASRec`, `CAST1..9`, same constructor / predict protocol as models/sasrec.py:5,127) are the only callers.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 / int32, row-major, contiguous unless an ld/stride is given);
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, never synchronise, allocate or free;
+ *   - return value: CAST_OK (0) or a negative CAST_ERR_*; `cast_last_error_string()` explains the last failure;
+ *   - scratch memory is caller-provided: `cast_<op>_workspace_bytes(...)` gives the size;
+ *   - N = B*T rows ("positions"); H = hidden_units; h = num_heads; V = rows of an embedding table;
+ *   - dropout is counter based: keep(site, idx) = hash(seed, *step, site, idx) >= rate*2^32, where idx is the
+ *     flat element index in the reference's tensor layout, so backward kernels and tests regenerate identical
+ *     masks (`cast_dropout_keep` materialises one).  `step` is a device pointer (may be null => 0) so a captured
+ *     CUDA graph stays valid across steps.
+ *   - all reductions run in a fixed order: results are bit-reproducible run to run.
+ */
+#ifndef CAST_B200_H_
+#define CAST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAST_OK 0
+#define CAST_ERR_BAD_ARG (-1)
+#define CAST_ERR_UNSUPPORTED (-2)
+#define CAST_ERR_WORKSPACE (-3)
+#define CAST_ERR_CUDA (-4)
+
+#define CAST_ABI_VERSION 1
+
+int cast_version(void);
+const char* cast_last_error_string(void);
+/* number of kernels this library has enqueued so far in this process (each launch site counts once). */
+unsigned long long cast_launch_count(void);
+
+/* modules.py:148-160 `embedding` (zero-padded row 0, x sqrt(H)) + position row add (sasrec.py:39-56) + context
+ * add (cast_1.py:87) + tf.layers.dropout (sasrec.py:59) + `*= mask` (sasrec.py:62).
+ * out[n,:] = ((ids[n] ? table[ids[n],:]*scale : 0) + pos[n % T,:] + add[n,:]) * dropout * (mask_ids[n] != 0)
+ * pos / add / mask_ids may be null; drop_rate 0 disables dropout. */
+int cast_embed_fwd(const int* ids, const float* table, int V, int H, long N, int T, float scale, const float* pos,
+                   const float* add, float drop_rate, unsigned long long seed, const unsigned long long* step,
+                   int site, const int* mask_ids, float* out, void* stream);
+
+/* element-wise backward of `x -> dropout(x) * mask`: out_masked = in*mask, out_masked_dropped = in*mask*dropout
+ * (either output may be null).  Used for sasrec.py:59-62 and modules.py:307-311 backward. */
+int cast_mask_dropout(const float* in, const int* mask_ids, float drop_rate, unsigned long long seed,
+                      const unsigned long long* step, int site, long N, int H, float* out_masked,
+                      float* out_masked_dropped, void* stream);
+
+/* tf.concat(axis=2) + tf.layers.dropout of the CAST merges (cast_2.py:89-92, cast_4.py:114-124):
+ * cat[n, s*H+c] = srcs[s][n,c] * dropA(first width_a sources, index in the [N, width_a*H] tensor)
+ *                              * dropB(all k sources, index in the [N, k*H] tensor).  k <= 4. srcs is a HOST array. */
+int cast_concat_dropout_fwd(const float* const* srcs, int k, int width_a, long N, int H, float rate_a, int site_a,
+                            float rate_b, int site_b, unsigned long long seed, const unsigned long long* step,
+                            float* cat, void* stream);
+int cast_concat_dropout_bwd(const float* dcat, int k, int width_a, long N, int H, float rate_a, int site_a,
+                            float rate_b, int site_b, unsigned long long seed, const unsigned long long* step,
+                            float* const* dsts, void* stream);
+
+/* keep[i] = 1 if element i of dropout site `site` is kept (test / oracle hand-off helper). */
+int cast_dropout_keep(float drop_rate, unsigned long long seed, const unsigned long long* step, int site, long n,
+                      unsigned char* keep, void* stream);
+
+int cast_add(const float* a, const float* b, float* out, long n, void* stream);
+/* out = dy * (act > 0 ? scale : 0): backward of tf.nn.relu in `mlp` (modules.py:333-334). */
+int cast_relu_bwd(const float* dy, const float* act, float scale, float* out, long n, void* stream);
+
+/* modules.py:53-80 `normalize`: y = gamma*(x-mean)/sqrt(var_biased+eps)+beta.  Optionally saves mean / rstd and the
+ * flags xnz[n] = (sum_H x[n,:] != 0), ynz[n] = (sum_H y[n,:] != 0) that multihead_attention turns into its key
+ * mask (modules.py:222) and query mask (modules.py:248). */
+int cast_layernorm_fwd(const float* x, const float* gamma, const float* beta, long N, int H, float eps, float* y,
+                       float* mean, float* rstd, float* xnz, float* ynz, void* stream);
+size_t cast_layernorm_bwd_workspace_bytes(long N, int H);
+/* dx = LN'(dy) (+ dx_add if non-null); dgamma, dbeta overwritten (deterministic two-stage reduction). */
+int cast_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       long N, int H, const float* dx_add, float* dx, float* dgamma, float* dbeta, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* tf.layers.dense / conv1d(k=1) (modules.py:203-205, :298-306, :333-334) and their gradients as one strided GEMM:
+ *   C[i,j] = epi( sum_k A[i*sam + k*sak] * B[k*sbk + j*sbn] ),  i<M, j<N, k<K
+ *   epi(c) = (((relu?max(c+bias[j],0):c+bias[j]) * dropout(i*N+j)) * (act[i,j]>0 ? act_scale : 0) + resid[i,j])
+ *            * (row_ids[i] != 0)                      — every term optional (null / 0).
+ * splits > 1: reduction dimension split across CTAs, partials summed in fixed order (no epilogue, ldc == N). */
+size_t cast_gemm_workspace_bytes(long M, int N, int splits);
+int cast_gemm(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc, long M,
+              int N, long K, const float* bias, int relu, float drop_rate, unsigned long long seed,
+              const unsigned long long* step, int site, const float* act, long ld_act, float act_scale,
+              const float* resid, long ldr, const int* row_ids, int splits, void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/* out[c] = sum_r X[r*ld + c] (bias gradients; learned-position gradient = sum over the batch), deterministic. */
+size_t cast_colsum_workspace_bytes(long rows, long cols);
+int cast_colsum(const float* X, long rows, long cols, long ld, float* out, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* modules.py:208-269: scaled QK^T, key mask, causal mask, softmax, query mask, dropout, PV, head merge, + queries.
+ * Q,K,V: [B*T, ld]; queries = LN(x) [B*T,H] (residual); kmask/qmask: [B*T] 0/1 floats from cast_layernorm_fwd.
+ * out [B*T,H]; attn_weights (optional) [h*B,T,T] = reference `attention_weights` (post dropout, modules.py:259);
+ * row_max/row_linv (optional, needed for backward) [B,h,T]. */
+int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv, const float* queries,
+                  const float* kmask, const float* qmask, int B, int T, int H, int h, float drop_rate,
+                  unsigned long long seed, const unsigned long long* step, int site, float* out, float* attn_weights,
+                  float* row_max, float* row_linv, void* stream);
+/* Gradient of the attention output (without the residual branch) w.r.t. Q, K, V.  rowD: scratch [B,h,T]. */
+int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv, const float* dO,
+                  const float* kmask, const float* qmask, const float* row_max, const float* row_linv, float* rowD,
+                  int B, int T, int H, int h, float drop_rate, unsigned long long seed, const unsigned long long* step,
+                  int site, float* dQ, long lddq, float* dK, long lddk, float* dV, long lddv, void* stream);
+
+/* models/sasrec.py:87-115: pos/neg row gathers from the zero-padded table, row dots, literal BCE
+ * (-log(sigmoid+1e-24)), istarget mask, AUC.  sums[0..2] = {sum loss terms, sum auc terms, sum istarget}
+ * (un-normalised: the caller divides, or all-reduces first under data parallelism, sasrec.py:105-108).
+ * If dseq != null also writes d(sum loss)/dseq_emb [N,H] and the per-position logit gradients gpos/gneg [N]. */
+size_t cast_logits_loss_workspace_bytes(long N);
+int cast_logits_loss(const float* seq_emb, const float* table, int V, int H, long N, const int* pos, const int* neg,
+                     float* pos_logits, float* neg_logits, float* sums, float* dseq, float* gpos, float* gneg,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Deterministic sparse embedding gradient (TF autodiff of the gathers: unsorted_segment_sum):
+ * dtable[r,:] = sum over entries e (in ascending e) with keys[e] == r of rows_s[n,:] * rowscale_s[n] * scale_s,
+ * where e = s*N + n enumerates `nsrc` sources of N positions each; row 0 (zero pad) gets 0.  Implemented as a
+ * stable LSD radix sort of (key, e) followed by a fixed-order segmented reduction: no float atomics.
+ * rows/rowscale/scale are HOST arrays of nsrc device pointers / floats (rowscale[s] may be null). */
+size_t cast_scatter_workspace_bytes(long N, int nsrc, int V);
+int cast_scatter_rows(const int* keys /* [nsrc*N] */, int nsrc, long N, const float* const* rows,
+                      const float* const* rowscale, const float* scale, int V, int H, float* dtable,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* tf.train.AdamOptimizer(lr, beta1=.9, beta2=.98, eps=1e-8) (sasrec.py:120-121), dense on every element:
+ *   g = grad/(*gdenom) + l2*w (gdenom: device scalar, e.g. the global sum(istarget); null => 1; l2 only for
+ *   elements in [l2_lo, l2_hi));
+ *   lr_t = lr*sqrt(1-b2p)/(1-b1p); m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g; w -= lr_t*m/(sqrt(v)+eps)
+ * state = device {float b1p, float b2p, uint64 step}; after the update b1p*=b1, b2p*=b2, step+=1 (TF order). */
+int cast_adam_init_state(void* state /* 16 bytes */, float beta1, float beta2, void* stream);
+int cast_adam_tf_step(float* w, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
+                      float eps, const float* gdenom, float l2, long l2_lo, long l2_hi, void* state, void* stream);
+
+/* sasrec.py:93-97 + util.py:318-321: logits[u,c] = seq_last[u,:] . table0[cand[u,c],:] (sequential-k, unfused
+ * multiply/add so the order is reproducible), and for candidate 0 the pair (count_greater, count_equal_excl_self)
+ * from which the reference rank follows (SURVEY A-12). */
+int cast_score_rank_cand(const float* seq_last, long ld, const float* table, int V, int H, long U, const int* cand,
+                         int C, float* logits, int* count_greater, int* count_equal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAST_B200_H_ */

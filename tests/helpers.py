@@ -1,0 +1,78 @@
+"""Shared test helpers: backend selection (real CUDA library on a GPU box; host-emulated kernels for CPU logic
+tests), oracle hand-off of dropout masks, comparison utilities."""
+import ctypes
+import os
+import subprocess
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cast_b200  # noqa: E402
+from cast_b200 import _lib as castlib  # noqa: E402
+from oracle import cast_oracle as O  # noqa: E402
+
+EMU_SO = os.path.join(ROOT, "tests", "emu", "_build", "libcast_emu.so")
+_emu = None
+
+
+def emu_lib():
+    """TEST INFRASTRUCTURE: the kernel sources compiled for the host (tests/emu).  Never used by the package."""
+    global _emu
+    if _emu is None:
+        subprocess.check_call(["bash", os.path.join(ROOT, "tests", "emu", "build_emu.sh")], stdout=subprocess.DEVNULL)
+        _emu = castlib.bind(ctypes.CDLL(EMU_SO))
+    return _emu
+
+
+def backend(kind):
+    """kind = 'gpu' -> (cuda lib, cuda device); kind = 'emu' -> (emulated lib, cpu)."""
+    if kind == "gpu":
+        return castlib.load_library(), torch.device("cuda", 0)
+    return emu_lib(), torch.device("cpu")
+
+
+def make_args(**kw):
+    d = dict(hidden_units=50, maxlen=50, num_heads=1, num_blocks=2, num_context_blocks=2, max_bins=200, l2_emb=0.0,
+             lr=1e-3, dropout_rate=0.0, seed=42, bin_in_hours=48, log_scale=False)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def golden_batch(tag="lin", idx=0, B=None, T=None):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_sampler.npz"))
+    out = {k: g[f"{tag}_{idx}_{k}"] for k in ("u", "seq", "pos", "neg", "timeseq", "hours", "days")}
+    if B is not None:
+        out = {k: v[:B] for k, v in out.items()}
+    if T is not None:
+        out = {k: (v[:, -T:] if v.ndim == 2 else v) for k, v in out.items()}
+    return out
+
+
+def oracle_batch(b):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    return {"input_seq": t(b["seq"]), "pos": t(b["pos"]), "neg": t(b["neg"]), "time_seq": t(b["timeseq"]),
+            "hours": t(b["hours"]), "days": t(b["days"])}
+
+
+def dropout_hook(eng, rate):
+    """Oracle `drop` callback that asks the library under test for the keep-mask of each site (same seed / step)."""
+    def drop(site, x):
+        if rate <= 0:
+            return x
+        n = x.numel()
+        keep = torch.empty(n, dtype=torch.uint8, device=eng.device)
+        rc = eng.lib.cast_dropout_keep(rate, eng.seed, eng.step_ptr, site, n, keep.data_ptr(), eng._stream())
+        assert rc == 0
+        k = keep.cpu().to(x.dtype).reshape(x.shape)
+        return x * k / (1.0 - rate)
+    return drop
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

@@ -1,0 +1,136 @@
+"""End-to-end parity of one training step and of evaluation scoring: kernels (through the C ABI and the model
+classes) vs the CPU oracle on batches produced by the REFERENCE's own sampler (tests/golden/ref_sampler.npz).
+
+Tolerance (BASELINE.json north_star): fp32 within 1e-4 relative for logits / loss; gradients are compared per
+tensor relative to that tensor's max magnitude.  The key-projection bias gradient is analytically zero (a constant
+added to every key shifts all scores of a softmax row equally) so it is compared absolutely against the scale of
+the query-bias gradient.  Runs on the GPU (`-m gpu`, real library) and, at tiny shapes, on the host-emulated
+kernel sources (`emu`, CPU, test infrastructure only).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, backend, dropout_hook, golden_batch, make_args, oracle_batch, rel_err
+from cast_b200.engine import Engine
+
+TOL = 1e-4
+
+
+def run_step(kind, model, B, T, H, heads, rate, seed=7, randomize=True, blocks=2, tag="lin", l2=0.0):
+    lib, dev = backend(kind)
+    args = make_args(hidden_units=H, maxlen=T, num_heads=heads, num_blocks=blocks, dropout_rate=rate, l2_emb=l2)
+    gb = golden_batch(tag=tag, B=B, T=T)
+    eng = Engine(model, 80, 300, args, device=dev, lib=lib, seed=seed)
+    p = {k: v.detach().cpu().clone() for k, v in eng.P.items()}
+    if randomize:  # non-trivial beta/gamma/biases so that query masks, residual LN paths etc. are exercised
+        g = torch.Generator().manual_seed(3)
+        for k in p:
+            if k.endswith(".b") or k.endswith("beta"):
+                p[k] = torch.randn(p[k].shape, generator=g) * 0.1
+            if k.endswith("gamma"):
+                p[k] = 1 + torch.randn(p[k].shape, generator=g) * 0.1
+        eng.load_parameters(p)
+    c = eng.ctx(B)
+    c.keys3.copy_(torch.from_numpy(np.stack([gb[k].reshape(-1) for k in ("seq", "pos", "neg")])))
+    c.cids.copy_(torch.from_numpy(np.stack([gb[k].reshape(-1) for k in ("timeseq", "hours", "days")])))
+    opt = O.TFAdam(p, lr=args.lr)
+    auc_o, loss_o, grads_o = O.train_step(model, p, opt, args, oracle_batch(gb), dropout_hook(eng, rate))
+    eng.launch_train_step(c)
+    s = eng.sums[:3].tolist()
+    return eng, p, grads_o, (auc_o, loss_o), s
+
+
+def check_step(eng, p, grads_o, ref, s, tol=TOL):
+    auc_o, loss_o = ref
+    loss, auc, cnt = s[0] / s[2], s[1] / s[2], s[2]
+    assert abs(loss - loss_o) <= tol * abs(loss_o)
+    assert abs(auc - auc_o) <= 1e-6
+    for k in eng.G:
+        go = grads_o[k].numpy().astype(np.float64) * cnt  # engine gradients are un-normalised
+        gk = eng.G[k].cpu().numpy()
+        if k.endswith("k.b"):
+            scale = np.abs(grads_o[k.replace("k.b", "q.b")].numpy()).max() * cnt
+            assert np.abs(gk - go).max() <= 1e-4 * max(scale, 1e-20), k
+        else:
+            assert rel_err(gk, go) <= tol, (k, rel_err(gk, go))
+    assert eng.state_step() == 1
+
+
+EMU_CASES = [("sasrec", 3, 12, 20, 2, 0.25), ("cast_1", 2, 10, 12, 1, 0.3), ("cast_4", 2, 10, 12, 2, 0.2),
+             ("cast_6", 2, 8, 12, 1, 0.2), ("cast_9", 2, 8, 8, 2, 0.1)]
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("model,B,T,H,heads,rate", EMU_CASES)
+def test_train_step_emulated(model, B, T, H, heads, rate):
+    check_step(*run_step("emu", model, B, T, H, heads, rate))
+
+
+GPU_CASES = [(m, 16, 50, 50, 1, 0.2) for m in O.MODELS] + [
+    ("sasrec", 16, 50, 50, 1, 0.0), ("sasrec", 8, 37, 50, 2, 0.5), ("cast_1", 16, 50, 50, 2, 0.2),
+    ("sasrec", 4, 50, 128, 4, 0.2), ("sasrec", 4, 50, 256, 1, 0.2), ("cast_4", 8, 50, 64, 2, 0.3),
+    ("sasrec", 8, 50, 100, 1, 0.1)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,B,T,H,heads,rate", GPU_CASES)
+def test_train_step_gpu(model, B, T, H, heads, rate):
+    check_step(*run_step("gpu", model, B, T, H, heads, rate))
+
+
+@pytest.mark.gpu
+def test_train_step_gpu_logscale_batch():
+    check_step(*run_step("gpu", "cast_3", 16, 50, 50, 1, 0.2, tag="log"))
+
+
+@pytest.mark.gpu
+def test_run_to_run_bitwise_determinism():
+    """Same seed, same batch, two engines: every gradient bit-identical (no float atomics anywhere)."""
+    a = run_step("gpu", "cast_1", 16, 50, 50, 2, 0.2)[0]
+    b = run_step("gpu", "cast_1", 16, 50, 50, 2, 0.2)[0]
+    assert torch.equal(a.gbuf, b.gbuf)
+    assert torch.equal(a.w, b.w)
+
+
+@pytest.mark.gpu
+def test_multi_step_training_tracks_oracle():
+    """5 consecutive steps on 3 different reference-sampler batches: loss trajectory within 1e-4 relative."""
+    import cast_b200
+    args = make_args(hidden_units=50, maxlen=50, num_heads=1, num_blocks=2, dropout_rate=0.2)
+    model = cast_b200.SASRec(80, 300, args, use_graph=True)
+    eng = model.engine
+    p = {k: v.detach().cpu().clone() for k, v in eng.P.items()}
+    opt = O.TFAdam(p, lr=args.lr)
+    for step in range(5):
+        gb = golden_batch(idx=step % 3)
+        auc_o, loss_o, _ = O.train_step("sasrec", p, opt, args, oracle_batch(gb), dropout_hook(eng, 0.2))
+        auc, loss = model.train_step(gb["u"], gb["seq"], gb["pos"], gb["neg"])
+        assert abs(loss - loss_o) <= 2e-4 * abs(loss_o), (step, loss, loss_o)
+    assert eng.state_step() == 5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["sasrec", "cast_1", "cast_7"])
+def test_predict_matches_oracle(model):
+    """models/sasrec.py:127-129 protocol: test_logits [B,101] within 1e-4, attention_weights [h*B,T,T] within 1e-5."""
+    import cast_b200
+    args = make_args(hidden_units=50, maxlen=50, num_heads=2, num_blocks=2, dropout_rate=0.2)
+    m = cast_b200.build_model(model, 80, 300, 5, args)
+    eng = m.engine
+    p = {k: v.detach().cpu().clone() for k, v in eng.P.items()}
+    g = torch.Generator().manual_seed(5)
+    for k in p:  # trained-looking LN betas: padded query rows become live (SURVEY A-8)
+        if k.endswith("beta"):
+            p[k] = torch.randn(p[k].shape, generator=g) * 0.2
+    eng.load_parameters(p)
+    gb = golden_batch(B=4)
+    item_idx = np.concatenate([[gb["pos"][0, -1]], np.random.RandomState(1).randint(1, 301, 100)]).astype(np.int32)
+    logits, attn = m.predict(None, gb["u"], gb["seq"], item_idx, timeseq=gb["timeseq"], hours_seq=gb["hours"],
+                             days_seq=gb["days"])
+    seq, table, attn_o = O.forward(model, p, args, oracle_batch(gb))
+    lo = O.test_logits(seq, table, item_idx).detach().numpy()
+    assert logits.shape == (4, 101)
+    assert rel_err(logits, lo) <= TOL
+    assert attn.shape == tuple(attn_o.shape)
+    assert np.abs(attn - attn_o.detach().numpy()).max() <= 1e-5
