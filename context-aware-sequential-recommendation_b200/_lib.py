@@ -30,6 +30,12 @@ SIGNATURES = {
     "cast_layernorm_bwd": (I, [P, P, P, P, P, L, I, P, P, P, P, P, SZ, P]),
     "cast_gemm_workspace_bytes": (SZ, [L, I, I]),
     "cast_gemm": (I, [P, L, L, P, L, L, P, L, L, I, L, P, I, F, U64, P, I, P, L, F, P, L, P, I, P, SZ, P]),
+    "cast_fused_supported": (I, [I]),
+    "cast_ln_qkv_fwd": (I, [P, P, P, P, P, P, P, P, P, L, I, F, P, P, P, P, P, P, P, P, P]),
+    "cast_ln_ffn_fwd": (I, [P, P, P, P, P, P, P, P, F, U64, P, I, I, L, I, F, P, P, P, P, P, P]),
+    "cast_block_bwd_workspace_bytes": (SZ, [L, I]),
+    "cast_ffn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, F, U64, P, I, L, I, P, P, P, SZ, P]),
+    "cast_qkv_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, L, I, P, P, P, SZ, P]),
     "cast_colsum_workspace_bytes": (SZ, [L, L]),
     "cast_colsum": (I, [P, L, L, L, P, P, SZ, P]),
     "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P]),
@@ -37,7 +43,8 @@ SIGNATURES = {
     "cast_logits_loss_workspace_bytes": (SZ, [L]),
     "cast_logits_loss": (I, [P, P, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),
     "cast_scatter_workspace_bytes": (SZ, [L, I, I]),
-    "cast_scatter_rows": (I, [P, I, L, P, P, P, I, I, P, P, SZ, P]),
+    "cast_scatter_partial_bytes": (SZ, [L, I, I]),
+    "cast_scatter_rows": (I, [P, I, L, P, P, P, I, I, P, P, SZ, P, SZ, P]),
     "cast_adam_init_state": (I, [P, F, F, P]),
     "cast_adam_tf_step": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, P]),
     "cast_score_rank_cand": (I, [P, L, P, I, I, L, P, I, P, P, P, P]),

@@ -16,6 +16,7 @@
 // warp per row.  Backward is two deterministic kernels (no float atomics): dQ per query tile, dK/dV per key tile,
 // both recomputing P from the saved row max / 1/rowsum and D_i = sum_j P_ij dP_ij.
 #include "cast_rt.cuh"
+#include "tile_ops.cuh"
 
 namespace cast {
 
@@ -25,7 +26,7 @@ struct AttnDims {
   int B, T, H, h, d;  // d = H / h
   int dpad, DS;       // d rounded to 4; smem row stride
   int Tp4, PS;        // T rounded to 4; score row stride
-  float sqrt_d;
+  float inv_sqrt_d;
 };
 
 static AttnDims make_dims(int B, int T, int H, int h) {
@@ -35,66 +36,19 @@ static AttnDims make_dims(int B, int T, int H, int h) {
   a.DS = ((a.dpad / 4) % 2 == 0) ? a.dpad + 4 : a.dpad;
   a.Tp4 = (T + 3) & ~3;
   a.PS = a.Tp4 + 4;
-  a.sqrt_d = sqrtf((float)a.d);  // K_.get_shape()[-1] ** 0.5
+  a.inv_sqrt_d = 1.0f / sqrtf((float)a.d);  // outputs / (K_.get_shape()[-1] ** 0.5), as a multiply
   return a;
 }
 
 // dst[r][c] (stride DS) = src[(row0 + r) * ld + c] for r < nrows, c < dpad; zero outside (row >= rows_valid, c >= d)
 __device__ __forceinline__ void load_tile(float* __restrict__ dst, int DS, int dpad, const float* __restrict__ src,
                                           long ld, int row0, int nrows, int rows_valid, int d) {
-  const int total = nrows * dpad;
-  for (int idx = threadIdx.x; idx < total; idx += ATT_THREADS) {
-    const int r = idx / dpad, c = idx - r * dpad;
+  const int lane = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r < nrows; r += ATT_THREADS / 32) {
     const int row = row0 + r;
-    dst[r * DS + c] = (row < rows_valid && c < d) ? src[(long)row * ld + c] : 0.f;
-  }
-}
-
-// acc[ii][jj] = sum_c As[(ty*RI+ii)][c] * Bs[(tx+16*jj)][c]
-template <int RI, int RJ>
-__device__ __forceinline__ void dot_tile(const float* __restrict__ As, const float* __restrict__ Bs, int DS, int dpad,
-                                         float (&acc)[RI][RJ], int ty, int tx) {
-#pragma unroll
-  for (int ii = 0; ii < RI; ++ii)
-#pragma unroll
-    for (int jj = 0; jj < RJ; ++jj) acc[ii][jj] = 0.f;
-  for (int c = 0; c < dpad; c += 4) {
-    float4 a[RI], b[RJ];
-#pragma unroll
-    for (int ii = 0; ii < RI; ++ii) a[ii] = *reinterpret_cast<const float4*>(&As[(ty * RI + ii) * DS + c]);
-#pragma unroll
-    for (int jj = 0; jj < RJ; ++jj) b[jj] = *reinterpret_cast<const float4*>(&Bs[(tx + 16 * jj) * DS + c]);
-#pragma unroll
-    for (int ii = 0; ii < RI; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < RJ; ++jj) {
-        float s = acc[ii][jj];
-        s = fmaf(a[ii].x, b[jj].x, s);
-        s = fmaf(a[ii].y, b[jj].y, s);
-        s = fmaf(a[ii].z, b[jj].z, s);
-        s = fmaf(a[ii].w, b[jj].w, s);
-        acc[ii][jj] = s;
-      }
-  }
-}
-
-// acc[ii][cc] += sum_{j<nj} Ps[(ty*RI+ii)*PS + j] * Vs[j*DS + col + cc]      (nj multiple of 4, col multiple of 4)
-template <int RI>
-__device__ __forceinline__ void pv_tile(const float* __restrict__ Ps, int PS, const float* __restrict__ Vs, int DS,
-                                        int nj, int col, float (&acc)[RI][4], int ty) {
-  for (int j = 0; j < nj; j += 4) {
-    float4 p[RI], v[4];
-#pragma unroll
-    for (int ii = 0; ii < RI; ++ii) p[ii] = *reinterpret_cast<const float4*>(&Ps[(ty * RI + ii) * PS + j]);
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) v[jj] = *reinterpret_cast<const float4*>(&Vs[(j + jj) * DS + col]);
-#pragma unroll
-    for (int ii = 0; ii < RI; ++ii) {
-      acc[ii][0] = fmaf(p[ii].w, v[3].x, fmaf(p[ii].z, v[2].x, fmaf(p[ii].y, v[1].x, fmaf(p[ii].x, v[0].x, acc[ii][0]))));
-      acc[ii][1] = fmaf(p[ii].w, v[3].y, fmaf(p[ii].z, v[2].y, fmaf(p[ii].y, v[1].y, fmaf(p[ii].x, v[0].y, acc[ii][1]))));
-      acc[ii][2] = fmaf(p[ii].w, v[3].z, fmaf(p[ii].z, v[2].z, fmaf(p[ii].y, v[1].z, fmaf(p[ii].x, v[0].z, acc[ii][2]))));
-      acc[ii][3] = fmaf(p[ii].w, v[3].w, fmaf(p[ii].z, v[2].w, fmaf(p[ii].y, v[1].w, fmaf(p[ii].x, v[0].w, acc[ii][3]))));
-    }
+    const bool ok = row < rows_valid;
+    const float* s = src + (long)row * ld;
+    for (int c = lane; c < dpad; c += 32) dst[r * DS + c] = (ok && c < d) ? s[c] : 0.f;
   }
 }
 
@@ -172,31 +126,32 @@ attn_fwd_kernel(AttnFwdArgs a, AttnDims dm) {
     float mx = -INFINITY;
     for (int j = lane; j < kend; j += 32) {
       const bool keep = (a.kmask[rowbase + j] != 0.f) && (j <= i);
-      const float s = keep ? Sr[j] / dm.sqrt_d : CAST_NEG_FILL;
+      const float s = keep ? Sr[j] * dm.inv_sqrt_d : CAST_NEG_FILL;
       Sr[j] = s;
       mx = fmaxf(mx, s);
     }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < kend; j += 32) {
-      const float e = expf(Sr[j] - mx);
+      const float e = __expf(Sr[j] - mx);
       Sr[j] = e;
       sum += e;
     }
     sum = warp_sum(sum);
-    const float qm = a.qmask[rowbase + i];
+    const float linv = 1.0f / sum;
+    const float qm = a.qmask[rowbase + i] * linv;
     const unsigned long long ibase = ((unsigned long long)((long)hh * dm.B + b) * T + i) * T;
     float* arow = a.attn ? a.attn + ibase : nullptr;
     for (int j = lane; j < dm.Tp4; j += 32) {
       float p = 0.f;
-      if (j < kend) p = (Sr[j] / sum) * qm * drop_mul(dr, ibase + j);
+      if (j < kend) p = Sr[j] * qm * drop_mul(dr, ibase + j);
       Sr[j] = p;
       if (arow && j < T) arow[j] = p;
     }
     if (lane == 0) {
       const long si = ((long)b * dm.h + hh) * T + i;
       if (a.row_max) a.row_max[si] = mx;
-      if (a.row_linv) a.row_linv[si] = 1.0f / sum;
+      if (a.row_linv) a.row_linv[si] = linv;
     }
   }
   // ---- O = P V
@@ -316,8 +271,8 @@ attn_bwd_dq_kernel(AttnBwdArgs a, AttnDims dm) {
     float D = 0.f;
     for (int j = lane; j < kend; j += 32) {
       const bool keep = (a.kmask[rowbase + j] != 0.f) && (j <= i);
-      const float s = keep ? Pr[j] / dm.sqrt_d : CAST_NEG_FILL;
-      const float p = expf(s - mx) * linv;
+      const float s = keep ? Pr[j] * dm.inv_sqrt_d : CAST_NEG_FILL;
+      const float p = __expf(s - mx) * linv;
       const float dp = dPr[j] * qm * drop_mul(dr, ibase + j);
       Pr[j] = p;
       dPr[j] = dp;
@@ -328,7 +283,7 @@ attn_bwd_dq_kernel(AttnBwdArgs a, AttnDims dm) {
       float ds = 0.f;
       if (j < kend) {
         const bool keep = (a.kmask[rowbase + j] != 0.f) && (j <= i);
-        if (keep) ds = Pr[j] * (dPr[j] - D) / dm.sqrt_d;
+        if (keep) ds = Pr[j] * (dPr[j] - D) * dm.inv_sqrt_d;
       }
       dPr[j] = ds;
     }
@@ -433,13 +388,13 @@ attn_bwd_dkv_kernel(AttnBwdArgs a, AttnDims dm) {
       float pd = 0.f, ds = 0.f;
       if (i < T && j < T) {
         const bool keep = (a.kmask[rowbase + j] != 0.f) && (j <= i);
-        const float s = keep ? St[jr * TCP + ic] / dm.sqrt_d : CAST_NEG_FILL;
-        const float p = expf(s - stat[ic]) * stat[TC + ic];
+        const float s = keep ? St[jr * TCP + ic] * dm.inv_sqrt_d : CAST_NEG_FILL;
+        const float p = __expf(s - stat[ic]) * stat[TC + ic];
         const unsigned long long eidx = (((unsigned long long)((long)hh * dm.B + b) * T + i) * T) + j;
         const float mul = stat[3 * TC + ic] * drop_mul(dr, eidx);
         pd = p * mul;
         const float dp = dSt[jr * TCP + ic] * mul;
-        if (keep) ds = p * (dp - stat[2 * TC + ic]) / dm.sqrt_d;
+        if (keep) ds = p * (dp - stat[2 * TC + ic]) * dm.inv_sqrt_d;
       }
       St[jr * TCP + ic] = pd;
       dSt[jr * TCP + ic] = ds;

@@ -46,8 +46,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // Masks are a pure function of (seed, step, site, flat element index in the TF-shaped tensor), so the
 // backward kernels regenerate them and tests can hand the identical masks to the oracle.
 struct Drop {
-  unsigned long long key;  // mixed (seed, step, site)
-  unsigned thresh;         // 0 => dropout disabled
+  unsigned k0, k1;   // mixed (seed, step, site)
+  unsigned thresh;   // 0 => dropout disabled
   float scale;
 };
 
@@ -64,16 +64,31 @@ __device__ __forceinline__ Drop make_drop(float rate, unsigned long long seed, c
                                           int site) {
   Drop d;
   unsigned long long st = step ? *step : 0ull;
-  d.key = mix64(seed + st * 0x9E3779B97F4A7C15ull) ^ mix64(0xD1B54A32D192ED03ull * (unsigned long long)(site + 1));
+  const unsigned long long key =
+      mix64(seed + st * 0x9E3779B97F4A7C15ull) ^ mix64(0xD1B54A32D192ED03ull * (unsigned long long)(site + 1));
+  d.k0 = (unsigned)key;
+  d.k1 = (unsigned)(key >> 32);
   d.thresh = rate > 0.f ? (unsigned)fmin(4294967295.0, floor((double)rate * 4294967296.0)) : 0u;
   d.scale = rate > 0.f ? 1.0f / (1.0f - rate) : 1.0f;
   return d;
 }
 
-__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
-  unsigned long long z = mix64(idx * 0x9E3779B97F4A7C15ull + d.key);
-  return (unsigned)(z >> 32) >= d.thresh;
+// 32-bit avalanche hash of the element index (two multiplies); the 64-bit key and the high index word are folded in
+__device__ __forceinline__ unsigned drop_hash(const Drop& d, unsigned long long idx) {
+  unsigned x = (unsigned)idx ^ d.k0;
+  x += (unsigned)(idx >> 32) * 0x9E3779B1u;
+  x ^= x >> 16;
+  x *= 0x21F0AAADu;
+  x ^= x >> 15;
+  x *= 0x735A2D97u;
+  x ^= x >> 15;
+  x ^= d.k1;
+  x *= 0x9E3779B1u;
+  x ^= x >> 16;
+  return x;
 }
+
+__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) { return drop_hash(d, idx) >= d.thresh; }
 
 // multiplier applied by tf.layers.dropout at element idx (0 or 1/(1-rate)); 1 when disabled
 __device__ __forceinline__ float drop_mul(const Drop& d, unsigned long long idx) {

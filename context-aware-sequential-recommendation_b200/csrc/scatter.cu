@@ -96,45 +96,138 @@ struct ScatterSrc {
   float scale[4];
 };
 
-__device__ __forceinline__ long lower_bound_u32(const unsigned* __restrict__ a, long n, unsigned key) {
-  long lo = 0, hi = n;
-  while (lo < hi) {
-    const long mid = (lo + hi) >> 1;
-    if (a[mid] < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
+constexpr int SEG_CHUNK = 64;  // sorted entries walked by one warp
 
+// Stage 1: every warp walks SEG_CHUNK consecutive sorted entries, lanes own columns.  Segments (runs of equal key)
+// that lie inside the chunk are summed and written straight to dtable; a run that crosses a chunk boundary leaves a
+// partial: part[w][0] ("head": the run began in an earlier chunk) and/or part[w][1] ("tail": the run begins here and
+// continues).  Stage 2 stitches the pieces of each crossing run in chunk order.  Work per warp is bounded by the
+// chunk size however skewed the id distribution is (popular items own thousands of entries).
 template <int NV>
-__global__ void segment_reduce_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay,
-                                      long total, long N, ScatterSrc src, int V, int H,
-                                      float* __restrict__ dtable) {
+__global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay,
+                                       long total, long N, ScatterSrc src, int V, int H, float* __restrict__ dtable,
+                                       float* __restrict__ part, int* __restrict__ pkey) {
   const int lane = threadIdx.x & 31;
-  const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= V) return;
+  const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long beg = w * SEG_CHUNK;
+  if (beg >= total) return;
+  const long end = beg + SEG_CHUNK < total ? beg + SEG_CHUNK : total;
   float acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-  if (r > 0) {  // row 0 is the zero pad: no gradient (modules.py:154-156)
-    const long lo = lower_bound_u32(skeys, total, (unsigned)r);
-    const long hi = lower_bound_u32(skeys, total, (unsigned)r + 1u);
-    for (long e = lo; e < hi; ++e) {
-      const unsigned p = spay[e];
-      const int s = (int)(p / N);
-      const long n = (long)p - (long)s * N;
-      const float f = src.scale[s] * (src.rowscale[s] ? src.rowscale[s][n] : 1.0f);
-      const float* row = src.rows[s] + n * H;
+  unsigned cur = skeys[beg];
+  const bool first_open = beg > 0 && skeys[beg - 1] == cur;
+  bool is_first = true;
+  int head_key = -1, tail_key = -1;
+  for (long e0 = beg; e0 < end; e0 += 4) {
+    unsigned k[4];
+    const float* row[4];
+    float f[4];
+    float val[4][NV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long e = e0 + u;
+      k[u] = e < end ? skeys[e] : 0xffffffffu;
+      row[u] = nullptr;
+      f[u] = 0.f;
+      if (e < end && k[u] != 0u && k[u] < (unsigned)V) {
+        const unsigned p = spay[e];
+        const int s = (int)(p / N);
+        const long n = (long)p - (long)s * N;
+        f[u] = src.scale[s] * (src.rowscale[s] ? src.rowscale[s][n] : 1.0f);
+        row[u] = src.rows[s] + n * H;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
-        if (c < H) acc[i] = fmaf(row[c], f, acc[i]);
+        val[u][i] = (row[u] && c < H) ? row[u][c] : 0.f;
       }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (e0 + u >= end) break;
+      if (k[u] != cur) {  // run of `cur` ends inside this chunk
+        if (is_first && first_open) {
+          head_key = (int)cur;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < H) part[(w * 2 + 0) * H + c] = acc[i];
+          }
+        } else if (cur != 0u && cur < (unsigned)V) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < H) dtable[(long)cur * H + c] = acc[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+        cur = k[u];
+        is_first = false;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = fmaf(val[u][i], f[u], acc[i]);
     }
   }
+  const bool last_open = end < total && skeys[end] == cur;
+  if (is_first && first_open) {
+    head_key = (int)cur;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < H) part[(w * 2 + 0) * H + c] = acc[i];
+    }
+  } else if (last_open) {
+    tail_key = (int)cur;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < H) part[(w * 2 + 1) * H + c] = acc[i];
+    }
+  } else if (cur != 0u && cur < (unsigned)V) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < H) dtable[(long)cur * H + c] = acc[i];
+    }
+  }
+  if (lane == 0) {
+    pkey[w * 2 + 0] = head_key;
+    pkey[w * 2 + 1] = tail_key;
+  }
+}
+
+// Stage 2: the chunk where a crossing run begins adds the following chunks' heads in chunk order.
+template <int NV>
+__global__ void segment_stitch_kernel(const float* __restrict__ part, const int* __restrict__ pkey, long nchunks,
+                                      int V, int H, float* __restrict__ dtable) {
+  const int lane = threadIdx.x & 31;
+  const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nchunks) return;
+  const int key = pkey[w * 2 + 1];
+  if (key < 0) return;
+  float acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
-    if (c < H) dtable[r * H + c] = acc[i];
+    acc[i] = c < H ? part[(w * 2 + 1) * H + c] : 0.f;
+  }
+  for (long w2 = w + 1; w2 < nchunks && pkey[w2 * 2 + 0] == key; ++w2) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < H) acc[i] += part[(w2 * 2 + 0) * H + c];
+    }
+  }
+  if (key > 0 && key < V) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < H) dtable[(long)key * H + c] = acc[i];
+    }
   }
 }
 
@@ -148,22 +241,31 @@ static inline int key_passes(int V) {
 
 using namespace cast;
 
+extern "C" size_t cast_scatter_partial_bytes(long N, int nsrc, int H) {
+  return (size_t)cdiv(N * nsrc, SEG_CHUNK) * 2 * (size_t)H * sizeof(float);
+}
+
 extern "C" size_t cast_scatter_workspace_bytes(long N, int nsrc, int V) {
   const long total = N * nsrc;
   const long nchunks = cdiv(total, RS_CHUNK);
   (void)V;
-  return (size_t)(4 * total + 256 * nchunks) * sizeof(unsigned) + 64;
+  const long nseg = cdiv(total, SEG_CHUNK);
+  (void)nsrc;
+  return (size_t)(4 * total + 256 * nchunks) * sizeof(unsigned) + (size_t)nseg * 2 * sizeof(int) + 64;
 }
 
 extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float* const* rows,
                                  const float* const* rowscale, const float* scale, int V, int H, float* dtable,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
+                                 void* workspace, size_t workspace_bytes, void* partial, size_t partial_bytes,
+                                 void* stream) {
   if (!keys || !rows || !scale || !dtable || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0 || H <= 0 || H > 1024)
     return set_error(CAST_ERR_BAD_ARG, "scatter_rows");
   const long total = N * nsrc;
   if (total >= (1L << 32)) return set_error(CAST_ERR_UNSUPPORTED, "scatter_rows: too many entries");
   if (!workspace || workspace_bytes < cast_scatter_workspace_bytes(N, nsrc, V))
     return set_error(CAST_ERR_WORKSPACE, "scatter_rows: workspace too small");
+  if (!partial || partial_bytes < cast_scatter_partial_bytes(N, nsrc, H))
+    return set_error(CAST_ERR_WORKSPACE, "scatter_rows: partial buffer too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int nchunks = (int)cdiv(total, RS_CHUNK);
   unsigned* bufK[2];
@@ -198,14 +300,26 @@ extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float*
     src.rowscale[s] = (s < nsrc && rowscale) ? rowscale[s] : nullptr;
     src.scale[s] = s < nsrc ? scale[s] : 0.f;
   }
+  // rows nobody touches (and row 0) must read as zero: dense-gradient semantics of the reference
+  cudaMemsetAsync(dtable, 0, (size_t)V * H * sizeof(float), st);
+  const long nseg = cdiv(total, SEG_CHUNK);
+  int* pkey = reinterpret_cast<int*>(hist + 256L * nchunks);
+  float* part = static_cast<float*>(partial);
   const int wpb = 8;
-  const dim3 grid((unsigned)cdiv(V, wpb)), block(32 * wpb);
-#define CAST_SEG(NV) CAST_LAUNCH(segment_reduce_kernel<NV>, grid, block, 0, st, kin, pin, total, N, src, V, H, dtable)
-  if (H <= 64) CAST_SEG(2);
-  else if (H <= 128) CAST_SEG(4);
-  else if (H <= 256) CAST_SEG(8);
-  else if (H <= 512) CAST_SEG(16);
-  else CAST_SEG(32);
+  const dim3 grid((unsigned)cdiv(nseg, wpb)), block(32 * wpb);
+#define CAST_SEG(NV)                                                                                            \
+  {                                                                                                             \
+    CAST_LAUNCH(segment_partial_kernel<NV>, grid, block, 0, st, kin, pin, total, N, src, V, H, dtable, part,    \
+                pkey);                                                                                          \
+    if ((rc = check_launch("segment_partial"))) return rc;                                                      \
+    CAST_LAUNCH(segment_stitch_kernel<NV>, grid, block, 0, st, (const float*)part, (const int*)pkey, nseg, V, H, \
+                dtable);                                                                                        \
+  }
+  if (H <= 64) CAST_SEG(2)
+  else if (H <= 128) CAST_SEG(4)
+  else if (H <= 256) CAST_SEG(8)
+  else if (H <= 512) CAST_SEG(16)
+  else CAST_SEG(32)
 #undef CAST_SEG
-  return check_launch("segment_reduce");
+  return check_launch("segment_stitch");
 }

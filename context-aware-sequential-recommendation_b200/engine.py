@@ -120,6 +120,7 @@ class Engine:
     def __init__(self, model: str, usernum: int, itemnum: int, args, device=None, lib=None, seed: Optional[int] = None):
         self.lib = lib if lib is not None else _lib.load_library()
         self.timing = None
+        self.use_fused = True
         if device is None:
             if not torch.cuda.is_available():
                 raise _lib.CastError("no CUDA device: this package has no CPU fallback")
@@ -254,13 +255,16 @@ class Engine:
         ws = max(lib.cast_layernorm_bwd_workspace_bytes(N, H),
                  lib.cast_gemm_workspace_bytes(kmax, kmax, c.splits),
                  lib.cast_colsum_workspace_bytes(N, kmax), lib.cast_colsum_workspace_bytes(B, T * H),
-                 lib.cast_logits_loss_workspace_bytes(N))
+                 lib.cast_logits_loss_workspace_bytes(N), lib.cast_block_bwd_workspace_bytes(N, H))
         c.ws = torch.empty(ws // 4 + 16, dtype=torch.float32, device=dev)
         c.ws_bytes = ws
         vmax = max(self.P[t].shape[0] for t in self.plan.tables)
         sws = lib.cast_scatter_workspace_bytes(N, 3, vmax)
         c.sws = torch.empty(sws // 4 + 16, dtype=torch.int32, device=dev)
         c.sws_bytes = sws
+        spb = lib.cast_scatter_partial_bytes(N, 3, H)
+        c.spart = torch.empty(spb // 4 + 16, dtype=torch.float32, device=dev)
+        c.spart_bytes = spb
         c.attn = None
         c.graph = None
         self._ctx[B] = c
@@ -322,7 +326,8 @@ class Engine:
         rs_a = (C.c_void_p * nsrc)(*[(r.data_ptr() if r is not None else None) for r in rowscale])
         sc_a = (C.c_float * nsrc)(*scale)
         self._call(self.lib.cast_scatter_rows, keys.data_ptr(), nsrc, N, rows_a, rs_a, sc_a, V, self.H,
-                   self.G[table_name].data_ptr(), c.sws.data_ptr(), c.sws_bytes, self._stream())
+                   self.G[table_name].data_ptr(), c.sws.data_ptr(), c.sws_bytes, c.spart.data_ptr(), c.spart_bytes,
+                   self._stream())
 
     # ------------------------------------------------------------------ towers
     def tower_fwd(self, c, tower, x_in, ids, train, want_attn=False):
@@ -333,12 +338,22 @@ class Engine:
         H, B, T, h = self.H, c.B, self.T, self.h
         x = x_in
         nb = len(tb.blocks)
+        fused = self.use_fused and bool(self.lib.cast_fused_supported(H))
+        P = self.P
         for i, b in enumerate(tb.blocks):
             pre = f"{tower}.{i}."
-            self.ln_fwd(x, pre + "ln1", b.qn, b.mu1, b.rs1, b.kmask, b.qmask)
-            self.linear_fwd(c, b.qn, self.P[pre + "q.w"], self.P[pre + "q.b"], b.Q)
-            self.linear_fwd(c, x, self.P[pre + "k.w"], self.P[pre + "k.b"], b.K)
-            self.linear_fwd(c, x, self.P[pre + "v.w"], self.P[pre + "v.b"], b.V)
+            if fused:
+                self._call(self.lib.cast_ln_qkv_fwd, x.data_ptr(), P[pre + "ln1.gamma"].data_ptr(),
+                           P[pre + "ln1.beta"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "q.b"].data_ptr(),
+                           P[pre + "k.w"].data_ptr(), P[pre + "k.b"].data_ptr(), P[pre + "v.w"].data_ptr(),
+                           P[pre + "v.b"].data_ptr(), c.N, H, 1e-8, b.qn.data_ptr(), b.Q.data_ptr(), b.K.data_ptr(),
+                           b.V.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(), b.kmask.data_ptr(),
+                           b.qmask.data_ptr(), self._stream())
+            else:
+                self.ln_fwd(x, pre + "ln1", b.qn, b.mu1, b.rs1, b.kmask, b.qmask)
+                self.linear_fwd(c, b.qn, self.P[pre + "q.w"], self.P[pre + "q.b"], b.Q)
+                self.linear_fwd(c, x, self.P[pre + "k.w"], self.P[pre + "k.b"], b.K)
+                self.linear_fwd(c, x, self.P[pre + "v.w"], self.P[pre + "v.b"], b.V)
             attn = None
             if want_attn and i == nb - 1:
                 if c.attn is None or c.attn.shape[0] != h * B:
@@ -348,11 +363,19 @@ class Engine:
                        b.qn.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), B, T, H, h, rate, self.seed,
                        self.step_ptr, block_site(tower, i, 1), b.y.data_ptr(), self._p(attn), b.rmax.data_ptr(),
                        b.rlinv.data_ptr(), self._stream())
-            self.ln_fwd(b.y, pre + "ln2", b.zn, b.mu2, b.rs2)
-            self.linear_fwd(c, b.zn, self.P[pre + "ffn1.w"], self.P[pre + "ffn1.b"], b.h1d, relu=1, rate=rate,
-                            site=block_site(tower, i, 2))
-            self.linear_fwd(c, b.h1d, self.P[pre + "ffn2.w"], self.P[pre + "ffn2.b"], b.xout, rate=rate,
-                            site=block_site(tower, i, 3), resid=b.zn, ldr=H, row_ids=ids)
+            if fused:
+                self._call(self.lib.cast_ln_ffn_fwd, b.y.data_ptr(), P[pre + "ln2.gamma"].data_ptr(),
+                           P[pre + "ln2.beta"].data_ptr(), P[pre + "ffn1.w"].data_ptr(), P[pre + "ffn1.b"].data_ptr(),
+                           P[pre + "ffn2.w"].data_ptr(), P[pre + "ffn2.b"].data_ptr(), ids.data_ptr(), rate,
+                           self.seed, self.step_ptr, block_site(tower, i, 2), block_site(tower, i, 3), c.N, H, 1e-8,
+                           b.zn.data_ptr(), b.h1d.data_ptr(), b.xout.data_ptr(), b.mu2.data_ptr(), b.rs2.data_ptr(),
+                           self._stream())
+            else:
+                self.ln_fwd(b.y, pre + "ln2", b.zn, b.mu2, b.rs2)
+                self.linear_fwd(c, b.zn, self.P[pre + "ffn1.w"], self.P[pre + "ffn1.b"], b.h1d, relu=1, rate=rate,
+                                site=block_site(tower, i, 2))
+                self.linear_fwd(c, b.h1d, self.P[pre + "ffn2.w"], self.P[pre + "ffn2.b"], b.xout, rate=rate,
+                                site=block_site(tower, i, 3), resid=b.zn, ldr=H, row_ids=ids)
             x = b.xout
         self.ln_fwd(x, tower + ".lnf", tb.out, tb.muf, tb.rsf)
         return tb.out
@@ -366,6 +389,7 @@ class Engine:
         t = c.t
         nb = len(tb.blocks)
         x_last = tb.blocks[-1].xout if nb else tb.x_in
+        fused = self.use_fused and bool(self.lib.cast_fused_supported(H))
         dx = t[0]
         self.ln_bwd(c, d_out, x_last, tb.muf, tb.rsf, tower + ".lnf", dx)
         for i in reversed(range(nb)):
@@ -373,6 +397,27 @@ class Engine:
             pre = f"{tower}.{i}."
             x_i = tb.blocks[i - 1].xout if i > 0 else tb.x_in
             gm, gmd, dh, dzn, dy = t[1], t[2], t[3], t[4], t[5]
+            if fused:
+                P = self.P
+                self._call(self.lib.cast_ffn_bwd, dx.data_ptr(), ids.data_ptr(), b.zn.data_ptr(), b.h1d.data_ptr(),
+                           b.y.data_ptr(), b.mu2.data_ptr(), b.rs2.data_ptr(), P[pre + "ln2.gamma"].data_ptr(),
+                           P[pre + "ffn1.w"].data_ptr(), P[pre + "ffn2.w"].data_ptr(), rate, self.seed, self.step_ptr,
+                           block_site(tower, i, 3), c.N, H, dy.data_ptr(), self.G[pre + "ln2.beta"].data_ptr(),
+                           c.ws.data_ptr(), c.ws_bytes, self._stream())
+                dQ, dK, dV = t[1], t[2], t[3]
+                self._call(self.lib.cast_attn_bwd, b.Q.data_ptr(), H, b.K.data_ptr(), H, b.V.data_ptr(), H,
+                           dy.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), b.rmax.data_ptr(),
+                           b.rlinv.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed, self.step_ptr,
+                           block_site(tower, i, 1), dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H,
+                           self._stream())
+                dst = tb.dx_in if i == 0 else t[0]
+                self._call(self.lib.cast_qkv_bwd, dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), dy.data_ptr(),
+                           x_i.data_ptr(), b.qn.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
+                           P[pre + "ln1.gamma"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "k.w"].data_ptr(),
+                           P[pre + "v.w"].data_ptr(), c.N, H, dst.data_ptr(), self.G[pre + "ln1.beta"].data_ptr(),
+                           c.ws.data_ptr(), c.ws_bytes, self._stream())
+                dx = dst
+                continue
             # x_out = (dropout(h1d W2 + b2) + zn) * mask                      modules.py:304-311, sasrec.py:83
             self.mask_dropout(dx, ids, rate, block_site(tower, i, 3), gm, gmd)
             self.linear_wgrad(c, b.h1d, gmd, self.G[pre + "ffn2.w"], self.G[pre + "ffn2.b"])

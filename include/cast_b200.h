@@ -95,6 +95,35 @@ int cast_gemm(const float* A, long sam, long sak, const float* B, long sbk, long
               const float* resid, long ldr, const int* row_ids, int splits, void* workspace, size_t workspace_bytes,
               void* stream);
 
+/* ---- fused row-tile kernels of one transformer block, hidden_units <= 64 (cast_fused_supported) -------------------
+ * ln_qkv_fwd  = normalize (modules.py:74-78) + the three tf.layers.dense of multihead_attention (:203-205) + the key /
+ *               query zero-sum flags (:222, :248).
+ * ln_ffn_fwd  = normalize + feedforward (modules.py:298-313) + `*= mask` (sasrec.py:83); saves LN output zn, the
+ *               post-dropout hidden activation h1d, LN stats.
+ * ffn_bwd / qkv_bwd = their backward passes.  Parameter gradients are written to `grads_out`, which must be the
+ *               contiguous flat block  [ln.beta H | ln.gamma H | W H*H | b H | ...]  in the order
+ *               (ffn_bwd) ln2.beta, ln2.gamma, ffn1.w, ffn1.b, ffn2.w, ffn2.b
+ *               (qkv_bwd) ln1.beta, ln1.gamma, q.w, q.b, k.w, k.b, v.w, v.b          (all W stored [in,out]).
+ *               qkv_bwd adds `dres` (gradient of the `outputs += queries` residual, modules.py:269) to d(LN(x)). */
+int cast_fused_supported(int H);
+int cast_ln_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* Wq, const float* bq,
+                    const float* Wk, const float* bk, const float* Wv, const float* bv, long N, int H, float eps,
+                    float* qn, float* Q, float* K, float* V, float* mean, float* rstd, float* kmask, float* qmask,
+                    void* stream);
+int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* beta, const float* W1, const float* b1,
+                    const float* W2, const float* b2, const int* ids, float drop_rate, unsigned long long seed,
+                    const unsigned long long* step, int site_hidden, int site_out, long N, int H, float eps, float* zn,
+                    float* h1d, float* xout, float* mean, float* rstd, void* stream);
+size_t cast_block_bwd_workspace_bytes(long N, int H);
+int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, const float* h1d, const float* y, const float* mean,
+                 const float* rstd, const float* gamma, const float* W1, const float* W2, float drop_rate,
+                 unsigned long long seed, const unsigned long long* step, int site_out, long N, int H, float* dy,
+                 float* grads_out, void* workspace, size_t workspace_bytes, void* stream);
+int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, const float* dres, const float* x, const float* qn,
+                 const float* mean, const float* rstd, const float* gamma, const float* Wq, const float* Wk,
+                 const float* Wv, long N, int H, float* dx, float* grads_out, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
 /* out[c] = sum_r X[r*ld + c] (bias gradients; learned-position gradient = sum over the batch), deterministic. */
 size_t cast_colsum_workspace_bytes(long rows, long cols);
 int cast_colsum(const float* X, long rows, long cols, long ld, float* out, void* workspace, size_t workspace_bytes,
@@ -126,12 +155,14 @@ int cast_logits_loss(const float* seq_emb, const float* table, int V, int H, lon
 /* Deterministic sparse embedding gradient (TF autodiff of the gathers: unsorted_segment_sum):
  * dtable[r,:] = sum over entries e (in ascending e) with keys[e] == r of rows_s[n,:] * rowscale_s[n] * scale_s,
  * where e = s*N + n enumerates `nsrc` sources of N positions each; row 0 (zero pad) gets 0.  Implemented as a
- * stable LSD radix sort of (key, e) followed by a fixed-order segmented reduction: no float atomics.
+ * stable LSD radix sort of (key, e) followed by a fixed-order segmented reduction (64-entry chunks per warp, chunk-
+ * crossing runs stitched in chunk order): no float atomics, work per warp independent of id skew.
  * rows/rowscale/scale are HOST arrays of nsrc device pointers / floats (rowscale[s] may be null). */
-size_t cast_scatter_workspace_bytes(long N, int nsrc, int V);
+size_t cast_scatter_workspace_bytes(long N, int nsrc, int V);     /* integer scratch (sort buffers) */
+size_t cast_scatter_partial_bytes(long N, int nsrc, int H);       /* float scratch (chunk-crossing partial sums) */
 int cast_scatter_rows(const int* keys /* [nsrc*N] */, int nsrc, long N, const float* const* rows,
                       const float* const* rowscale, const float* scale, int V, int H, float* dtable,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      void* workspace, size_t workspace_bytes, void* partial, size_t partial_bytes, void* stream);
 
 /* tf.train.AdamOptimizer(lr, beta1=.9, beta2=.98, eps=1e-8) (sasrec.py:120-121), dense on every element:
  *   g = grad/(*gdenom) + l2*w (gdenom: device scalar, e.g. the global sum(istarget); null => 1; l2 only for

@@ -194,3 +194,5 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
     if (emu_shfl<unsigned>(v, l) == v) r |= (1u << l);
   return r;
 }
+#define __expf(x) expf(x)
+#define __logf(x) logf(x)
