@@ -38,8 +38,8 @@ SIGNATURES = {
     "cast_qkv_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, L, I, P, P, P, SZ, P]),
     "cast_colsum_workspace_bytes": (SZ, [L, L]),
     "cast_colsum": (I, [P, L, L, L, P, P, SZ, P]),
-    "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P]),
-    "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P]),
+    "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P, P]),
+    "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P]),
     "cast_logits_loss_workspace_bytes": (SZ, [L]),
     "cast_logits_loss": (I, [P, P, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),
     "cast_scatter_workspace_bytes": (SZ, [L, I, I]),

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(FT) ln_qkv_fwd_kernel(LnQkvArgs a, FDims d) {
     if (col < d.HP4) {
       float acc[4][4];
       zero_acc(acc);
-      pv_tile<4>(m == 0 ? Ns : Xs, d.HS, Ws, d.HS, d.HP4, col, acc, ty);
+      pv_tile<4, 0>(m == 0 ? Ns : Xs, d.HS, Ws, d.HS, d.HP4, col, acc, ty);
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii) {
         const long row = row0 + ty * 4 + ii;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(FT) ln_ffn_fwd_kernel(LnFfnArgs a, FDims d) {
   const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
   float acc[4][4];
   zero_acc(acc);
-  if (col < d.HP4) pv_tile<4>(Ns, d.HS, Ws, d.HS, d.HP4, col, acc, ty);
+  if (col < d.HP4) pv_tile<4, 0>(Ns, d.HS, Ws, d.HS, d.HP4, col, acc, ty);
   __syncthreads();  // everybody is done with Ws (W1) and with Ys (LN input)
   if (col < d.HP4) {
 #pragma unroll
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(FT) ln_ffn_fwd_kernel(LnFfnArgs a, FDims d) {
   __syncthreads();
   if (col < d.HP4) {
     zero_acc(acc);
-    pv_tile<4>(Ys, d.HS, Ws, d.HS, d.HP4, col, acc, ty);
+    pv_tile<4, 0>(Ys, d.HS, Ws, d.HS, d.HP4, col, acc, ty);
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
       const int r = ty * 4 + ii;
@@ -391,10 +391,10 @@ __global__ void __launch_bounds__(FT) ffn_bwd_kernel(FfnBwdArgs a, FDims d) {
     __syncthreads();
     // dW2 += h1d^T Gd ; db2 += colsum(Gd) ; dh = (Gd W2^T) * relu/dropout mask
     if (active) {
-      if (ty * 4 < d.HP4) pv_tile<4>(HdT, FTS, Gd, d.HS, FR, col, gW2, ty);
+      if (ty * 4 < d.HP4) pv_tile<4, 0>(HdT, FTS, Gd, d.HS, FR, col, gW2, ty);
       float acc[4][4];
       zero_acc(acc);
-      pv_tile<4>(Gd, d.HS, W2T, d.HS, d.HP4, col, acc, ty);
+      pv_tile<4, 0>(Gd, d.HS, W2T, d.HS, d.HP4, col, acc, ty);
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii) {
         const int r = ty * 4 + ii;
@@ -409,10 +409,10 @@ __global__ void __launch_bounds__(FT) ffn_bwd_kernel(FfnBwdArgs a, FDims d) {
     __syncthreads();
     // dW1 += zn^T Dh ; db1 += colsum(Dh) ; dzn = Dh W1^T + Gm  (stored over Gd)
     if (active) {
-      if (ty * 4 < d.HP4) pv_tile<4>(ZnT, FTS, Dh, d.HS, FR, col, gW1, ty);
+      if (ty * 4 < d.HP4) pv_tile<4, 0>(ZnT, FTS, Dh, d.HS, FR, col, gW1, ty);
       float acc[4][4];
       zero_acc(acc);
-      pv_tile<4>(Dh, d.HS, W1T, d.HS, d.HP4, col, acc, ty);
+      pv_tile<4, 0>(Dh, d.HS, W1T, d.HS, d.HP4, col, acc, ty);
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii) {
         const int r = ty * 4 + ii;
@@ -484,13 +484,13 @@ __global__ void __launch_bounds__(FT) qkv_bwd_kernel(QkvBwdArgs a, FDims d) {
     zero_acc(acck);
     if (active) {
       if (ty * 4 < d.HP4) {
-        pv_tile<4>(QnT, FTS, Gq, d.HS, FR, col, gWq, ty);
-        pv_tile<4>(XT, FTS, Gk, d.HS, FR, col, gWk, ty);
-        pv_tile<4>(XT, FTS, Gv, d.HS, FR, col, gWv, ty);
+        pv_tile<4, 0>(QnT, FTS, Gq, d.HS, FR, col, gWq, ty);
+        pv_tile<4, 0>(XT, FTS, Gk, d.HS, FR, col, gWk, ty);
+        pv_tile<4, 0>(XT, FTS, Gv, d.HS, FR, col, gWv, ty);
       }
-      pv_tile<4>(Gq, d.HS, WqT, d.HS, d.HP4, col, accq, ty);   // dqn (without the residual)
-      pv_tile<4>(Gk, d.HS, WkT, d.HS, d.HP4, col, acck, ty);   // dx through K ...
-      pv_tile<4>(Gv, d.HS, WvT, d.HS, d.HP4, col, acck, ty);   // ... and V
+      pv_tile<4, 0>(Gq, d.HS, WqT, d.HS, d.HP4, col, accq, ty);   // dqn (without the residual)
+      pv_tile<4, 0>(Gk, d.HS, WkT, d.HS, d.HP4, col, acck, ty);   // dx through K ...
+      pv_tile<4, 0>(Gv, d.HS, WvT, d.HS, d.HP4, col, acck, ty);   // ... and V
     }
     f_colsum(Gq, 0, d, vb);
     f_colsum(Gk, 1, d, vb);

@@ -361,8 +361,8 @@ class Engine:
                 attn = c.attn
             self._call(self.lib.cast_attn_fwd, b.Q.data_ptr(), H, b.K.data_ptr(), H, b.V.data_ptr(), H,
                        b.qn.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), B, T, H, h, rate, self.seed,
-                       self.step_ptr, block_site(tower, i, 1), b.y.data_ptr(), self._p(attn), b.rmax.data_ptr(),
-                       b.rlinv.data_ptr(), self._stream())
+                       self.step_ptr, block_site(tower, i, 1), ids.data_ptr(), b.y.data_ptr(), self._p(attn),
+                       b.rmax.data_ptr(), b.rlinv.data_ptr(), self._stream())
             if fused:
                 self._call(self.lib.cast_ln_ffn_fwd, b.y.data_ptr(), P[pre + "ln2.gamma"].data_ptr(),
                            P[pre + "ln2.beta"].data_ptr(), P[pre + "ffn1.w"].data_ptr(), P[pre + "ffn1.b"].data_ptr(),
@@ -407,7 +407,8 @@ class Engine:
                 dQ, dK, dV = t[1], t[2], t[3]
                 self._call(self.lib.cast_attn_bwd, b.Q.data_ptr(), H, b.K.data_ptr(), H, b.V.data_ptr(), H,
                            dy.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), b.rmax.data_ptr(),
-                           b.rlinv.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed, self.step_ptr,
+                           b.rlinv.data_ptr(), ids.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed,
+                           self.step_ptr,
                            block_site(tower, i, 1), dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H,
                            self._stream())
                 dst = tb.dx_in if i == 0 else t[0]
@@ -429,7 +430,8 @@ class Engine:
             dQ, dK, dV = t[1], t[2], t[3]
             self._call(self.lib.cast_attn_bwd, b.Q.data_ptr(), H, b.K.data_ptr(), H, b.V.data_ptr(), H,
                        dy.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), b.rmax.data_ptr(), b.rlinv.data_ptr(),
-                       b.rowD.data_ptr(), B, T, H, h, rate, self.seed, self.step_ptr, block_site(tower, i, 1),
+                       ids.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed, self.step_ptr,
+                       block_site(tower, i, 1),
                        dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H, self._stream())
             self.linear_wgrad(c, b.qn, dQ, self.G[pre + "q.w"], self.G[pre + "q.b"])
             self.linear_wgrad(c, x_i, dK, self.G[pre + "k.w"], self.G[pre + "k.b"])

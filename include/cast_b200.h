@@ -132,16 +132,20 @@ int cast_colsum(const float* X, long rows, long cols, long ld, float* out, void*
 /* modules.py:208-269: scaled QK^T, key mask, causal mask, softmax, query mask, dropout, PV, head merge, + queries.
  * Q,K,V: [B*T, ld]; queries = LN(x) [B*T,H] (residual); kmask/qmask: [B*T] 0/1 floats from cast_layernorm_fwd.
  * out [B*T,H]; attn_weights (optional) [h*B,T,T] = reference `attention_weights` (post dropout, modules.py:259);
- * row_max/row_linv (optional, needed for backward) [B,h,T]. */
+ * row_max/row_linv (optional, needed for backward) [B,h,T].
+ * skip_ids (optional) [B*T] item ids: the leading rows of a sequence whose id is 0 are padding whose block output is
+ * multiplied by 0 afterwards (`seq *= mask`, sasrec.py:83); with skip_ids given (and attn_weights null) their
+ * attention rows are not computed (out = queries there) and the backward pass gives them zero gradient. */
 int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv, const float* queries,
                   const float* kmask, const float* qmask, int B, int T, int H, int h, float drop_rate,
-                  unsigned long long seed, const unsigned long long* step, int site, float* out, float* attn_weights,
-                  float* row_max, float* row_linv, void* stream);
+                  unsigned long long seed, const unsigned long long* step, int site, const int* skip_ids, float* out,
+                  float* attn_weights, float* row_max, float* row_linv, void* stream);
 /* Gradient of the attention output (without the residual branch) w.r.t. Q, K, V.  rowD: scratch [B,h,T]. */
 int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv, const float* dO,
-                  const float* kmask, const float* qmask, const float* row_max, const float* row_linv, float* rowD,
-                  int B, int T, int H, int h, float drop_rate, unsigned long long seed, const unsigned long long* step,
-                  int site, float* dQ, long lddq, float* dK, long lddk, float* dV, long lddv, void* stream);
+                  const float* kmask, const float* qmask, const float* row_max, const float* row_linv,
+                  const int* skip_ids, float* rowD, int B, int T, int H, int h, float drop_rate,
+                  unsigned long long seed, const unsigned long long* step, int site, float* dQ, long lddq, float* dK,
+                  long lddk, float* dV, long lddv, void* stream);
 
 /* models/sasrec.py:87-115: pos/neg row gathers from the zero-padded table, row dots, literal BCE
  * (-log(sigmoid+1e-24)), istarget mask, AUC.  sums[0..2] = {sum loss terms, sum auc terms, sum istarget}

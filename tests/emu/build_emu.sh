@@ -8,7 +8,11 @@ mkdir -p "$HERE/_build"
 OBJS=""
 for f in "$SRC"/*.cu; do
   o="$HERE/_build/$(basename "$f" .cu).o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$SRC/cast_rt.cuh" -nt "$o" ] || [ "$HERE/cuda_emu.h" -nt "$o" ]; then
+  stale=0
+  for dep in "$f" "$SRC"/*.cuh "$HERE/cuda_emu.h" "$HERE/../../include/cast_b200.h"; do
+    if [ ! -f "$o" ] || [ "$dep" -nt "$o" ]; then stale=1; fi
+  done
+  if [ $stale = 1 ]; then
     g++ -std=c++17 -O2 -g -fPIC -DCAST_EMU -I"$HERE" -x c++ -c "$f" -o "$o" -Wno-unknown-pragmas &
   fi
   OBJS="$OBJS $o"
