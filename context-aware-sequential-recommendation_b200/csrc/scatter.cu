@@ -1,54 +1,62 @@
 // K7: deterministic sparse embedding gradient.  TF's autodiff of `tf.nn.embedding_lookup` sums duplicate ids
 // with unsorted_segment_sum (atomics, order not reproducible — SURVEY a9); here the (id, entry) pairs are put
-// through a stable LSD radix sort (8-bit digits, one warp per 1024-key chunk, ranks by warp match/ballot) and
-// each table row then sums its own segment in ascending entry order — no float atomics, bit-reproducible.
-// Entries enumerate up to 4 gradient sources of N positions each (item table: the input-sequence lookup x sqrt(H),
-// the positive-item lookup and the negative-item lookup, models/sasrec.py:27,89-90).
+// through a stable LSD radix sort (digits of <= 8 bits sized to the table, one warp per 256-key chunk, ranks by warp
+// match/ballot) and each table row then sums its own segment in ascending entry order — no float atomics,
+// bit-reproducible.  Entries enumerate up to 4 gradient sources of N positions each (item table: the input-sequence
+// lookup x sqrt(H), the positive-item lookup and the negative-item lookup, models/sasrec.py:27,89-90).
 #include "cast_rt.cuh"
 
 namespace cast {
 
-constexpr int RS_WARPS = 8;
-constexpr int RS_CHUNK = 1024;
+constexpr int RS_WARPS = 8;     // warps per CTA
+constexpr int RS_CHUNK = 256;   // keys ranked by one warp
 
-__global__ void radix_hist_kernel(const unsigned* __restrict__ keys, long n, int shift, int nchunks,
+// counts of each digit per chunk: hist[digit * nchunks + chunk]
+__global__ void radix_hist_kernel(const unsigned* __restrict__ keys, long n, int shift, unsigned mask, int nchunks,
                                   unsigned* __restrict__ hist) {
   __shared__ unsigned cnt[RS_WARPS][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chunk = blockIdx.x * RS_WARPS + w;
-  for (int i = lane; i < 256; i += 32) cnt[w][i] = 0u;
+  for (int i = lane; i <= (int)mask; i += 32) cnt[w][i] = 0u;
   __syncwarp();
   if (chunk < nchunks) {
     const long beg = (long)chunk * RS_CHUNK;
     const long end = beg + RS_CHUNK < n ? beg + RS_CHUNK : n;
-    for (long i = beg + lane; i < end; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & 255u], 1u);
+    for (long i = beg + lane; i < end; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & mask], 1u);
   }
   __syncwarp();
   if (chunk < nchunks)
-    for (int i = lane; i < 256; i += 32) hist[(long)i * nchunks + chunk] = cnt[w][i];
+    for (int i = lane; i <= (int)mask; i += 32) hist[(long)i * nchunks + chunk] = cnt[w][i];
 }
 
-// exclusive scan of `total` counters in place (single CTA, fixed order)
-__global__ void radix_scan_kernel(unsigned* __restrict__ hist, long total) {
-  __shared__ unsigned sums[1024];
-  const int t = threadIdx.x;
+// exclusive scan of `total` counters in place (single CTA of 1024 threads, integer => order-free)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ hist, long total) {
+  __shared__ unsigned wsum[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const long per = (total + blockDim.x - 1) / blockDim.x;
   const long beg = (long)t * per;
   const long end = beg + per < total ? beg + per : total;
   unsigned s = 0;
   for (long i = beg; i < end; ++i) s += hist[i];
-  sums[t] = s;
+  unsigned inc = s;  // inclusive scan inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) wsum[w] = inc;
   __syncthreads();
-  if (t == 0) {
-    unsigned run = 0;
-    for (int i = 0; i < (int)blockDim.x; ++i) {
-      const unsigned v = sums[i];
-      sums[i] = run;
-      run += v;
+  if (w == 0) {
+    unsigned v = wsum[lane], vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= o) vi += u;
     }
+    wsum[lane] = vi - v;  // exclusive warp offsets
   }
   __syncthreads();
-  unsigned run = sums[t];
+  unsigned run = wsum[w] + inc - s;
   for (long i = beg; i < end; ++i) {
     const unsigned v = hist[i];
     hist[i] = run;
@@ -57,13 +65,13 @@ __global__ void radix_scan_kernel(unsigned* __restrict__ hist, long total) {
 }
 
 __global__ void radix_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ pay_in, long n,
-                                     int shift, int nchunks, const unsigned* __restrict__ offs,
+                                     int shift, unsigned mask, int nchunks, const unsigned* __restrict__ offs,
                                      unsigned* __restrict__ keys_out, unsigned* __restrict__ pay_out) {
   __shared__ unsigned base[RS_WARPS][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chunk = blockIdx.x * RS_WARPS + w;
   if (chunk >= nchunks) return;  // warp-uniform; no block barriers below
-  for (int i = lane; i < 256; i += 32) base[w][i] = offs[(long)i * nchunks + chunk];
+  for (int i = lane; i <= (int)mask; i += 32) base[w][i] = offs[(long)i * nchunks + chunk];
   __syncwarp();
   const long beg = (long)chunk * RS_CHUNK;
   const long end = beg + RS_CHUNK < n ? beg + RS_CHUNK : n;
@@ -71,7 +79,8 @@ __global__ void radix_scatter_kernel(const unsigned* __restrict__ keys_in, const
     const long i = i0 + lane;
     const bool valid = i < end;
     const unsigned k = valid ? keys_in[i] : 0u;
-    const unsigned dgt = valid ? ((k >> shift) & 255u) : (256u + lane);
+    const unsigned pay = valid ? (pay_in ? pay_in[i] : (unsigned)i) : 0u;
+    const unsigned dgt = valid ? ((k >> shift) & mask) : (256u + lane);
     const unsigned peers = __match_any_sync(0xffffffffu, dgt);
     const int rank = __popc(peers & ((1u << lane) - 1u));
     const int leader = __ffs((int)peers) - 1;
@@ -84,7 +93,7 @@ __global__ void radix_scatter_kernel(const unsigned* __restrict__ keys_in, const
     if (valid) {
       const unsigned p = b + (unsigned)rank;
       keys_out[p] = k;
-      pay_out[p] = pay_in ? pay_in[i] : (unsigned)i;
+      pay_out[p] = pay;
     }
     __syncwarp();
   }
@@ -96,13 +105,16 @@ struct ScatterSrc {
   float scale[4];
 };
 
-constexpr int SEG_CHUNK = 64;  // sorted entries walked by one warp
+constexpr int SEG_CHUNK = 64;  // sorted entries walked by one warp (two per lane)
+// entries whose row loads are in flight together (NV = columns per lane): bounded so the staging registers stay <= 64
 
-// Stage 1: every warp walks SEG_CHUNK consecutive sorted entries, lanes own columns.  Segments (runs of equal key)
-// that lie inside the chunk are summed and written straight to dtable; a run that crosses a chunk boundary leaves a
-// partial: part[w][0] ("head": the run began in an earlier chunk) and/or part[w][1] ("tail": the run begins here and
-// continues).  Stage 2 stitches the pieces of each crossing run in chunk order.  Work per warp is bounded by the
-// chunk size however skewed the id distribution is (popular items own thousands of entries).
+// Stage 1: every warp walks SEG_CHUNK consecutive sorted entries, lanes own columns.  Each lane first resolves two
+// entries (key, scale factor, source row) in parallel; the walk then broadcasts them by shuffle, so the serial part
+// only waits on the row loads (SEG_U rows in flight).  Segments (runs of equal key) inside the chunk are summed in
+// entry order and written straight to dtable; a run that crosses a chunk boundary leaves a partial: part[w][0]
+// ("head": the run began in an earlier chunk) and/or part[w][1] ("tail": the run begins here and continues).  Stage 2
+// stitches the pieces of each crossing run in chunk order.  Work per warp is bounded by the chunk size however
+// skewed the id distribution is (popular items own thousands of entries).
 template <int NV>
 __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay,
                                        long total, long N, ScatterSrc src, int V, int H, float* __restrict__ dtable,
@@ -112,42 +124,61 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
   const long beg = w * SEG_CHUNK;
   if (beg >= total) return;
   const long end = beg + SEG_CHUNK < total ? beg + SEG_CHUNK : total;
+  const int cnt = (int)(end - beg);
+  constexpr int SEG_U = NV <= 4 ? 8 : (NV <= 8 ? 4 : 2);
+  // ---- this lane's two entries
+  unsigned mk[2];
+  float mf[2];
+  const float* mrow[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const long e = beg + lane + 32 * q;
+    mk[q] = e < end ? skeys[e] : 0xffffffffu;
+    mf[q] = 0.f;
+    mrow[q] = nullptr;
+    if (e < end && mk[q] != 0u && mk[q] < (unsigned)V) {
+      const unsigned p = spay[e];
+      const int s = (int)(p / N);
+      const long n = (long)p - (long)s * N;
+      mf[q] = src.scale[s] * (src.rowscale[s] ? src.rowscale[s][n] : 1.0f);
+      mrow[q] = src.rows[s] + n * H;
+    }
+  }
+  const unsigned last_key = __shfl_sync(0xffffffffu, mk[(cnt - 1) >> 5], (cnt - 1) & 31);
+  if (last_key == 0u) {  // sorted => the whole chunk is padding (id 0): contributes nothing
+    if (lane == 0) { pkey[w * 2 + 0] = -1; pkey[w * 2 + 1] = -1; }
+    return;
+  }
   float acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-  unsigned cur = skeys[beg];
+  unsigned cur = __shfl_sync(0xffffffffu, mk[0], 0);
   const bool first_open = beg > 0 && skeys[beg - 1] == cur;
   bool is_first = true;
   int head_key = -1, tail_key = -1;
-  for (long e0 = beg; e0 < end; e0 += 4) {
-    unsigned k[4];
-    const float* row[4];
-    float f[4];
-    float val[4][NV];
+  for (int e0 = 0; e0 < cnt; e0 += SEG_U) {
+    unsigned k[SEG_U];
+    float f[SEG_U];
+    float val[SEG_U][NV];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long e = e0 + u;
-      k[u] = e < end ? skeys[e] : 0xffffffffu;
-      row[u] = nullptr;
-      f[u] = 0.f;
-      if (e < end && k[u] != 0u && k[u] < (unsigned)V) {
-        const unsigned p = spay[e];
-        const int s = (int)(p / N);
-        const long n = (long)p - (long)s * N;
-        f[u] = src.scale[s] * (src.rowscale[s] ? src.rowscale[s][n] : 1.0f);
-        row[u] = src.rows[s] + n * H;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < SEG_U; ++u) {
+      const int e = e0 + u;  // < 64; entries >= cnt carry key 0xffffffff / null row
+      const int q = e >> 5, sl = e & 31;
+      const unsigned kk = __shfl_sync(0xffffffffu, q ? mk[1] : mk[0], sl);
+      const float ff = __shfl_sync(0xffffffffu, q ? mf[1] : mf[0], sl);
+      const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)(q ? mrow[1] : mrow[0]), sl);
+      const float* row = reinterpret_cast<const float*>(rp);
+      k[u] = kk;
+      f[u] = ff;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
-        val[u][i] = (row[u] && c < H) ? row[u][c] : 0.f;
+        val[u][i] = (row && c < H) ? row[c] : 0.f;
       }
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (e0 + u >= end) break;
+    for (int u = 0; u < SEG_U; ++u) {
+      if (e0 + u >= cnt) break;
       if (k[u] != cur) {  // run of `cur` ends inside this chunk
         if (is_first && first_open) {
           head_key = (int)cur;
@@ -200,7 +231,9 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
   }
 }
 
-// Stage 2: the chunk where a crossing run begins adds the following chunks' heads in chunk order.
+// Stage 2: the chunk where a crossing run begins adds the following chunks' heads.  The run length is found 32 chunks
+// per ballot; the sum uses ST_U interleaved accumulators (chunk j goes to accumulator j mod ST_U, each in ascending
+// chunk order) folded in a fixed order at the end => still a fixed summation tree, with ST_U loads in flight.
 template <int NV>
 __global__ void segment_stitch_kernel(const float* __restrict__ part, const int* __restrict__ pkey, long nchunks,
                                       int V, int H, float* __restrict__ dtable) {
@@ -208,33 +241,54 @@ __global__ void segment_stitch_kernel(const float* __restrict__ part, const int*
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nchunks) return;
   const int key = pkey[w * 2 + 1];
-  if (key < 0) return;
-  float acc[NV];
+  if (key <= 0 || key >= V) return;
+  constexpr int ST_U = NV <= 2 ? 8 : (NV <= 4 ? 4 : (NV <= 8 ? 2 : 1));
+  long L = 0;  // chunks w+1 .. w+L continue the run
+  for (;;) {
+    const long w2 = w + 1 + L + lane;
+    const bool cont = w2 < nchunks && pkey[w2 * 2 + 0] == key;
+    const unsigned m = __ballot_sync(0xffffffffu, cont);
+    if (m == 0xffffffffu) { L += 32; continue; }
+    L += __ffs((int)~m) - 1;
+    break;
+  }
+  float acc[ST_U][NV];
+#pragma unroll
+  for (int u = 0; u < ST_U; ++u)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[u][i] = 0.f;
+  for (long j0 = 0; j0 < L; j0 += ST_U) {
+#pragma unroll
+    for (int u = 0; u < ST_U; ++u) {
+      const long j = j0 + u;
+      if (j < L) {
+        const float* src = part + ((w + 1 + j) * 2 + 0) * H;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + 32 * i;
+          if (c < H) acc[u][i] += src[c];
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
-    acc[i] = c < H ? part[(w * 2 + 1) * H + c] : 0.f;
-  }
-  for (long w2 = w + 1; w2 < nchunks && pkey[w2 * 2 + 0] == key; ++w2) {
+    if (c < H) {
+      float s = part[(w * 2 + 1) * H + c];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < H) acc[i] += part[(w2 * 2 + 0) * H + c];
-    }
-  }
-  if (key > 0 && key < V) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < H) dtable[(long)key * H + c] = acc[i];
+      for (int u = 0; u < ST_U; ++u) s += acc[u][i];
+      dtable[(long)key * H + c] = s;
     }
   }
 }
 
-static inline int key_passes(int V) {
+// number of radix passes and digit width for a table of V rows (ids < V)
+static inline void key_plan(int V, int* passes, int* dbits) {
   int bits = 1;
   while ((1L << bits) < (long)V) ++bits;
-  return (bits + 7) / 8;
+  *passes = (bits + 7) / 8;
+  *dbits = (bits + *passes - 1) / *passes;
 }
 
 }  // namespace cast
@@ -250,7 +304,6 @@ extern "C" size_t cast_scatter_workspace_bytes(long N, int nsrc, int V) {
   const long nchunks = cdiv(total, RS_CHUNK);
   (void)V;
   const long nseg = cdiv(total, SEG_CHUNK);
-  (void)nsrc;
   return (size_t)(4 * total + 256 * nchunks) * sizeof(unsigned) + (size_t)nseg * 2 * sizeof(int) + 64;
 }
 
@@ -278,17 +331,19 @@ extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float*
   unsigned* hist = base + 4 * total;
   const unsigned* kin = reinterpret_cast<const unsigned*>(keys);
   const unsigned* pin = nullptr;
-  const int passes = key_passes(V);
+  int passes, dbits;
+  key_plan(V, &passes, &dbits);
+  const unsigned mask = (1u << dbits) - 1u;
   const int nblk = (int)cdiv(nchunks, RS_WARPS);
   int rc;
   for (int p = 0; p < passes; ++p) {
     unsigned* kout = bufK[p & 1];
     unsigned* pout = bufP[p & 1];
-    CAST_LAUNCH(radix_hist_kernel, dim3(nblk), dim3(32 * RS_WARPS), 0, st, kin, total, 8 * p, nchunks, hist);
+    CAST_LAUNCH(radix_hist_kernel, dim3(nblk), dim3(32 * RS_WARPS), 0, st, kin, total, dbits * p, mask, nchunks, hist);
     if ((rc = check_launch("radix_hist"))) return rc;
-    CAST_LAUNCH(radix_scan_kernel, dim3(1), dim3(1024), 0, st, hist, 256L * nchunks);
+    CAST_LAUNCH(radix_scan_kernel, dim3(1), dim3(1024), 0, st, hist, (long)(mask + 1) * nchunks);
     if ((rc = check_launch("radix_scan"))) return rc;
-    CAST_LAUNCH(radix_scatter_kernel, dim3(nblk), dim3(32 * RS_WARPS), 0, st, kin, pin, total, 8 * p, nchunks,
+    CAST_LAUNCH(radix_scatter_kernel, dim3(nblk), dim3(32 * RS_WARPS), 0, st, kin, pin, total, dbits * p, mask, nchunks,
                 (const unsigned*)hist, kout, pout);
     if ((rc = check_launch("radix_scatter"))) return rc;
     kin = kout;
@@ -305,7 +360,7 @@ extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float*
   const long nseg = cdiv(total, SEG_CHUNK);
   int* pkey = reinterpret_cast<int*>(hist + 256L * nchunks);
   float* part = static_cast<float*>(partial);
-  const int wpb = 8;
+  const int wpb = 4;
   const dim3 grid((unsigned)cdiv(nseg, wpb)), block(32 * wpb);
 #define CAST_SEG(NV)                                                                                            \
   {                                                                                                             \
