@@ -526,7 +526,13 @@ __global__ void __launch_bounds__(FT) qkv_bwd_kernel(QkvBwdArgs a, FDims d) {
   if (grp < 3 && (t & 63) < H) P[2 * H + grp * (H * H + H) + H * H + (t & 63)] = vb;
 }
 
-static int bwd_grid(long ntiles) { return (int)(ntiles < 296 ? ntiles : 296); }
+// persistent grids: one wave of resident CTAs on the 148 SMs of a B200 (ffn_bwd: 2 CTAs/SM; qkv_bwd: 1 CTA/SM — 160
+// registers x 256 threads), so no CTA waits for a slot and the number of weight-gradient partials stays minimal
+constexpr int NUM_SMS = 148;
+static int bwd_grid(long ntiles, int ctas_per_sm = 2) {
+  const long cap = (long)NUM_SMS * ctas_per_sm;
+  return (int)(ntiles < cap ? ntiles : cap);
+}
 
 }  // namespace cast
 
@@ -619,7 +625,7 @@ extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, c
     return set_error(CAST_ERR_WORKSPACE, "qkv_bwd: workspace too small");
   const FDims d = fdims(N, H);
   const long ntiles = cdiv(N, FR);
-  const int grid = bwd_grid(ntiles);
+  const int grid = bwd_grid(ntiles, 1);
   QkvBwdArgs a{dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv, dx, static_cast<float*>(workspace), ntiles};
   const size_t smem = sizeof(float) * ((size_t)3 * FR * d.HS + (size_t)2 * d.HP4 * FTS + (size_t)3 * d.HP4 * d.HS +
                                        (size_t)FR * 4);

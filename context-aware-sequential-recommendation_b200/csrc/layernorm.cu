@@ -122,25 +122,51 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
   }
 }
 
-// out[c] = sum_{p < nparts} partial[p][c], fixed order.  Generic second stage used by LN, bias and wgrad.
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, long count,
-                                       float* __restrict__ out0, long split, float* __restrict__ out1) {
-  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c < count; c += (long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(long)p * count + c];
-    if (c < split)
-      out0[c] = s;
-    else
-      out1[c - split] = s;
+// out[c] = sum_{p < nparts} partial[p][c] in a fixed order.  Generic second stage used by LN, bias and wgrad.
+// A CTA covers 32 columns with 8 part-groups (group g owns parts g, g+8, ...; 4 interleaved accumulators each, so 32
+// independent loads are in flight per column instead of one dependent chain over all parts); the 8 group sums are
+// then folded in group order through shared memory => same bits every run.
+constexpr int RP_COLS = 32, RP_GROUPS = 8, RP_ILP = 4;
+__global__ void __launch_bounds__(RP_COLS * RP_GROUPS)
+reduce_partials_kernel(const float* __restrict__ partial, int nparts, long count, float* __restrict__ out0, long split,
+                       float* __restrict__ out1) {
+  __shared__ float red[RP_GROUPS][RP_COLS];
+  const int cl = threadIdx.x % RP_COLS, g = threadIdx.x / RP_COLS;
+  for (long c0 = (long)blockIdx.x * RP_COLS; c0 < count; c0 += (long)gridDim.x * RP_COLS) {
+    const long c = c0 + cl;
+    float acc[RP_ILP];
+#pragma unroll
+    for (int u = 0; u < RP_ILP; ++u) acc[u] = 0.f;
+    if (c < count) {
+      for (int p0 = g; p0 < nparts; p0 += RP_GROUPS * RP_ILP) {
+#pragma unroll
+        for (int u = 0; u < RP_ILP; ++u) {
+          const int p = p0 + u * RP_GROUPS;
+          if (p < nparts) acc[u] += partial[(long)p * count + c];
+        }
+      }
+    }
+    red[g][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (g == 0 && c < count) {
+      float s = red[0][cl];
+#pragma unroll
+      for (int k = 1; k < RP_GROUPS; ++k) s += red[k][cl];
+      if (c < split)
+        out0[c] = s;
+      else
+        out1[c - split] = s;
+    }
+    __syncthreads();
   }
 }
 
 int launch_reduce_partials(const float* partial, int nparts, long count, float* out0, long split, float* out1,
                            cudaStream_t stream) {
-  long g = cdiv(count, 256);
-  if (g > 1184) g = 1184;
-  CAST_LAUNCH(reduce_partials_kernel, dim3((unsigned)g), dim3(256), 0, stream, partial, nparts, count, out0, split,
-              out1);
+  long g = cdiv(count, RP_COLS);
+  if (g > 2368) g = 2368;
+  CAST_LAUNCH(reduce_partials_kernel, dim3((unsigned)g), dim3(RP_COLS * RP_GROUPS), 0, stream, partial, nparts, count,
+              out0, split, out1);
   return check_launch("reduce_partials");
 }
 

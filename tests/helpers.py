@@ -23,8 +23,13 @@ def emu_lib():
     """TEST INFRASTRUCTURE: the kernel sources compiled for the host (tests/emu).  Never used by the package."""
     global _emu
     if _emu is None:
-        subprocess.check_call(["bash", os.path.join(ROOT, "tests", "emu", "build_emu.sh")], stdout=subprocess.DEVNULL)
-        _emu = castlib.bind(ctypes.CDLL(EMU_SO))
+        import fcntl
+        os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+        with open(EMU_SO + ".lock", "w") as lk:  # several test processes (gloo ranks) may arrive together
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            subprocess.check_call(["bash", os.path.join(ROOT, "tests", "emu", "build_emu.sh")],
+                                  stdout=subprocess.DEVNULL)
+            _emu = castlib.bind(ctypes.CDLL(EMU_SO))
     return _emu
 
 
