@@ -183,6 +183,23 @@ int cast_adam_tf_step(float* w, const float* grad, float* m, float* v, long n, f
 int cast_score_rank_cand(const float* seq_last, long ld, const float* table, int V, int H, long U, const int* cand,
                          int C, float* logits, int* count_greater, int* count_equal, void* stream);
 
+/* Full-catalog evaluation scoring (BASELINE north_star (4); the reference's util.py:291-321 only ever scores 101
+ * candidates, its test_logits GEMM sasrec.py:93-97 is the same contraction over the whole table):
+ *   count_greater[u] = #{ j in [1,V), j != target[u], j not in rated(u) : s(u,j) >  s(u,target[u]) }
+ *   count_equal[u]   = #{ same set                                      : s(u,j) == s(u,target[u]) }
+ * with s the canonical logit of cast_score_rank_cand (sequential-k, unfused fp32).  rank = count_greater.
+ * seq_last [U, ld] last-position vectors; table [V,H] (row 0 = pad, never a candidate); rated_ptr [U+1] / rated_idx:
+ * CSR of each user's already-seen item ids (unique per user; null => nothing excluded).
+ * mode 0: tcgen05 tensor-core GEMM (3xTF32 split, accumulator in TMEM) + exact re-scoring of the error band;
+ * mode 1: exact brute force.  Both return identical integers.  stats (optional, device, 2 x u64): [0] = number of
+ * band candidates re-scored exactly. */
+size_t cast_score_rank_full_workspace_bytes(long U, int V);
+int cast_score_rank_full(const float* seq_last, long ld, const float* table, int V, int H, long U, const int* target,
+                         const int* rated_ptr, const int* rated_idx, int mode, int* count_greater, int* count_equal,
+                         unsigned long long* stats, void* workspace, size_t workspace_bytes, void* stream);
+/* Synchronises the stream and reports the tensor-core pass's watchdog flag (0 = ok). */
+int cast_score_rank_full_status(const void* workspace, long U, int V, int* host_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

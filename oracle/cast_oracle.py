@@ -405,3 +405,39 @@ def metrics_from_ranks(ranks):
             NDCG += 1 / np.log2(rank + 2)
             HT += 1
     return NDCG / valid_user, HT / valid_user
+
+
+# ----------------------------------------------------------------------------------------------------------
+# full-catalog scoring (sasrec.py:93-97 over the whole table + util.py:318-321 rank) — canonical fp32 order
+# ----------------------------------------------------------------------------------------------------------
+def canonical_logits(users: np.ndarray, table: np.ndarray) -> np.ndarray:
+    """s[u,j] = sum_k users[u,k]*table[j,k], k ascending, product and sum each rounded to fp32 (no FMA) — the
+    summation order the kernels' `canonical_dot` uses, so logits compare bit for bit."""
+    u = np.asarray(users, np.float32)
+    e = np.asarray(table, np.float32)
+    acc = np.zeros((u.shape[0], e.shape[0]), np.float32)
+    for k in range(u.shape[1]):
+        acc = (acc + (u[:, k:k + 1] * e[None, :, k]).astype(np.float32)).astype(np.float32)
+    return acc
+
+
+def rank_full_counts(users, table, target, rated=None):
+    """(count_greater, count_equal) of the target against every item in [1,V) that is not the target and not in
+    rated[u] (iterable of ids per user); an id outside [1,V) as target scores 0 like the zero-pad row."""
+    s = canonical_logits(users, table)
+    U, V = s.shape
+    gt = np.zeros(U, np.int64)
+    eq = np.zeros(U, np.int64)
+    for u in range(U):
+        t = int(target[u])
+        ts = s[u, t] if 0 < t < V else np.float32(0)
+        ok = np.ones(V, bool)
+        ok[0] = False
+        if 0 <= t < V:
+            ok[t] = False
+        if rated is not None:
+            r = np.asarray(list(rated[u]), np.int64)
+            ok[r[(r >= 0) & (r < V)]] = False
+        gt[u] = int((s[u, ok] > ts).sum())
+        eq[u] = int((s[u, ok] == ts).sum())
+    return gt, eq
