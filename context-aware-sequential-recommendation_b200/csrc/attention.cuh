@@ -538,17 +538,13 @@ int dispatch_att(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, const 
   static size_t cfg[3] = {48 * 1024, 48 * 1024, 48 * 1024};
   const int T = dm.T, h = dm.h, B = dm.B;
   if (NB == 1) {
-    // small heads: 64-row tiles while the [tile, T] score block fits, 32-row tiles for long sequences
-    if (which == 0) {
-      if (fwd_smem(dm, 4, 4) <= SMEM_MAX)
-        return launch_att(attn_fwd_kernel<4, 4, 1, DPAD, DS>, fwd_smem(dm, 4, 4), (int)cdiv(T, 64), h, B, *fa, dm, stream, &cfg[0]);
+    // small heads (measured at T=200, d=50 on B200, gpurun_out/tune_*.log): 32-query tiles for the forward and the
+    // dQ kernels (46 / 79 KB of shared memory => 4 / 2 CTAs per SM instead of 2 / 1, and half the causal waste on
+    // the diagonal tile), 64-key tiles for dK/dV (its 32-row variant re-reads Q/dO twice as often and was slower)
+    if (which == 0)
       return launch_att(attn_fwd_kernel<2, 4, 1, DPAD, DS>, fwd_smem(dm, 2, 4), (int)cdiv(T, 32), h, B, *fa, dm, stream, &cfg[0]);
-    }
-    if (which == 1) {
-      if (dq_smem(dm, 4, 4) <= SMEM_MAX)
-        return launch_att(attn_bwd_dq_kernel<4, 4, 1, DPAD, DS>, dq_smem(dm, 4, 4), (int)cdiv(T, 64), h, B, *ba, dm, stream, &cfg[1]);
+    if (which == 1)
       return launch_att(attn_bwd_dq_kernel<2, 4, 1, DPAD, DS>, dq_smem(dm, 2, 4), (int)cdiv(T, 32), h, B, *ba, dm, stream, &cfg[1]);
-    }
     return launch_att(attn_bwd_dkv_kernel<4, 4, 1, DPAD, DS>, dkv_smem(dm, 4, 4), (int)cdiv(T, 64), h, B, *ba, dm, stream, &cfg[2]);
   } else if (NB == 2) {
     if (which == 0)

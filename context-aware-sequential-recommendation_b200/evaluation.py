@@ -60,7 +60,7 @@ def build_candidates(dataset, args, split: str = "test", rng=None):
     lo, hi = get_delta_range(train)
     target_of = test if split == "test" else valid
     member = np.zeros(itemnum + 2, dtype=bool)
-    us, seqs, cands, tss, hrs, dys = [], [], [], [], [], []
+    us, seqs, cands, tss, hrs, dys, rated = [], [], [], [], [], [], []
     trunc = None
     if getattr(args, "test_model", None):
         if not getattr(args, "test_seq_len", None):
@@ -94,6 +94,7 @@ def build_candidates(dataset, args, split: str = "test", rng=None):
             hours[:-trunc] = 0
             days[:-trunc] = 0
         us.append(u)
+        rated.append(np.unique(items).astype(np.int32))
         seqs.append(seq)
         cands.append(np.concatenate([[target_of[u][0].item], neg]).astype(np.int32))
         tss.append(timeseq)
@@ -101,7 +102,7 @@ def build_candidates(dataset, args, split: str = "test", rng=None):
         dys.append(days)
     st = lambda a, w: np.stack(a) if a else np.zeros((0, w), np.int32)  # noqa: E731
     return {"u": np.asarray(us, np.int32), "seq": st(seqs, T), "item_idx": st(cands, 101), "timeseq": st(tss, T),
-            "hours": st(hrs, T), "days": st(dys, T)}
+            "hours": st(hrs, T), "days": st(dys, T), "rated": rated}
 
 
 def reference_rank(logits_row: np.ndarray) -> int:
@@ -139,8 +140,10 @@ def metrics_from_histogram(hist) -> tuple:
     return ndcg / n, ht / n
 
 
-def score_users(model, cand, batch_users: int = 256, lo: int = 0, hi: Optional[int] = None):
-    """Ranks of cand rows [lo, hi) through the model's batched scoring path; fixed batch shape (tail padded)."""
+def score_users(model, cand, batch_users: int = 256, lo: int = 0, hi: Optional[int] = None, mode: str = "101"):
+    """Ranks of cand rows [lo, hi) through the model's batched scoring path; fixed batch shape (tail padded).
+    mode "101": the reference's target + 100 sampled negatives; mode "full": rank among every item the user has not
+    rated (count of strictly greater logits; exact ties do not push the target down)."""
     hi = len(cand["u"]) if hi is None else hi
     ranks = np.zeros(max(0, hi - lo), np.int64)
     B = max(1, min(batch_users, max(1, hi - lo)))
@@ -155,13 +158,19 @@ def score_users(model, cand, batch_users: int = 256, lo: int = 0, hi: Optional[i
             out[:n] = a[s:e]
             return out
 
+        if mode == "full":
+            rated = list(cand["rated"][s:e]) + [np.zeros(0, np.int32)] * (B - n)
+            cgt, _ = model.score_full_catalog(pad(cand["seq"]), pad(cand["item_idx"])[:, 0], rated, pad(cand["timeseq"]),
+                                              pad(cand["hours"]), pad(cand["days"]))
+            ranks[s - lo:e - lo] = cgt[:n]
+            continue
         logits, cgt, ceq = model.score_candidates(pad(cand["seq"]), pad(cand["item_idx"]), pad(cand["timeseq"]),
                                                   pad(cand["hours"]), pad(cand["days"]))
         ranks[s - lo:e - lo] = ranks_from_device(logits[:n], cgt[:n], ceq[:n])
     return ranks
 
 
-def _evaluate(model, dataset, args, split, batch_users, rng):
+def _evaluate(model, dataset, args, split, batch_users, rng, mode="101"):
     cand = build_candidates(dataset, args, split, rng)
     U = len(cand["u"])
     try:
@@ -170,12 +179,12 @@ def _evaluate(model, dataset, args, split, batch_users, rng):
     except Exception:  # pragma: no cover
         world = 1
     if world == 1:
-        return metrics_from_ranks(score_users(model, cand, batch_users))
+        return metrics_from_ranks(score_users(model, cand, batch_users, mode=mode))
     import torch
     from . import dist as cdist
     rank = dist.get_rank()
     lo, hi = cdist.shard_users(U, rank, world)
-    ranks = score_users(model, cand, batch_users, lo, hi)
+    ranks = score_users(model, cand, batch_users, lo, hi, mode=mode)
     hist = np.zeros(11, np.int64)
     for r in ranks:
         if r < 10:
@@ -187,11 +196,12 @@ def _evaluate(model, dataset, args, split, batch_users, rng):
     return metrics_from_histogram(h.cpu().numpy())
 
 
-def evaluate(model, dataset, args, sess=None, batch_users: int = 256, rng=None):
-    """Drop-in for reference util.evaluate (test split)."""
-    return _evaluate(model, dataset, args, "test", batch_users, rng)
+def evaluate(model, dataset, args, sess=None, batch_users: int = 256, rng=None, mode: str = "101"):
+    """Drop-in for reference util.evaluate (test split).  mode="full" ranks against the whole catalog instead of the
+    reference's 100 sampled negatives (the negatives are still drawn, so the RNG streams stay aligned)."""
+    return _evaluate(model, dataset, args, "test", batch_users, rng, mode)
 
 
-def evaluate_valid(model, dataset, args, sess=None, batch_users: int = 256, rng=None):
+def evaluate_valid(model, dataset, args, sess=None, batch_users: int = 256, rng=None, mode: str = "101"):
     """Drop-in for reference util.evaluate_valid."""
-    return _evaluate(model, dataset, args, "valid", batch_users, rng)
+    return _evaluate(model, dataset, args, "valid", batch_users, rng, mode)

@@ -152,6 +152,44 @@ class _Model:
                   ceq.data_ptr(), eng._stream())
         return logits.cpu().numpy(), cgt.cpu().numpy(), ceq.cpu().numpy()
 
+    def score_full_catalog(self, seq, target, rated=None, time_seq=None, hours=None, days=None, mode: int = 0):
+        """Full-catalog evaluation scoring: rank of target[u] among every item in [1, itemnum] the user has not
+        rated (rated: optional list of id collections, one per user).  mode 0 = tcgen05 tensor-core GEMM with exact
+        band re-scoring, mode 1 = exact brute force.  Returns (count_greater [U], count_equal [U]) int32 arrays."""
+        eng = self.engine
+        c = self.forward_eval(seq, time_seq, hours, days)
+        B, T, H = c.B, eng.T, eng.H
+        dev = eng.device
+        V = eng.P["item_emb"].shape[0]
+        tgt = torch.from_numpy(np.ascontiguousarray(np.asarray(target, dtype=np.int32).reshape(-1))).to(dev)
+        rptr = ridx = None
+        if rated is not None:
+            ptr = np.zeros(B + 1, np.int32)
+            flat = []
+            for u, r in enumerate(rated):
+                ids = np.unique(np.asarray(list(r), dtype=np.int64))
+                flat.append(ids)
+                ptr[u + 1] = ptr[u] + len(ids)
+            idx = np.concatenate(flat + [np.zeros(1, np.int64)]).astype(np.int32)
+            rptr, ridx = torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev)
+        cgt = torch.empty(B, dtype=torch.int32, device=dev)
+        ceq = torch.empty(B, dtype=torch.int32, device=dev)
+        wsb = eng.lib.cast_score_rank_full_workspace_bytes(B, V)
+        ws = self._pinned.get(("sfws", B))
+        if ws is None:
+            ws = self._pinned[("sfws", B)] = torch.empty(wsb // 4 + 16, dtype=torch.int32, device=dev)
+        last = c.seq_emb.view(B, T, H)[:, T - 1, :]
+        eng._call(eng.lib.cast_score_rank_full, last.data_ptr(), T * H, eng.P["item_emb"].data_ptr(), V, H, B,
+                  tgt.data_ptr(), eng._p(rptr), eng._p(ridx), mode, cgt.data_ptr(), ceq.data_ptr(), None,
+                  ws.data_ptr(), wsb, eng._stream())
+        if mode == 0:
+            import ctypes
+            flag = ctypes.c_int(0)
+            eng._call(eng.lib.cast_score_rank_full_status, ws.data_ptr(), B, V, ctypes.byref(flag), eng._stream())
+            if flag.value != 0:
+                raise RuntimeError("score_rank_full: tensor-core pass watchdog fired")
+        return cgt.cpu().numpy(), ceq.cpu().numpy()
+
     # parameter access by role name
     def state_dict(self):
         return {k: v.detach().cpu().clone() for k, v in self.engine.P.items()}
