@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--cpu_steps", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
+    ap.add_argument("--no_eval", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -240,6 +241,28 @@ def main():
     e2e = {"value": world * B * a.steps / t_e2e, "unit": "seq/s", "h2d_bytes_per_step": 3 * B * T * 4,
            "d2h_bytes_per_step": 12, "ms_per_step": t_e2e / a.steps * 1e3}
 
+    # ---- (2b) evaluation throughput (BASELINE metric "eval users/sec"): host candidate arrays in, ranks out, through
+    # the public batched API — forward at maxlen 200 + 101-candidate scoring, and the full-catalog tcgen05 ranking
+    eval_out = None
+    if rank == 0 and not a.no_eval:
+        rs = np.random.RandomState(7)
+        EU, EB = 2048, 512
+        eseq = np.concatenate([b[0] for b in synth_batches(EU // B, B, T, ITEMNUM, seed=99)], 0)[:EU]
+        ecand = rs.randint(1, ITEMNUM + 1, (EU, 101)).astype(np.int32)
+        res = {}
+        for name, fn in (("101", lambda s_, c_: model.score_candidates(s_, c_)),
+                         ("full", lambda s_, c_: model.score_full_catalog(s_, c_[:, 0]))):
+            fn(eseq[:EB], ecand[:EB])  # warm (buffers, smem attributes)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for s0 in range(0, EU, EB):
+                fn(eseq[s0:s0 + EB], ecand[s0:s0 + EB])
+            torch.cuda.synchronize(dev)
+            res[name] = EU / (time.perf_counter() - t0)
+        eval_out = {"users_per_sec_101": res["101"], "users_per_sec_full_catalog": res["full"], "users": EU,
+                    "batch_users": EB, "unit": "users/s",
+                    "note": "host int32 arrays in, ranks out (H2D + forward + scoring + D2H inside the timed region)"}
+
     # ---- (3) per-kernel CUDA-event profile (eager launches on the same stream) -> dominant kernel roofline
     roofline, kernels = None, None
     if rank == 0 and not a.no_profile:
@@ -256,6 +279,8 @@ def main():
                       "input_path": "pre-generated synthetic batches (not the reference sampler)"},
            "e2e": e2e, "gpu_launches": int(launches_per_step) * a.steps, "launches_per_step": int(launches_per_step),
            "clocks": clk}
+    if eval_out is not None:
+        out["eval"] = eval_out
     if roofline is not None:
         out["roofline"] = roofline
         out["kernel_profile"] = kernels
@@ -264,8 +289,9 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": cores, "kind": "port",
                                "sample": f"{a.cpu_steps} training steps of B={B} (fwd+bwd+TF-Adam), PyTorch-CPU oracle"}
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 

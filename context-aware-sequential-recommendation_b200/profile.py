@@ -20,6 +20,14 @@ def _work(name, a, B, T, H, h):
         return 4.0 * B * T * T * H, 4.0 * 5 * B * T * H
     if name == "cast_attn_bwd":   # dP, dQ, dK, dV = 2x forward (algorithmic; recomputation of S not counted)
         return 8.0 * B * T * T * H, 4.0 * 8 * B * T * H
+    if name == "cast_ln_qkv_fwd":   # 3 projections  (a[9]=N, a[10]=H)
+        return 6.0 * a[9] * a[10] * a[10], 4.0 * 5 * a[9] * a[10]
+    if name == "cast_ln_ffn_fwd":   # 2 GEMMs        (a[13]=N, a[14]=H)
+        return 4.0 * a[13] * a[14] * a[14], 4.0 * 4 * a[13] * a[14]
+    if name == "cast_ffn_bwd":      # 2 dgrad + 2 wgrad  (a[14]=N, a[15]=H)
+        return 8.0 * a[14] * a[15] * a[15], 4.0 * 5 * a[14] * a[15]
+    if name == "cast_qkv_bwd":      # 3 dgrad + 3 wgrad  (a[12]=N, a[13]=H)
+        return 12.0 * a[12] * a[13] * a[13], 4.0 * 7 * a[12] * a[13]
     if name in ("cast_layernorm_fwd",):
         return 8.0 * a[3] * a[4], 4.0 * 2 * a[3] * a[4]
     if name in ("cast_layernorm_bwd",):
@@ -45,6 +53,7 @@ def profile_step(model, c, steps=5):
     {name, calls_per_step, ms_per_step, share, tflops, gbs} sorted by time."""
     eng = model.engine
     B, T, H, h = c.B, eng.T, eng.H, eng.h
+    saved_allreduce, eng.grad_allreduce = eng.grad_allreduce, None  # rank-local profiling: no collective in here
     eng.launch_train_step(c)  # warm
     torch.cuda.synchronize(eng.device)
     eng.timing = []
@@ -52,6 +61,7 @@ def profile_step(model, c, steps=5):
         eng.launch_train_step(c)
     torch.cuda.synchronize(eng.device)
     rec, eng.timing = eng.timing, None
+    eng.grad_allreduce = saved_allreduce
     agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
     for name, a, e0, e1 in rec:
         ms = e0.elapsed_time(e1)
@@ -84,7 +94,20 @@ def load_peaks(root):
     return d
 
 
-COMPUTE_BOUND = ("cast_attn_fwd", "cast_attn_bwd", "cast_gemm")
+COMPUTE_BOUND = ("cast_attn_fwd", "cast_attn_bwd", "cast_gemm", "cast_qkv_bwd", "cast_ffn_bwd", "cast_ln_qkv_fwd",
+                 "cast_ln_ffn_fwd")
+
+
+def ncu_traffic(root, name):
+    """DRAM bytes per launch of a C-ABI call from the committed ncu `--set full` capture (profiles/traffic.json:
+    {call: {"dram_bytes": read+write summed over the call's kernels, "source": file}}), or None."""
+    p = os.path.join(root, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(name)
+    return (e["dram_bytes"], e.get("source")) if e else (None, None)
 
 
 def roofline_of_dominant(kernels, B, T, H, args, root):
@@ -92,16 +115,19 @@ def roofline_of_dominant(kernels, B, T, H, args, root):
         return None
     top = kernels[0]
     pk = load_peaks(root)
+    traffic, tsrc = ncu_traffic(root, top["name"])
     if top["name"] in COMPUTE_BOUND:
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         fp32_peak = 2 * 128 * 148 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         return {"kernel": top["name"], "bound": "tensor", "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": top["tflops"] / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "frac": top["tflops"] / peak, "traffic": traffic, "traffic_source": tsrc,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "share_of_step": top["share"], "ms_per_step": top["ms_per_step"],
                 "algorithmic_flops_per_step": top["flops_per_step"],
                 "pipe_used": "fp32 FFMA (fp32 parity 1e-4; tensor cores reserved for catalog scoring)",
                 "fp32_pipe_peak_tflops": fp32_peak, "frac_of_fp32_pipe": top["tflops"] / fp32_peak}
     peak = pk["hbm_gbs"]
     return {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": top["gbs"] / peak, "traffic": None, "peak_source": pk["source"], "share_of_step": top["share"],
+            "frac": top["gbs"] / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": pk["source"],
+            "share_of_step": top["share"],
             "ms_per_step": top["ms_per_step"], "algorithmic_bytes_per_step": top["bytes_per_step"]}
