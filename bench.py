@@ -29,15 +29,38 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C2: SASRec ml-1m-shaped synthetic (6040 users, 3416 items, mean train len 163.5), maxlen=200, hidden=50, " \
-           "blocks=2, heads=1, dropout=0.2"
-USERNUM, ITEMNUM, MEAN_LEN = 6040, 3416, 163.5
+# BASELINE.json configs: the metric is quoted on C2; the others are selectable with --config
+CONFIGS = {
+    "c2": dict(model="sasrec", users=6040, items=3416, mean_len=163.5, T=200, H=50, L=2, h=1, drop=0.2,
+               desc="C2: SASRec ml-1m-shaped synthetic (6040 users, 3416 items, mean train len 163.5), maxlen=200, "
+                    "hidden=50, blocks=2, heads=1, dropout=0.2"),
+    "c1": dict(model="sasrec", users=52024, items=57289, mean_len=7.6, T=50, H=50, L=2, h=1, drop=0.5,
+               desc="C1: SASRec Beauty-shaped synthetic (52024 users, 57289 items, mean len 7.6), maxlen=50, hidden=50, "
+                    "blocks=2, heads=1, dropout=0.5"),
+    "c3": dict(model="cast_1", users=6040, items=3416, mean_len=163.5, T=200, H=50, L=2, h=2, drop=0.2,
+               desc="C3: CAST (cast_1, time-context tower) on ml-1m-shaped synthetic data with time bins, maxlen=200, "
+                    "hidden=50, blocks=2, heads=2, dropout=0.2"),
+    "c4": dict(model="sasrec", users=300000, items=30000, mean_len=12.0, T=50, H=128, L=4, h=4, drop=0.2,
+               desc="C4: Steam/Video-shaped synthetic (300k users, 30k items, mean len 12), maxlen=50, hidden=128, "
+                    "blocks=4, heads=4, dropout=0.2"),
+    "c5": dict(model="sasrec", users=10000000, items=1000000, mean_len=100.0, T=200, H=256, L=2, h=1, drop=0.2,
+               desc="C5: synthetic large catalog (10M users, 1M items, mean len 100), maxlen=200, hidden=256, blocks=2, "
+                    "heads=1, dropout=0.2"),
+}
+CFG = CONFIGS["c2"]
+WORKLOAD, USERNUM, ITEMNUM, MEAN_LEN = CFG["desc"], CFG["users"], CFG["items"], CFG["mean_len"]
+
+
+def select_config(name):
+    global CFG, WORKLOAD, USERNUM, ITEMNUM, MEAN_LEN
+    CFG = CONFIGS[name]
+    WORKLOAD, USERNUM, ITEMNUM, MEAN_LEN = CFG["desc"], CFG["users"], CFG["items"], CFG["mean_len"]
 
 
 def make_args(batch_size):
-    return SimpleNamespace(hidden_units=50, maxlen=200, num_heads=1, num_blocks=2, num_context_blocks=2, max_bins=200,
-                           l2_emb=0.0, lr=1e-3, dropout_rate=0.2, seed=42, batch_size=batch_size, bin_in_hours=48,
-                           log_scale=False)
+    return SimpleNamespace(hidden_units=CFG["H"], maxlen=CFG["T"], num_heads=CFG["h"], num_blocks=CFG["L"],
+                           num_context_blocks=2, max_bins=200, l2_emb=0.0, lr=1e-3, dropout_rate=CFG["drop"], seed=42,
+                           batch_size=batch_size, bin_in_hours=48, log_scale=False)
 
 
 def synth_batches(n_batches, B, T, itemnum, seed):
@@ -47,20 +70,27 @@ def synth_batches(n_batches, B, T, itemnum, seed):
     ranks = np.arange(1, itemnum + 1, dtype=np.float64)
     prob = ranks ** -1.0
     prob /= prob.sum()
+    cdf = np.cumsum(prob)
+    cdf[-1] = 1.0
     out = []
     for _ in range(n_batches):
         seq = np.zeros((B, T), np.int32)
         pos = np.zeros((B, T), np.int32)
         neg = np.zeros((B, T), np.int32)
-        lens = np.clip(rng.lognormal(np.log(MEAN_LEN) - 0.32, 0.8, B), 5, 2000).astype(np.int64)
+        lens = np.clip(rng.lognormal(np.log(MEAN_LEN) - 0.32, 0.8, B), 3, 2000).astype(np.int64)
         for b in range(B):
             n = int(min(lens[b], T + 1))
-            items = rng.choice(itemnum, size=n, p=prob) + 1
+            items = np.searchsorted(cdf, rng.rand(n)) + 1
             k = n - 1
             seq[b, T - k:] = items[:-1][-k:] if k else []
             pos[b, T - k:] = items[1:][-k:] if k else []
             neg[b, T - k:] = rng.randint(1, itemnum + 1, k)
-        out.append((seq, pos, neg))
+        live = seq > 0
+        ts = np.where(live, np.minimum(200, rng.geometric(0.05, (B, T)) - 1), 0).astype(np.int32)
+        ts[:, -1] = 0  # the newest event is always in bin 0 (sampler.py:61-72)
+        hrs = np.where(live, rng.randint(1, 25, (B, T)), 0).astype(np.int32)
+        dys = np.where(live, rng.randint(1, 8, (B, T)), 0).astype(np.int32)
+        out.append((seq, pos, neg, ts, hrs, dys))
     return out
 
 
@@ -116,7 +146,7 @@ def cpu_reference_arm(batch_size, steps, warmup, seed=20191019):
     from oracle import cast_oracle as O
     args = make_args(batch_size)
     torch.set_num_threads(os.cpu_count() or 1)
-    p = O.init_params("sasrec", args, ITEMNUM, seed=42)
+    p = O.init_params(CFG["model"], args, ITEMNUM, seed=42)
     opt = O.TFAdam(p, lr=args.lr)
     batches = synth_batches(2, batch_size, args.maxlen, ITEMNUM, seed)
     gen = torch.Generator().manual_seed(1)
@@ -126,9 +156,10 @@ def cpu_reference_arm(batch_size, steps, warmup, seed=20191019):
         return x * keep / (1.0 - args.dropout_rate)
 
     def step(i):
-        seq, pos, neg = batches[i % len(batches)]
-        b = {"input_seq": torch.from_numpy(seq), "pos": torch.from_numpy(pos), "neg": torch.from_numpy(neg)}
-        return O.train_step("sasrec", p, opt, args, b, drop)
+        seq, pos, neg, ts, hrs, dys = batches[i % len(batches)]
+        b = {"input_seq": torch.from_numpy(seq), "pos": torch.from_numpy(pos), "neg": torch.from_numpy(neg),
+             "time_seq": torch.from_numpy(ts), "hours": torch.from_numpy(hrs), "days": torch.from_numpy(dys)}
+        return O.train_step(CFG["model"], p, opt, args, b, drop)
 
     for i in range(warmup):
         step(i)
@@ -146,11 +177,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch_size", type=int, default=128, help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json workload (default: the "
+                    "one the metric is quoted on)")
     ap.add_argument("--cpu_steps", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
     ap.add_argument("--no_eval", action="store_true")
     a = ap.parse_args()
+    select_config(a.config)
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,7 +211,7 @@ def main():
     torch.cuda.set_device(dev)
     args = make_args(a.batch_size)
     B, T, H = a.batch_size, args.maxlen, args.hidden_units
-    model = cast_b200.SASRec(USERNUM, ITEMNUM, args, device=dev, use_graph=True)
+    model = cast_b200.build_model(CFG["model"], USERNUM, ITEMNUM, 5, args, device=dev, use_graph=True)
     eng = model.engine
     cdist.attach(eng)
     lib = eng.lib
@@ -192,7 +226,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     # ---- (1) device-resident throughput: inputs already in HBM, graph replay, per-step CUDA events
-    dev_batches = [torch.from_numpy(np.stack([x.reshape(-1) for x in b])).to(dev) for b in batches]
+    dev_batches = [(torch.from_numpy(np.stack([x.reshape(-1) for x in b[:3]])).to(dev),
+                    torch.from_numpy(np.stack([x.reshape(-1) for x in b[3:]])).to(dev)) for b in batches]
     model.train_step(None, *batches[0])  # builds buffers, captures the graph(s)
     n0 = lib.cast_launch_count()
     model.train_step(None, *batches[1])
@@ -200,7 +235,9 @@ def main():
     launches_per_step = getattr(model, "launches_per_step", None) or launches_eager
 
     def device_step(i):
-        c.keys3.copy_(dev_batches[i % len(dev_batches)])
+        k3, c3 = dev_batches[i % len(dev_batches)]
+        c.keys3.copy_(k3)
+        c.cids.copy_(c3)
         model.launch(c)
 
     for i in range(a.warmup):
@@ -238,13 +275,13 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     t_e2e = float(t.item())
-    e2e = {"value": world * B * a.steps / t_e2e, "unit": "seq/s", "h2d_bytes_per_step": 3 * B * T * 4,
+    e2e = {"value": world * B * a.steps / t_e2e, "unit": "seq/s", "h2d_bytes_per_step": (6 if len(eng.plan.tables) > 1 else 3) * B * T * 4,
            "d2h_bytes_per_step": 12, "ms_per_step": t_e2e / a.steps * 1e3}
 
     # ---- (2b) evaluation throughput (BASELINE metric "eval users/sec"): host candidate arrays in, ranks out, through
     # the public batched API — forward at maxlen 200 + 101-candidate scoring, and the full-catalog tcgen05 ranking
     eval_out = None
-    if rank == 0 and not a.no_eval:
+    if rank == 0 and not a.no_eval and CFG["model"].startswith("sasrec"):
         rs = np.random.RandomState(7)
         EU, EB = 2048, 512
         eseq = np.concatenate([b[0] for b in synth_batches(EU // B, B, T, ITEMNUM, seed=99)], 0)[:EU]

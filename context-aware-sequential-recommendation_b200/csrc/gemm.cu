@@ -17,6 +17,27 @@ int launch_reduce_partials(const float* partial, int nparts, long count, float* 
 
 constexpr int TM = 64, TN = 64, TK = 16, LDS_ = 68;
 
+#ifndef CAST_EMU
+// tensor-core path (gemm_umma.cu); its epilogue descriptor has the same fields as GemmEpi
+struct UGemmEpi {
+  const float* bias;
+  int relu;
+  float drop_rate;
+  unsigned long long seed;
+  const unsigned long long* step;
+  int site;
+  const float* act;
+  long ld_act;
+  float act_scale;
+  const float* resid;
+  long ldr;
+  const int* row_ids;
+};
+int gemm_umma_launch(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc, long M,
+                     int N, long K, const UGemmEpi& epi, int splits, float* partials, cudaStream_t stream);
+#endif
+static int g_gemm_backend = 0;  // 0 = auto (tensor cores for wide shapes), 1 = FP32 FFMA tiles, 2 = tensor cores
+
 struct GemmEpi {
   const float* bias;   // [N] or null
   int relu;            // max(0, .)
@@ -150,16 +171,26 @@ extern "C" int cast_gemm(const float* A, long sam, long sak, const float* B, lon
   GemmEpi e;
   e.bias = bias; e.relu = relu; e.drop_rate = drop_rate; e.seed = seed; e.step = step; e.site = site;
   e.act = act; e.ld_act = ld_act; e.act_scale = act_scale; e.resid = resid; e.ldr = ldr; e.row_ids = row_ids;
+  if (splits > 1) {
+    if (bias || relu || drop_rate > 0.f || act || resid || row_ids || ldc != N)
+      return set_error(CAST_ERR_BAD_ARG, "gemm: split-K supports no epilogue and needs ldc == N");
+    if (!workspace || workspace_bytes < cast_gemm_workspace_bytes(M, N, splits))
+      return set_error(CAST_ERR_WORKSPACE, "gemm: workspace too small");
+  }
+#ifndef CAST_EMU
+  const bool wide = N >= 64 && K >= 64 && M >= 64;
+  if (g_gemm_backend == 2 || (g_gemm_backend == 0 && wide)) {
+    UGemmEpi ue{bias, relu, drop_rate, seed, step, site, act, ld_act, act_scale, resid, ldr, row_ids};
+    return gemm_umma_launch(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, ue, splits,
+                            splits > 1 ? static_cast<float*>(workspace) : nullptr, (cudaStream_t)stream);
+  }
+#endif
   dim3 grid((unsigned)cdiv(M, TM), (unsigned)cdiv(N, TN), (unsigned)splits);
   if (splits == 1) {
     CAST_LAUNCH(gemm_kernel, grid, dim3(256), 0, (cudaStream_t)stream, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, K,
                 e, (float*)nullptr);
     return check_launch("gemm");
   }
-  if (bias || relu || drop_rate > 0.f || act || resid || row_ids || ldc != N)
-    return set_error(CAST_ERR_BAD_ARG, "gemm: split-K supports no epilogue and needs ldc == N");
-  if (!workspace || workspace_bytes < cast_gemm_workspace_bytes(M, N, splits))
-    return set_error(CAST_ERR_WORKSPACE, "gemm: workspace too small");
   long klen = cdiv(K, splits);
   klen = cdiv(klen, TK) * TK;
   float* part = static_cast<float*>(workspace);
@@ -168,6 +199,12 @@ extern "C" int cast_gemm(const float* A, long sam, long sak, const float* B, lon
   int rc = check_launch("gemm(split)");
   if (rc) return rc;
   return launch_reduce_partials(part, splits, M * (long)N, C, M * (long)N, (float*)nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cast_gemm_set_backend(int which) {
+  if (which < 0 || which > 2) return set_error(CAST_ERR_BAD_ARG, "gemm_set_backend");
+  g_gemm_backend = which;
+  return CAST_OK;
 }
 
 extern "C" size_t cast_colsum_workspace_bytes(long rows, long cols) {

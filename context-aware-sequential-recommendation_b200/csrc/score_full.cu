@@ -153,28 +153,11 @@ struct ScoreFullArgs {
 };
 
 // rows [row0, row0+R) x elements [k0, k0 + 4*slabs) of a row-major fp32 matrix -> tf32 hi / lo slabs
+template <int R_MAX>
 __device__ __forceinline__ void stage_split(unsigned char* __restrict__ hi, unsigned char* __restrict__ lo, int pitch,
                                             const float* __restrict__ src, long ld, long row0, long rows_total, int R,
                                             int k0, int slabs, int H) {
-  for (int idx = threadIdx.x; idx < R * slabs; idx += SF_THREADS) {
-    const int r = idx / slabs, c = idx - r * slabs;
-    const long row = row0 + r;
-    const int k = k0 + 4 * c;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < rows_total) {
-      const float* p = src + row * ld + k;
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (k + e < H) x[e] = __ldg(p + e);
-    }
-    float4 h, l;
-    umma::split_tf32(x[0], h.x, l.x);
-    umma::split_tf32(x[1], h.y, l.y);
-    umma::split_tf32(x[2], h.z, l.z);
-    umma::split_tf32(x[3], h.w, l.w);
-    *reinterpret_cast<float4*>(hi + (size_t)c * pitch + r * 16) = h;
-    *reinterpret_cast<float4*>(lo + (size_t)c * pitch + r * 16) = l;
-  }
+  umma::stage_split_strided<SF_THREADS, R_MAX, SF_SLABS>(hi, lo, pitch, src, ld, 1, row0, rows_total, R, k0, H, slabs);
 }
 
 __global__ void __launch_bounds__(SF_THREADS, 1) score_full_umma_kernel(ScoreFullArgs a) {
@@ -212,13 +195,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) score_full_umma_kernel(ScoreFul
     const int tgt = live ? a.target[me] : -1;
     int gt = 0, eq = 0;
     unsigned band = 0;
-    if (a.nkc == 1) stage_split(Ahi, Alo, SF_A_PITCH, a.users, a.ldu, u0, a.U, SF_M, 0, a.kpad / 4, a.H);
+    if (a.nkc == 1) stage_split<SF_M>(Ahi, Alo, SF_A_PITCH, a.users, a.ldu, u0, a.U, SF_M, 0, a.kpad / 4, a.H);
     for (long j0 = jb; j0 < je && !failed; j0 += SF_N) {
       for (int kc = 0; kc < a.nkc; ++kc) {
         const int k0 = kc * SF_KC;
         const int slabs = (a.kpad - k0 < SF_KC ? a.kpad - k0 : SF_KC) / 4;
-        if (a.nkc > 1) stage_split(Ahi, Alo, SF_A_PITCH, a.users, a.ldu, u0, a.U, SF_M, k0, slabs, a.H);
-        stage_split(Bhi, Blo, SF_B_PITCH, a.table, a.H, j0, a.V, SF_N, k0, slabs, a.H);
+        if (a.nkc > 1) stage_split<SF_M>(Ahi, Alo, SF_A_PITCH, a.users, a.ldu, u0, a.U, SF_M, k0, slabs, a.H);
+        stage_split<SF_N>(Bhi, Blo, SF_B_PITCH, a.table, a.H, j0, a.V, SF_N, k0, slabs, a.H);
         if (kc == 0)
           for (int c = t; c < SF_N; c += SF_THREADS) nrm[c] = (j0 + c < a.V) ? a.inorm[j0 + c] : 0.f;
         umma::fence_smem_to_async();

@@ -115,3 +115,59 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 }  // namespace umma
 }  // namespace cast
+
+namespace cast {
+namespace umma {
+
+// Stage rows [row0, row0+R) x k in [k0, k0 + 4*slabs) of a strided fp32 matrix (element (r,k) at src[r*sr + k*sk]) as
+// tf32 hi / lo slabs (layout in the header comment).  Elements with row >= rows_total or k >= kend are zero.  The
+// thread <-> element mapping follows the unit stride of the source so that global reads coalesce: k-fast sources
+// (sk == 1) walk the 4-element slabs of a row, row-fast sources (sr == 1; i.e. the operand is stored transposed)
+// walk consecutive rows of a slab.  One thread owns ITEMS (row, slab) pairs; all of its global loads are issued
+// before the first conversion so that 4*ITEMS loads are in flight per thread (the loop is latency-bound otherwise),
+// then each pair becomes one 16-byte shared-memory store per half.
+template <int NTHREADS, int R_MAX, int SLABS_MAX>
+__device__ __forceinline__ void stage_split_strided(unsigned char* __restrict__ hi, unsigned char* __restrict__ lo,
+                                                    int pitch, const float* __restrict__ src, long sr, long sk,
+                                                    long row0, long rows_total, int R, long k0, long kend,
+                                                    int slabs) {
+  constexpr int ITEMS = (R_MAX * SLABS_MAX + NTHREADS - 1) / NTHREADS;
+  const bool kfast = (sk == 1);
+  const int total = R * slabs;
+  float x[ITEMS][4];
+  int off[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int idx = threadIdx.x + i * NTHREADS;
+    off[i] = -1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[i][e] = 0.f;
+    if (idx < total) {
+      int r, c;
+      if (kfast) { r = idx / slabs; c = idx - r * slabs; } else { c = idx / R; r = idx - c * R; }
+      off[i] = c * pitch + r * 16;
+      const long row = row0 + r;
+      const long k = k0 + 4 * c;
+      if (row < rows_total) {
+        const float* p = src + row * sr + k * sk;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k + e < kend) x[i][e] = __ldg(p + e * sk);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    if (off[i] < 0) continue;
+    float4 h, l;
+    split_tf32(x[i][0], h.x, l.x);
+    split_tf32(x[i][1], h.y, l.y);
+    split_tf32(x[i][2], h.z, l.z);
+    split_tf32(x[i][3], h.w, l.w);
+    *reinterpret_cast<float4*>(hi + off[i]) = h;
+    *reinterpret_cast<float4*>(lo + off[i]) = l;
+  }
+}
+
+}  // namespace umma
+}  // namespace cast
