@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
     ap.add_argument("--no_eval", action="store_true")
+    ap.add_argument("--shard_item_table", action="store_true", help="row-shard the item-table update across ranks "
+                    "(default for --config c5 when --gpus > 1)")
     a = ap.parse_args()
     select_config(a.config)
     a.warmup = max(a.warmup, 3)
@@ -211,9 +213,11 @@ def main():
     torch.cuda.set_device(dev)
     args = make_args(a.batch_size)
     B, T, H = a.batch_size, args.maxlen, args.hidden_units
-    model = cast_b200.build_model(CFG["model"], USERNUM, ITEMNUM, 5, args, device=dev, use_graph=True)
+    shard = world > 1 and (a.shard_item_table or a.config == "c5")
+    model = cast_b200.build_model(CFG["model"], USERNUM, ITEMNUM, 5, args, device=dev, use_graph=True,
+                                  item_row_align=world if shard else 1)
     eng = model.engine
-    cdist.attach(eng)
+    cdist.attach(eng, shard_item_table=shard)
     lib = eng.lib
     batches = synth_batches(8, B, T, ITEMNUM, seed=20191019 + 1000 * rank)
     c = eng.ctx(B)
@@ -311,7 +315,7 @@ def main():
            "warmup": a.warmup, "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                      "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) between timed steps",
+                      "parallelism": f"dp{world}" + ("+item-table-row-sharded-update" if shard else ""), "l2": "flushed (256 MiB write) between timed steps",
                       "timing": "per-step CUDA events on the launch stream, max over ranks",
                       "input_path": "pre-generated synthetic batches (not the reference sampler)"},
            "e2e": e2e, "gpu_launches": int(launches_per_step) * a.steps, "launches_per_step": int(launches_per_step),

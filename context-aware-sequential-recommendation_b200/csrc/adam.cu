@@ -39,6 +39,33 @@ __global__ void adam_step_kernel(float* __restrict__ w, const float* __restrict_
   }
 }
 
+// same update, four elements per thread (16-byte loads/stores); n4 = n/4, pointers 16-byte aligned
+__global__ void adam_step_vec4_kernel(float4* __restrict__ w, const float4* __restrict__ grad, float4* __restrict__ m,
+                                      float4* __restrict__ v, long n4, float lr, float b1, float b2, float eps,
+                                      const float* __restrict__ gdenom, float l2, long l2_lo, long l2_hi,
+                                      const AdamState* __restrict__ st) {
+  const float gs = gdenom ? 1.0f / *gdenom : 1.0f;
+  const float lr_t = lr * sqrtf(1.0f - st->b2p) / (1.0f - st->b1p);
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 wi = w[i], gi = grad[i], mi = m[i], vi = v[i];
+    float wv[4] = {wi.x, wi.y, wi.z, wi.w}, gv[4] = {gi.x, gi.y, gi.z, gi.w};
+    float mv[4] = {mi.x, mi.y, mi.z, mi.w}, vv[4] = {vi.x, vi.y, vi.z, vi.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long idx = 4 * i + e;
+      float g = gv[e] * gs;
+      if (idx >= l2_lo && idx < l2_hi) g = fmaf(l2, wv[e], g);
+      mv[e] = b1 * mv[e] + omb1 * g;
+      vv[e] = b2 * vv[e] + omb2 * g * g;
+      wv[e] = wv[e] - lr_t * mv[e] / (sqrtf(vv[e]) + eps);
+    }
+    m[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    v[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    w[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  }
+}
+
 __global__ void adam_advance_kernel(AdamState* st, float b1, float b2) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->b1p *= b1;
@@ -58,17 +85,38 @@ extern "C" int cast_adam_init_state(void* state, float beta1, float beta2, void*
   return check_launch("adam_init");
 }
 
+// the update of one contiguous range; `advance` != 0 also steps the beta powers / step counter afterwards (callers that
+// update several ranges of one model — a row shard of the item table plus the replicated weights — advance once)
+extern "C" int cast_adam_tf_range(float* w, const float* grad, float* m, float* v, long n, float lr, float beta1,
+                                  float beta2, float eps, const float* gdenom, float l2, long l2_lo, long l2_hi,
+                                  void* state, int advance, void* stream) {
+  if (!w || !grad || !m || !v || !state || n <= 0) return set_error(CAST_ERR_BAD_ARG, "adam_tf_range");
+  const bool vec = (n % 4 == 0) && ((((uintptr_t)w | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  int rc;
+  if (vec) {
+    long g = cdiv(n / 4, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    CAST_LAUNCH(adam_step_vec4_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream,
+                reinterpret_cast<float4*>(w), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(m),
+                reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps, gdenom, l2, l2_lo, l2_hi,
+                static_cast<const AdamState*>(state));
+  } else {
+    long g = cdiv(n, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    CAST_LAUNCH(adam_step_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, w, grad, m, v, n, lr, beta1,
+                beta2, eps, gdenom, l2, l2_lo, l2_hi, static_cast<const AdamState*>(state));
+  }
+  if ((rc = check_launch("adam_step"))) return rc;
+  if (advance) {
+    CAST_LAUNCH(adam_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, static_cast<AdamState*>(state),
+                beta1, beta2);
+    return check_launch("adam_advance");
+  }
+  return CAST_OK;
+}
+
 extern "C" int cast_adam_tf_step(float* w, const float* grad, float* m, float* v, long n, float lr, float beta1,
                                  float beta2, float eps, const float* gdenom, float l2, long l2_lo, long l2_hi,
                                  void* state, void* stream) {
-  if (!w || !grad || !m || !v || !state || n <= 0) return set_error(CAST_ERR_BAD_ARG, "adam_tf_step");
-  long g = cdiv(n, 256);
-  if (g > 148 * 8) g = 148 * 8;
-  CAST_LAUNCH(adam_step_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, w, grad, m, v, n, lr, beta1,
-              beta2, eps, gdenom, l2, l2_lo, l2_hi, static_cast<const AdamState*>(state));
-  int rc = check_launch("adam_step");
-  if (rc) return rc;
-  CAST_LAUNCH(adam_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, static_cast<AdamState*>(state), beta1,
-              beta2);
-  return check_launch("adam_advance");
+  return cast_adam_tf_range(w, grad, m, v, n, lr, beta1, beta2, eps, gdenom, l2, l2_lo, l2_hi, state, 1, stream);
 }

@@ -82,13 +82,19 @@ def model_plan(model: str, args) -> SimpleNamespace:
     return p
 
 
-def param_shapes(plan, args, itemnum: int):
-    """Ordered (name, shape, fan_in, fan_out | None) — tables first so the l2_emb region is contiguous."""
+def param_shapes(plan, args, itemnum: int, item_row_align: int = 1):
+    """Ordered (name, shape, fan_in, fan_out | None) — tables first so the l2_emb region is contiguous.  The item
+    table comes first and is followed by `item_emb.pad` zero rows up to a multiple of item_row_align rows, so that
+    its region of the flat buffers splits evenly into row shards (dist.attach(shard_item_table=True))."""
     H, T = args.hidden_units, args.maxlen
     out = []
     rows = {"item_emb": itemnum + 1, "time_emb": args.max_bins + 1, **TABLE_ROWS}
     for t in plan.tables:
         out.append((t, (rows[t], H), rows[t], H))
+        if t == "item_emb":
+            pad = (-rows[t]) % max(1, item_row_align)
+            if pad:
+                out.append(("item_emb.pad", (pad, H), None, 0.0))
     if plan.learned_pos:
         out.append(("pos_emb", (T, H), T, H))
     n_tables = len(out)
@@ -117,7 +123,8 @@ def param_shapes(plan, args, itemnum: int):
 class Engine:
     """Owns parameters, optimizer state, activations and launches.  One instance per process / GPU."""
 
-    def __init__(self, model: str, usernum: int, itemnum: int, args, device=None, lib=None, seed: Optional[int] = None):
+    def __init__(self, model: str, usernum: int, itemnum: int, args, device=None, lib=None, seed: Optional[int] = None,
+                 item_row_align: int = 1):
         self.lib = lib if lib is not None else _lib.load_library()
         self.timing = None
         self.use_fused = True
@@ -137,7 +144,8 @@ class Engine:
         self.l2 = float(getattr(args, "l2_emb", 0.0))
         self.seed = int(seed if seed is not None else (getattr(args, "seed", 0) or 0))
         self.beta1, self.beta2, self.eps = 0.9, 0.98, 1e-8  # models/sasrec.py:120 (beta2=0.98), TF defaults else
-        shapes, n_tables = param_shapes(self.plan, args, itemnum)
+        shapes, n_tables = param_shapes(self.plan, args, itemnum, item_row_align)
+        self.item_rows_padded = (itemnum + 1) + (-(itemnum + 1)) % max(1, item_row_align)
         self.shapes = shapes
         total = sum(int(np.prod(s)) for _, s, _, _ in shapes)
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -168,6 +176,8 @@ class Engine:
         self._ctx: Dict[int, SimpleNamespace] = {}
         self.world_size = 1
         self.grad_allreduce = None  # set by dist.attach(); called between backward and Adam
+        self.shard = None           # set by dist.attach(shard_item_table=True): row-sharded item-table update
+        self.after_adam = None      # ... and the all-gather of the updated rows that follows Adam
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -557,10 +567,28 @@ class Engine:
 
     def adam(self, c):
         # gradients are divided by sums[2] = sum(istarget) (global under data parallelism) inside the kernel
+        if self.shard is not None:
+            return self._adam_sharded()
         self._call(self.lib.cast_adam_tf_step, self.w.data_ptr(), self.g.data_ptr(), self.m.data_ptr(),
                    self.v.data_ptr(), self.n_params, self.lr, self.beta1, self.beta2, self.eps,
                    self.sums[2:].data_ptr(), self.l2, 0, self.l2_hi if self.l2 else 0, self.adam_state.data_ptr(),
                    self._stream())
+
+    def _adam_sharded(self):
+        """Row-sharded item table (dist.attach(shard_item_table=True)): this rank applies TF-Adam to its own rows
+        (gradient = the reduce-scattered shard) and to the replicated remainder; the beta powers advance once."""
+        sh = self.shard
+        lo, n = sh.lo, sh.n            # element range of the own shard inside the item-table region
+        rest = sh.region               # first element after the (padded) item table
+        nrest = self.n_params - rest
+        l2 = self.l2
+        self._call(self.lib.cast_adam_tf_range, self.w[lo:].data_ptr(), sh.g_shard.data_ptr(),
+                   self.m[lo:].data_ptr(), self.v[lo:].data_ptr(), n, self.lr, self.beta1, self.beta2, self.eps,
+                   self.sums[2:].data_ptr(), l2, 0, n if l2 else 0, self.adam_state.data_ptr(), 0, self._stream())
+        self._call(self.lib.cast_adam_tf_range, self.w[rest:].data_ptr(), self.g[rest:].data_ptr(),
+                   self.m[rest:].data_ptr(), self.v[rest:].data_ptr(), nrest, self.lr, self.beta1, self.beta2,
+                   self.eps, self.sums[2:].data_ptr(), l2, 0, max(0, self.l2_hi - rest) if l2 else 0,
+                   self.adam_state.data_ptr(), 1, self._stream())
 
     def launch_fwd_bwd(self, c):
         self.forward(c, train=True)
@@ -573,3 +601,5 @@ class Engine:
         if self.grad_allreduce is not None:
             self.grad_allreduce(c)
         self.adam(c)
+        if self.after_adam is not None:
+            self.after_adam()

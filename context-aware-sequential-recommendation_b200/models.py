@@ -20,9 +20,11 @@ from .engine import Engine, MODELS
 class _Model:
     registry_name = "sasrec"
 
-    def __init__(self, usernum, itemnum, args, *, device=None, use_graph: bool = True, _lib=None, seed=None):
+    def __init__(self, usernum, itemnum, args, *, device=None, use_graph: bool = True, _lib=None, seed=None,
+                 item_row_align: int = 1):
         self.usernum, self.itemnum, self.args = usernum, itemnum, args
-        self.engine = Engine(self.registry_name, usernum, itemnum, args, device=device, lib=_lib, seed=seed)
+        self.engine = Engine(self.registry_name, usernum, itemnum, args, device=device, lib=_lib, seed=seed,
+                             item_row_align=item_row_align)
         self.use_graph = bool(use_graph) and self.engine.device.type == "cuda"
         self.attention_weights = None
         self.launches_per_step = None
@@ -90,6 +92,8 @@ class _Model:
             if eng.grad_allreduce is not None:
                 eng.grad_allreduce(c)
             c.graph[1].replay()
+            if eng.after_adam is not None:
+                eng.after_adam()
         else:
             eng.launch_train_step(c)
 

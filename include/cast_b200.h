@@ -183,6 +183,11 @@ int cast_scatter_rows(const int* keys /* [nsrc*N] */, int nsrc, long N, const fl
 int cast_adam_init_state(void* state /* 16 bytes */, float beta1, float beta2, void* stream);
 int cast_adam_tf_step(float* w, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
                       float eps, const float* gdenom, float l2, long l2_lo, long l2_hi, void* state, void* stream);
+/* The same update on one contiguous range; advance != 0 steps the state afterwards.  A rank that owns a row shard of
+ * the item table updates {its shard, the replicated weights} with two calls and advances once. */
+int cast_adam_tf_range(float* w, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
+                       float eps, const float* gdenom, float l2, long l2_lo, long l2_hi, void* state, int advance,
+                       void* stream);
 
 /* sasrec.py:93-97 + util.py:318-321: logits[u,c] = seq_last[u,:] . table0[cand[u,c],:] (sequential-k, unfused
  * multiply/add so the order is reproducible), and for candidate 0 the pair (count_greater, count_equal_excl_self)

@@ -30,7 +30,7 @@ def _load_batch(eng, gb, lo, hi):
     return c
 
 
-def _worker(rank, world, port, model, out):
+def _worker(rank, world, port, model, out, shard=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     from cast_b200 import dist as cdist
@@ -40,8 +40,9 @@ def _worker(rank, world, port, model, out):
     B, T, H = 4, 10, 12
     args = make_args(hidden_units=H, maxlen=T, num_heads=2, num_blocks=1, dropout_rate=0.0)
     gb = golden_batch(B=B, T=T)
-    eng = Engine(model, 80, 300, args, device=dev, lib=lib, seed=5 + rank)  # different init per rank on purpose
-    cdist.attach(eng)                                                       # rank 0's parameters win
+    eng = Engine(model, 80, 300, args, device=dev, lib=lib, seed=5 + rank,  # different init per rank on purpose
+                 item_row_align=world if shard else 1)
+    cdist.attach(eng, shard_item_table=shard)                               # rank 0's parameters win
     per = B // world
     c = _load_batch(eng, gb, rank * per, (rank + 1) * per)
     eng.launch_train_step(c)
@@ -49,7 +50,7 @@ def _worker(rank, world, port, model, out):
     cdist.reduce_rank_histogram(hist)
     lo, hi = cdist.shard_users(11, rank, world)
     if rank == 0:
-        single = Engine(model, 80, 300, args, device=dev, lib=lib, seed=5)
+        single = Engine(model, 80, 300, args, device=dev, lib=lib, seed=5, item_row_align=world if shard else 1)
         cs = _load_batch(single, gb, 0, B)
         single.launch_train_step(cs)
         res = {"g_dp": eng.gbuf.numpy().copy(), "g_1": single.gbuf.numpy().copy(), "w_dp": eng.w.numpy().copy(),
@@ -79,3 +80,22 @@ def test_two_rank_step_equals_single_process(tmp_path, model):
         assert rel_err(g_dp[off:off + n], g_1[off:off + n]) <= 2e-5, k
     assert np.array_equal(r["hist"], np.array([3] * 10 + [14]))
     assert r["shard"] == (0, 6)
+
+
+@pytest.mark.emu
+def test_row_sharded_item_table_update_equals_single_process(tmp_path):
+    """dist.attach(shard_item_table=True): reduce-scatter of the table gradient, Adam on the own row shard, all-gather
+    of the updated rows — the parameters after the step must equal the single-process step (301 rows padded to 302)."""
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), "sasrec", out, True), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    w_dp, w_1, g_1 = r["w_dp"], r["w_1"], r["g_1"][:len(r["w_1"])]
+    assert "item_emb.pad" in r["offsets"]
+    cnt = r["g_1"][-2]
+    sig = np.abs(g_1 / cnt) > 1e-5          # elements whose Adam step is not dominated by epsilon / rounding
+    assert sig.sum() > 1000
+    assert np.abs(w_dp[sig] - w_1[sig]).max() <= 2e-6
+    n_item = r["sizes"]["item_emb"] + r["sizes"]["item_emb.pad"]   # table rows nobody touched must not move at all
+    untouched = g_1[:n_item] == 0
+    assert untouched.sum() > 1000
+    assert np.array_equal(w_dp[:n_item][untouched], w_1[:n_item][untouched])
