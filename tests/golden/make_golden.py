@@ -13,6 +13,9 @@ Outputs (tests/golden/):
                          (seq, item_idx, timeseq, hours, days), the ranks they derived from a deterministic
                          fake scorer, and the (NDCG@10, HR@10) they returned
   ref_timebins.npz       `util.get_timedelta_bin` (linear and log) and `get_delta_range` known answers
+  ml1m_sasrec_ckpt.npz   the trained weights of the reference's shipped ml-1m SASRec checkpoint
+                         (saved_models/ml-1m.txt/sasrec_baseline_10-19-2019-21-23-42/model.ckpt, global_step 9400),
+                         read with this repo's TF-free bundle reader and stored under role names
 """
 import os
 import random
@@ -112,7 +115,21 @@ def main():
     lg = [util.get_timedelta_bin(d, max_bins=200, log_scale=True, min_ts=min_td, max_ts=max_td) for d in deltas]
     np.savez_compressed(os.path.join(HERE, "ref_timebins.npz"), deltas=deltas, lin24=np.array(lin24),
                         lin48=np.array(lin48), log=np.array(lg), delta_range=np.array([min_td, max_td]))
-    print("wrote fixtures:", usernum, itemnum, len(q.items), "batches; eval users", len(fm.calls))
+    # ---- trained reference weights (TF checkpoint shipped with the reference: ml-1m SASRec, epoch 200), role-named
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)),
+                                    "context-aware-sequential-recommendation_b200"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ckpt", os.path.join(
+        os.path.dirname(os.path.dirname(HERE)), "context-aware-sequential-recommendation_b200", "checkpoint.py"))
+    ck = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ck)
+    prefix = os.path.join(refdata.REFERENCE_ROOT, "saved_models", "ml-1m.txt", "sasrec_baseline_10-19-2019-21-23-42",
+                          "model.ckpt")
+    tfv = ck.read_bundle(prefix)
+    roles = ck.to_role_names("sasrec", tfv, 2)
+    np.savez_compressed(os.path.join(HERE, "ml1m_sasrec_ckpt.npz"), global_step=tfv["global_step"], **roles)
+    print("wrote fixtures:", usernum, itemnum, len(q.items), "batches; eval users", len(fm.calls),
+          "; checkpoint tensors", len(roles))
 
 
 if __name__ == "__main__":
