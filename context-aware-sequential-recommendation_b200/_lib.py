@@ -51,7 +51,7 @@ SIGNATURES = {
     "cast_adam_tf_step": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, P]),
     "cast_adam_tf_range": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, I, P]),
     "cast_score_rank_cand": (I, [P, L, P, I, I, L, P, I, P, P, P, P]),
-    "cast_score_rank_full_workspace_bytes": (SZ, [L, I]),
+    "cast_score_rank_full_workspace_bytes": (SZ, [L, I, I]),
     "cast_score_rank_full": (I, [P, L, P, I, I, L, P, P, P, I, P, P, P, P, SZ, P]),
     "cast_score_rank_full_status": (I, [P, L, I, P, P]),
 }

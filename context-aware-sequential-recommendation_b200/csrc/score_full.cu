@@ -47,6 +47,17 @@ __global__ void item_norm_kernel(const float* __restrict__ table, int V, int H, 
   if (lane == 0) inorm[j] = sqrtf(s) * NORM_SLACK;
 }
 
+// tnorm[t] = max of inorm over the 256 items of tile t (one warp per tile)
+__global__ void tile_norm_kernel(const float* __restrict__ inorm, int V, int tile, float* __restrict__ tnorm) {
+  const int lane = threadIdx.x & 31;
+  const long t = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t * tile >= V) return;
+  float m = 0.f;
+  for (long j = t * tile + lane; j < (t + 1) * tile && j < V; j += 32) m = fmaxf(m, inorm[j]);
+  m = warp_max(m);
+  if (lane == 0) tnorm[t] = m;
+}
+
 // per user: |u|_2 bound and the canonical target score (target id outside [1,V) scores 0 like the zero-pad row)
 __global__ void user_prep_kernel(const float* __restrict__ users, long ldu, const float* __restrict__ table, int V,
                                  int H, long U, const int* __restrict__ target, float* __restrict__ unorm,
@@ -121,26 +132,74 @@ __global__ void rated_subtract_kernel(const float* __restrict__ users, long ldu,
 
 #ifndef CAST_EMU
 // ------------------------------------------------------------------------------------------------ tensor-core path
-constexpr int SF_THREADS = 256;
+// Warp-specialised pipeline, one persistent CTA per SM:
+//   warp 0 (one lane)  producer : TMA 1-D bulk copies (cp.async.bulk) of pre-split operand chunks into a 2-stage
+//                                 shared-memory ring, completion counted on `full[s]` as transaction bytes
+//   warp 1 (one lane)  MMA      : waits full[s], issues 3 x tcgen05.mma per 8 K-elements into one of TWO TMEM
+//                                 accumulators (2 x 256 columns), tcgen05.commit -> empty[s] (stage free) and, after the
+//                                 last K chunk of a tile, -> tfull[acc]
+//   warps 2-9          epilogue : wait tfull[acc], tcgen05.ld the 128 x 256 tile (thread <-> user row, two warps per
+//                                 lane quarter split the columns), two compares per element against per-(user, tile)
+//                                 thresholds, band pairs appended to a list, then arrive on tempty[acc]
+// so the copy of chunk k+1, the MMAs of chunk k and the epilogue of the previous tile overlap.  Operands are split
+// into tf32 hi/lo ONCE by presplit_kernel into the exact shared-memory image of a chunk (K-major slabs, see umma.cuh),
+// so the hot loop executes no conversion instructions at all: the item table is static for a whole evaluation.
+constexpr int SF_EPI_WARPS = 8;                // two warps per TMEM lane quarter (each takes half of the columns)
+constexpr int SF_THREADS = 64 + 32 * SF_EPI_WARPS;
 constexpr int SF_M = 128;                      // users per tile  (UMMA M)
-constexpr int SF_N = 256;                      // items per tile  (UMMA N) = TMEM columns
-constexpr int SF_KC = 64;                      // K elements staged per chunk
+constexpr int SF_N = 256;                      // items per tile  (UMMA N); 2 accumulators = all 512 TMEM columns
+constexpr int SF_KC = 32;                      // K elements per pipeline chunk
+constexpr int SF_SLABS = SF_KC / 4;
 constexpr int SF_A_PITCH = SF_M * 16 + 16;     // bytes between K slabs of the user tile
 constexpr int SF_B_PITCH = SF_N * 16 + 16;     // bytes between K slabs of the item tile
-constexpr int SF_SLABS = SF_KC / 4;
-constexpr size_t SF_SMEM = 2 * (size_t)SF_SLABS * (SF_A_PITCH + SF_B_PITCH) + SF_N * sizeof(float) + 128;
+constexpr int SF_ABYTES = 2 * SF_SLABS * SF_A_PITCH;   // one user-tile chunk: hi slabs then lo slabs
+constexpr int SF_BBYTES = 2 * SF_SLABS * SF_B_PITCH;   // one item-tile chunk
+constexpr int SF_STAGES = 2;
+constexpr size_t SF_SMEM = (size_t)SF_STAGES * (SF_ABYTES + SF_BBYTES) + 128;
+
+// X [R, ld] row-major fp32 -> out[tile][kchunk][hi|lo][slab][TR rows x 16 B (+16 B pad)]; zero beyond R rows / H cols
+template <int TR>
+__global__ void presplit_kernel(const float* __restrict__ X, long ld, long R, int H, int nkc,
+                                unsigned char* __restrict__ out) {
+  constexpr int PITCH = TR * 16 + 16;
+  constexpr int CBYTES = 2 * SF_SLABS * PITCH;
+  const long tile = blockIdx.x;
+  const int kc = blockIdx.y;
+  unsigned char* dst = out + ((size_t)tile * nkc + kc) * CBYTES;
+  for (int idx = threadIdx.x; idx < TR * SF_SLABS; idx += blockDim.x) {
+    const int r = idx / SF_SLABS, c = idx - r * SF_SLABS;
+    const long row = tile * TR + r;
+    const int k = kc * SF_KC + 4 * c;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < R) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (k + e < H) x[e] = __ldg(X + row * ld + k + e);
+    }
+    float4 h, l;
+    umma::split_tf32(x[0], h.x, l.x);
+    umma::split_tf32(x[1], h.y, l.y);
+    umma::split_tf32(x[2], h.z, l.z);
+    umma::split_tf32(x[3], h.w, l.w);
+    *reinterpret_cast<float4*>(dst + (size_t)c * PITCH + r * 16) = h;
+    *reinterpret_cast<float4*>(dst + (size_t)(SF_SLABS + c) * PITCH + r * 16) = l;
+  }
+}
 
 struct ScoreFullArgs {
   const float* users;
   long ldu;
   const float* table;
+  const unsigned char* apre;   // pre-split user tiles
+  const unsigned char* bpre;   // pre-split item tiles
   const float* inorm;
+  const float* tnorm;          // per item tile: max of inorm over the tile
   const float* tscore;
   const float* unorm;
   const int* target;
   int V, H;
   long U;
-  int nkc;               // K chunks of SF_KC elements (last one may be shorter)
+  int nkc;               // K chunks of SF_KC elements
   int kpad;              // H rounded up to 8
   long items_per_split;  // multiple of SF_N
   int nsplit;
@@ -149,125 +208,207 @@ struct ScoreFullArgs {
   int* cgt;
   int* ceq;
   unsigned long long* stats;  // [0] band candidates re-scored exactly  (optional)
+  unsigned long long* band_count;   // device counter of deferred band pairs
+  int2* band_pairs;                 // (user, item) pairs inside the error band, re-scored by band_rescore_kernel
+  unsigned long long band_cap;
   int* err;
 };
 
-// rows [row0, row0+R) x elements [k0, k0 + 4*slabs) of a row-major fp32 matrix -> tf32 hi / lo slabs
-template <int R_MAX>
-__device__ __forceinline__ void stage_split(unsigned char* __restrict__ hi, unsigned char* __restrict__ lo, int pitch,
-                                            const float* __restrict__ src, long ld, long row0, long rows_total, int R,
-                                            int k0, int slabs, int H) {
-  umma::stage_split_strided<SF_THREADS, R_MAX, SF_SLABS>(hi, lo, pitch, src, ld, 1, row0, rows_total, R, k0, H, slabs);
+// Deferred exact decisions: one thread per (user, item) pair that the tensor-core pass could not classify.  The
+// canonical dot is a sequential chain, so the parallelism is across pairs (inline in the epilogue it would stall a
+// whole warp per pair: measured 9 ms -> see profiles/r01e).
+__global__ void band_rescore_kernel(const float* __restrict__ users, long ldu, const float* __restrict__ table, int H,
+                                    const float* __restrict__ tscore, const int2* __restrict__ pairs,
+                                    const unsigned long long* __restrict__ count, unsigned long long cap,
+                                    int* __restrict__ cgt, int* __restrict__ ceq) {
+  unsigned long long n = *count;
+  if (n > cap) n = cap;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const int2 p = pairs[i];
+    const float ex = canonical_dot(users + (long)p.x * ldu, table + (long)p.y * H, H);
+    const float t = tscore[p.x];
+    if (ex > t) atomicAdd(&cgt[p.x], 1);
+    else if (ex == t) atomicAdd(&ceq[p.x], 1);
+  }
 }
 
 __global__ void __launch_bounds__(SF_THREADS, 1) score_full_umma_kernel(ScoreFullArgs a) {
   extern __shared__ __align__(128) unsigned char sf_smem[];
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t full[SF_STAGES], empty[SF_STAGES], tfull[2], tempty[2], afull, adone;
   __shared__ uint32_t tmem_slot;
-  unsigned char* Ahi = sf_smem;
-  unsigned char* Alo = Ahi + SF_SLABS * SF_A_PITCH;
-  unsigned char* Bhi = Alo + SF_SLABS * SF_A_PITCH;
-  unsigned char* Blo = Bhi + SF_SLABS * SF_B_PITCH;
-  float* nrm = reinterpret_cast<float*>(Blo + SF_SLABS * SF_B_PITCH);
-
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, SF_N);
-  if (t == 0) umma::mbar_init(&mbar, 1);
+  // small K: the user tile stays resident (loaded once per work unit) and the ring holds item chunks only
+  const bool a_res = a.nkc <= SF_STAGES;
+  unsigned char* Ares = sf_smem;
+  unsigned char* ring = a_res ? sf_smem + (size_t)SF_STAGES * SF_ABYTES : sf_smem;
+  const int stage_bytes = a_res ? SF_BBYTES : SF_ABYTES + SF_BBYTES;
+  if (warp == 1) umma::tmem_alloc(&tmem_slot, 2 * SF_N);
+  if (t == 0) {
+    for (int i = 0; i < SF_STAGES; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], SF_EPI_WARPS); }
+    umma::mbar_init(&afull, 1);
+    umma::mbar_init(&adone, 1);
+  }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t idesc = umma::idesc_tf32(SF_M, SF_N);
-  const uint32_t q = warp & 3, half = warp >> 2;  // TMEM lane quarter this warp may read; column half it counts
-  uint32_t parity = 0;
   bool failed = false;
 
-  for (long unit = blockIdx.x; unit < a.nunits && !failed; unit += gridDim.x) {
-    const long ut = unit / a.nsplit;
-    const int sp = (int)(unit - ut * a.nsplit);
-    const long u0 = ut * SF_M;
-    const long jb = (long)sp * a.items_per_split;
-    const long je = jb + a.items_per_split < a.V ? jb + a.items_per_split : a.V;
-    const long me = u0 + q * 32 + lane;  // the user row whose accumulator lane this thread reads
-    const bool live = me < a.U;
-    const float tsc = live ? a.tscore[me] : 0.f;
-    const float nu = live ? a.unorm[me] : 0.f;
-    const int tgt = live ? a.target[me] : -1;
-    int gt = 0, eq = 0;
-    unsigned band = 0;
-    if (a.nkc == 1) stage_split<SF_M>(Ahi, Alo, SF_A_PITCH, a.users, a.ldu, u0, a.U, SF_M, 0, a.kpad / 4, a.H);
-    for (long j0 = jb; j0 < je && !failed; j0 += SF_N) {
-      for (int kc = 0; kc < a.nkc; ++kc) {
-        const int k0 = kc * SF_KC;
-        const int slabs = (a.kpad - k0 < SF_KC ? a.kpad - k0 : SF_KC) / 4;
-        if (a.nkc > 1) stage_split<SF_M>(Ahi, Alo, SF_A_PITCH, a.users, a.ldu, u0, a.U, SF_M, k0, slabs, a.H);
-        stage_split<SF_N>(Bhi, Blo, SF_B_PITCH, a.table, a.H, j0, a.V, SF_N, k0, slabs, a.H);
-        if (kc == 0)
-          for (int c = t; c < SF_N; c += SF_THREADS) nrm[c] = (j0 + c < a.V) ? a.inorm[j0 + c] : 0.f;
-        umma::fence_smem_to_async();
-        __syncthreads();
-        if (t == 0) {
-          umma::fence_after_sync();
-          const uint32_t ah = umma::smem_u32(Ahi), al = umma::smem_u32(Alo);
-          const uint32_t bh = umma::smem_u32(Bhi), bl = umma::smem_u32(Blo);
-          for (int s = 0; s < slabs / 2; ++s) {
-            const uint64_t dah = umma::smem_desc(ah + 2 * s * SF_A_PITCH, SF_A_PITCH, 128);
-            const uint64_t dal = umma::smem_desc(al + 2 * s * SF_A_PITCH, SF_A_PITCH, 128);
-            const uint64_t dbh = umma::smem_desc(bh + 2 * s * SF_B_PITCH, SF_B_PITCH, 128);
-            const uint64_t dbl = umma::smem_desc(bl + 2 * s * SF_B_PITCH, SF_B_PITCH, 128);
-            umma::mma_tf32(tmem, dal, dbh, idesc, (kc > 0 || s > 0) ? 1u : 0u);
-            umma::mma_tf32(tmem, dah, dbl, idesc, 1u);
-            umma::mma_tf32(tmem, dah, dbh, idesc, 1u);
-          }
-          umma::mma_commit(&mbar);
+  if (warp == 0) {
+    // ================================================================== producer
+    if (lane == 0) {
+      uint32_t it = 0;          // ring position counter
+      uint32_t units_done = 0;
+      for (long unit = blockIdx.x; unit < a.nunits && !failed; unit += gridDim.x, ++units_done) {
+        const long ut = unit / a.nsplit;
+        const int sp = (int)(unit - ut * a.nsplit);
+        const long jb = (long)sp * a.items_per_split;
+        const long je = jb + a.items_per_split < a.V ? jb + a.items_per_split : a.V;
+        const unsigned char* asrc = a.apre + (size_t)ut * a.nkc * SF_ABYTES;
+        if (a_res) {
+          if (units_done > 0 && !umma::mbar_wait(&adone, (units_done - 1) & 1)) { failed = true; break; }
+          umma::mbar_arrive_expect_tx(&afull, (uint32_t)(a.nkc * SF_ABYTES));
+          for (int kc = 0; kc < a.nkc; ++kc) umma::bulk_g2s(Ares + (size_t)kc * SF_ABYTES, asrc + (size_t)kc * SF_ABYTES,
+                                                            SF_ABYTES, &afull);
         }
-        // the MMAs read shared memory asynchronously: nobody restages (or reads the accumulator) before they finish
-        const bool ok = umma::mbar_wait(&mbar, parity);
-        parity ^= 1u;
-        if (!__syncthreads_and(ok ? 1 : 0)) {
-          failed = true;
-          break;
-        }
-        umma::fence_after_sync();
-      }
-      if (failed) break;
-      // ---- epilogue: thread <-> user row (TMEM lane), 128 of the 256 columns per warp half
-#pragma unroll 1
-      for (int cb = 0; cb < SF_N / 2; cb += 32) {
-        const int col0 = (int)half * (SF_N / 2) + cb;
-        float v[32];
-        umma::tmem_ld32(tmem + ((q * 32u) << 16) + (uint32_t)col0, v);
-        if (live) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const long item = j0 + col0 + e;
-            if (item < 1 || item >= je || item == tgt) continue;
-            const float d = a.cbound * nu * nrm[col0 + e];
-            const float s = v[e];
-            if (s > tsc + d) {
-              ++gt;
-            } else if (s >= tsc - d) {  // inside the error band: decide with the canonical fp32 logit
-              const float ex = canonical_dot(a.users + me * a.ldu, a.table + item * a.H, a.H);
-              gt += ex > tsc ? 1 : 0;
-              eq += ex == tsc ? 1 : 0;
-              ++band;
+        for (long j0 = jb; j0 < je && !failed; j0 += SF_N) {
+          const unsigned char* bsrc = a.bpre + (size_t)(j0 / SF_N) * a.nkc * SF_BBYTES;
+          for (int kc = 0; kc < a.nkc; ++kc, ++it) {
+            const int s = it % SF_STAGES;
+            const uint32_t round = it / SF_STAGES;
+            if (!umma::mbar_wait(&empty[s], (round & 1) ^ 1)) { failed = true; break; }
+            unsigned char* dst = ring + (size_t)s * stage_bytes;
+            if (a_res) {
+              umma::mbar_arrive_expect_tx(&full[s], SF_BBYTES);
+              umma::bulk_g2s(dst, bsrc + (size_t)kc * SF_BBYTES, SF_BBYTES, &full[s]);
+            } else {
+              umma::mbar_arrive_expect_tx(&full[s], SF_ABYTES + SF_BBYTES);
+              umma::bulk_g2s(dst, asrc + (size_t)kc * SF_ABYTES, SF_ABYTES, &full[s]);
+              umma::bulk_g2s(dst + SF_ABYTES, bsrc + (size_t)kc * SF_BBYTES, SF_BBYTES, &full[s]);
             }
           }
         }
       }
-      umma::fence_before_sync();
-      __syncthreads();  // accumulator fully read before the next tile's first MMA overwrites it
-      umma::fence_after_sync();
     }
-    if (live && !failed) {
-      if (gt) atomicAdd(&a.cgt[me], gt);
-      if (eq) atomicAdd(&a.ceq[me], eq);
-      if (a.stats && band) atomicAdd(&a.stats[0], (unsigned long long)band);
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma::idesc_tf32(SF_M, SF_N);
+      uint32_t it = 0, tile_no = 0, units_done = 0;
+      for (long unit = blockIdx.x; unit < a.nunits && !failed; unit += gridDim.x, ++units_done) {
+        const long ut = unit / a.nsplit;
+        const int sp = (int)(unit - ut * a.nsplit);
+        const long jb = (long)sp * a.items_per_split;
+        const long je = jb + a.items_per_split < a.V ? jb + a.items_per_split : a.V;
+        if (a_res && !umma::mbar_wait(&afull, units_done & 1)) { failed = true; break; }
+        for (long j0 = jb; j0 < je && !failed; j0 += SF_N, ++tile_no) {
+          const uint32_t acc = tile_no & 1;
+          if (!umma::mbar_wait(&tempty[acc], ((tile_no >> 1) & 1) ^ 1)) { failed = true; break; }
+          umma::fence_after_sync();
+          const uint32_t dcol = tmem + acc * SF_N;
+          for (int kc = 0; kc < a.nkc; ++kc, ++it) {
+            const int s = it % SF_STAGES;
+            if (!umma::mbar_wait(&full[s], (it / SF_STAGES) & 1)) { failed = true; break; }
+            umma::fence_after_sync();
+            const unsigned char* st = ring + (size_t)s * stage_bytes;
+            const uint32_t ab = umma::smem_u32(a_res ? Ares + (size_t)kc * SF_ABYTES : st);
+            const uint32_t bb = umma::smem_u32(a_res ? st : st + SF_ABYTES);
+            const int kleft = a.kpad - kc * SF_KC;
+            const int ksteps = (kleft < SF_KC ? kleft : SF_KC) / 8;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t dah = umma::smem_desc(ab + 2 * ks * SF_A_PITCH, SF_A_PITCH, 128);
+              const uint64_t dal = umma::smem_desc(ab + (SF_SLABS + 2 * ks) * SF_A_PITCH, SF_A_PITCH, 128);
+              const uint64_t dbh = umma::smem_desc(bb + 2 * ks * SF_B_PITCH, SF_B_PITCH, 128);
+              const uint64_t dbl = umma::smem_desc(bb + (SF_SLABS + 2 * ks) * SF_B_PITCH, SF_B_PITCH, 128);
+              umma::mma_tf32(dcol, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+              umma::mma_tf32(dcol, dah, dbl, idesc, 1u);
+              umma::mma_tf32(dcol, dah, dbh, idesc, 1u);
+            }
+            umma::mma_commit(&empty[s]);   // stage s may be refilled once these MMAs have read it
+          }
+          if (!failed) umma::mma_commit(&tfull[acc]);
+        }
+        if (a_res && !failed) umma::mma_commit(&adone);
+      }
+    }
+  } else {
+    // ================================================================== epilogue (warps 2..9, thread <-> user row)
+    const uint32_t q = warp & 3;               // TMEM lane quarter this warp may read
+    const int chalf = (warp - 2) >> 2;         // which half of the 256 columns it takes
+    uint32_t tile_no = 0;
+    for (long unit = blockIdx.x; unit < a.nunits && !failed; unit += gridDim.x) {
+      const long ut = unit / a.nsplit;
+      const int sp = (int)(unit - ut * a.nsplit);
+      const int jb = (int)((long)sp * a.items_per_split);
+      const int je = (long)jb + a.items_per_split < a.V ? (int)(jb + a.items_per_split) : a.V;
+      const long me = ut * SF_M + q * 32 + lane;
+      const bool live = me < a.U;
+      const float tsc = live ? a.tscore[me] : 0.f;
+      const float nu = live ? a.unorm[me] * a.cbound : 0.f;
+      const int tgt = live ? a.target[me] : -1;
+      int gt = 0;
+      unsigned band = 0;
+      for (int j0 = jb; j0 < je && !failed; j0 += SF_N, ++tile_no) {
+        const uint32_t acc = tile_no & 1;
+        const bool ok = umma::mbar_wait(&tfull[acc], (tile_no >> 1) & 1);
+        if (!__all_sync(0xffffffffu, ok)) { failed = true; break; }
+        umma::fence_after_sync();
+        // |s~ - s| <= nu * |e_j| <= d for every item of the tile: above `hi` is certainly greater, below `lo`
+        // certainly smaller, in between the canonical fp32 logit decides (deferred)
+        const float d = nu * __ldg(a.tnorm + j0 / SF_N);
+        const float hi = tsc + d, lo = tsc - d;
+        const bool interior = j0 >= 1 && j0 + SF_N <= je && (tgt < j0 || tgt >= j0 + SF_N);  // no per-item exclusions
+#pragma unroll 1
+        for (int cb = chalf * (SF_N / 2); cb < (chalf + 1) * (SF_N / 2); cb += 32) {
+          float v[32];
+          umma::tmem_ld32(tmem + ((q * 32u) << 16) + acc * SF_N + (uint32_t)cb, v);
+          if (!live) continue;
+          unsigned inband = 0;
+          if (interior) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              gt += v[e] > hi ? 1 : 0;
+              inband |= (v[e] >= lo && !(v[e] > hi)) ? (1u << e) : 0u;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int item = j0 + cb + e;
+              const bool valid = item >= 1 && item < je && item != tgt;
+              gt += (valid && v[e] > hi) ? 1 : 0;
+              inband |= (valid && v[e] >= lo && !(v[e] > hi)) ? (1u << e) : 0u;
+            }
+          }
+          while (inband) {  // rare: hand the pair to band_rescore_kernel
+            const int e = __ffs((int)inband) - 1;
+            inband &= inband - 1;
+            const int item = j0 + cb + e;
+            const unsigned long long slot = atomicAdd(a.band_count, 1ull);
+            if (slot < a.band_cap) {
+              a.band_pairs[slot] = make_int2((int)me, item);
+            } else {  // list full: decide here (slow path)
+              const float ex = canonical_dot(a.users + me * a.ldu, a.table + (long)item * a.H, a.H);
+              if (ex > tsc) ++gt;
+              else if (ex == tsc) atomicAdd(&a.ceq[me], 1);
+            }
+            ++band;
+          }
+        }
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&tempty[acc]);   // this warp's share of the accumulator is free
+      }
+      if (live && !failed) {
+        if (gt) atomicAdd(&a.cgt[me], gt);
+        if (a.stats && band) atomicAdd(&a.stats[0], (unsigned long long)band);
+      }
     }
   }
-  if (failed && t == 0) atomicExch(a.err, 1);
+  if (failed) atomicExch(a.err, 1);
   __syncthreads();
-  if (warp == 0) umma::tmem_free(tmem, SF_N);
+  if (warp == 1) umma::tmem_free(tmem, 2 * SF_N);
 }
 #endif  // !CAST_EMU
 
@@ -277,8 +418,33 @@ using namespace cast;
 
 static inline size_t sf_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
-extern "C" size_t cast_score_rank_full_workspace_bytes(long U, int V) {
-  return sf_align((size_t)V * 4) + 2 * sf_align((size_t)U * 4) + 256;
+// tensor-core pass only: pre-split operand images (users: 128-row tiles, items: 256-row tiles)
+static size_t sf_presplit_bytes(long U, int V, int H, size_t* a_bytes) {
+#ifndef CAST_EMU
+  const int kpad = (H + 7) & ~7;
+  const size_t nkc = (size_t)cdiv(kpad, SF_KC);
+  const size_t ab = (size_t)cdiv(U, SF_M) * nkc * SF_ABYTES;
+  const size_t bb = (size_t)cdiv(V, SF_N) * nkc * SF_BBYTES;
+  if (a_bytes) *a_bytes = sf_align(ab);
+  return sf_align(ab) + sf_align(bb);
+#else
+  (void)U; (void)V; (void)H;
+  if (a_bytes) *a_bytes = 0;
+  return 0;
+#endif
+}
+
+// capacity of the deferred band list: 0.5 % of the (user, item) pairs, at least 64k (overflow is handled inline)
+static unsigned long long sf_band_cap(long U, int V) {
+  unsigned long long c = (unsigned long long)U * (unsigned long long)V / 200ull;
+  if (c < 65536ull) c = 65536ull;
+  if (c > (1ull << 28)) c = 1ull << 28;
+  return c;
+}
+
+extern "C" size_t cast_score_rank_full_workspace_bytes(long U, int V, int H) {
+  return sf_align((size_t)V * 4) + 2 * sf_align((size_t)U * 4) + 256 + sf_presplit_bytes(U, V, H, nullptr) +
+         sf_align((size_t)sf_band_cap(U, V) * sizeof(int2)) + sf_align((size_t)(V / 256 + 2) * 4);
 }
 
 extern "C" int cast_score_rank_full(const float* seq_last, long ld, const float* table, int V, int H, long U,
@@ -288,7 +454,7 @@ extern "C" int cast_score_rank_full(const float* seq_last, long ld, const float*
   if (!seq_last || !table || !target || !count_greater || !count_equal || V <= 1 || H <= 0 || U <= 0 ||
       (mode != 0 && mode != 1) || (rated_ptr && !rated_idx))
     return set_error(CAST_ERR_BAD_ARG, "score_rank_full");
-  if (!workspace || workspace_bytes < cast_score_rank_full_workspace_bytes(U, V))
+  if (!workspace || workspace_bytes < cast_score_rank_full_workspace_bytes(U, V, H))
     return set_error(CAST_ERR_WORKSPACE, "score_rank_full: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* w = static_cast<unsigned char*>(workspace);
@@ -322,6 +488,23 @@ extern "C" int cast_score_rank_full(const float* seq_last, long ld, const float*
     a.kpad = (H + 7) & ~7;
     a.nkc = (int)cdiv(a.kpad, SF_KC);
     const long utiles = cdiv(U, SF_M);
+    size_t a_bytes = 0;
+    sf_presplit_bytes(U, V, H, &a_bytes);
+    unsigned char* apre = w + sf_align((size_t)V * 4) + 2 * sf_align((size_t)U * 4) + 256;
+    unsigned char* bpre = apre + a_bytes;
+    presplit_kernel<SF_M><<<dim3((unsigned)utiles, (unsigned)a.nkc), 256, 0, st>>>(seq_last, ld, U, H, a.nkc, apre);
+    presplit_kernel<SF_N><<<dim3((unsigned)cdiv(V, SF_N), (unsigned)a.nkc), 256, 0, st>>>(table, H, V, H, a.nkc, bpre);
+    if ((rc = check_launch("score_full(presplit)"))) return rc;
+    a.apre = apre; a.bpre = bpre;
+    size_t pre_total = sf_presplit_bytes(U, V, H, nullptr);
+    a.band_pairs = reinterpret_cast<int2*>(apre + pre_total);
+    a.band_cap = sf_band_cap(U, V);
+    a.band_count = reinterpret_cast<unsigned long long*>(err + 2);   // inside the 256-byte flag block
+    cudaMemsetAsync(a.band_count, 0, sizeof(unsigned long long), st);
+    float* tnorm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.band_pairs) +
+                                            sf_align((size_t)a.band_cap * sizeof(int2)));
+    tile_norm_kernel<<<dim3((unsigned)cdiv(cdiv(V, SF_N), 8)), dim3(256), 0, st>>>(inorm, V, SF_N, tnorm);
+    a.tnorm = tnorm;
     const long ntile_items = cdiv(V, SF_N);
     long nsplit = cdiv(148L * 2, utiles);          // ~2 work units per SM
     if (nsplit > ntile_items) nsplit = ntile_items;
@@ -341,6 +524,10 @@ extern "C" int cast_score_rank_full(const float* seq_last, long ld, const float*
     const long grid = a.nunits < 148 ? a.nunits : 148;
     score_full_umma_kernel<<<dim3((unsigned)grid), dim3(SF_THREADS), SF_SMEM, st>>>(a);
     if ((rc = check_launch("score_full(umma)"))) return rc;
+    band_rescore_kernel<<<dim3(148 * 8), dim3(256), 0, st>>>(seq_last, ld, table, H, (const float*)tscore,
+                                                             (const int2*)a.band_pairs, a.band_count, a.band_cap,
+                                                             count_greater, count_equal);
+    if ((rc = check_launch("score_full(band)"))) return rc;
 #endif
   }
   if (rated_ptr) {
@@ -353,6 +540,7 @@ extern "C" int cast_score_rank_full(const float* seq_last, long ld, const float*
 
 // 0 = ok; non-zero = the tensor-core pass timed out waiting for its MMAs (never expected; results invalid)
 extern "C" int cast_score_rank_full_status(const void* workspace, long U, int V, int* host_flag, void* stream) {
+  // (the flag sits right after the norm / score arrays; H does not move it)
   if (!workspace || !host_flag) return set_error(CAST_ERR_BAD_ARG, "score_rank_full_status");
   const unsigned char* w = static_cast<const unsigned char*>(workspace);
   const int* err = reinterpret_cast<const int*>(w + sf_align((size_t)V * 4) + 2 * sf_align((size_t)U * 4));

@@ -68,6 +68,24 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
   return false;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// one arrival + announce `bytes` of asynchronous copies that will complete on this barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// TMA 1-D bulk copy global -> shared (16-byte aligned addresses, size multiple of 16); completion is signalled on the
+// mbarrier as transaction bytes.  Issued by ONE thread.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T for one K = 8 step; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {

@@ -178,7 +178,7 @@ class _Model:
             rptr, ridx = torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev)
         cgt = torch.empty(B, dtype=torch.int32, device=dev)
         ceq = torch.empty(B, dtype=torch.int32, device=dev)
-        wsb = eng.lib.cast_score_rank_full_workspace_bytes(B, V)
+        wsb = eng.lib.cast_score_rank_full_workspace_bytes(B, V, H)
         ws = self._pinned.get(("sfws", B))
         if ws is None:
             ws = self._pinned[("sfws", B)] = torch.empty(wsb // 4 + 16, dtype=torch.int32, device=dev)

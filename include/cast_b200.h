@@ -205,7 +205,7 @@ int cast_score_rank_cand(const float* seq_last, long ld, const float* table, int
  * mode 0: tcgen05 tensor-core GEMM (3xTF32 split, accumulator in TMEM) + exact re-scoring of the error band;
  * mode 1: exact brute force.  Both return identical integers.  stats (optional, device, 2 x u64): [0] = number of
  * band candidates re-scored exactly. */
-size_t cast_score_rank_full_workspace_bytes(long U, int V);
+size_t cast_score_rank_full_workspace_bytes(long U, int V, int H);
 int cast_score_rank_full(const float* seq_last, long ld, const float* table, int V, int H, long U, const int* target,
                          const int* rated_ptr, const int* rated_idx, int mode, int* count_greater, int* count_equal,
                          unsigned long long* stats, void* workspace, size_t workspace_bytes, void* stream);

@@ -39,7 +39,7 @@ def run(kind, U, V, H, mode, seed=0, ld_extra=0, ties=True):
     cgt = torch.full((U,), -7, dtype=torch.int32, device=dev)
     ceq = torch.full((U,), -7, dtype=torch.int32, device=dev)
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
-    wsb = lib.cast_score_rank_full_workspace_bytes(U, V)
+    wsb = lib.cast_score_rank_full_workspace_bytes(U, V, H)
     ws = torch.empty(wsb // 4 + 16, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else None
     rc = lib.cast_score_rank_full(tu.data_ptr(), H + ld_extra, tt.data_ptr(), V, H, U, tg.data_ptr(), tp.data_ptr(),
