@@ -30,7 +30,7 @@ SIGNATURES = {
     "cast_layernorm_bwd": (I, [P, P, P, P, P, L, I, P, P, P, P, P, SZ, P]),
     "cast_gemm_set_backend": (I, [I]),
     "cast_gemm_tensor_status": (I, [P, P]),
-    "cast_gemm_workspace_bytes": (SZ, [L, I, I]),
+    "cast_gemm_workspace_bytes": (SZ, [L, I, L, I]),
     "cast_gemm": (I, [P, L, L, P, L, L, P, L, L, I, L, P, I, F, U64, P, I, P, L, F, P, L, P, I, P, SZ, P]),
     "cast_fused_supported": (I, [I]),
     "cast_ln_qkv_fwd": (I, [P, P, P, P, P, P, P, P, P, L, I, F, P, P, P, P, P, P, P, P, P]),

@@ -34,7 +34,9 @@ struct UGemmEpi {
   const int* row_ids;
 };
 int gemm_umma_launch(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc, long M,
-                     int N, long K, const UGemmEpi& epi, int splits, float* partials, cudaStream_t stream);
+                     int N, long K, const UGemmEpi& epi, int splits, float* partials, void* image, size_t image_bytes,
+                     cudaStream_t stream);
+size_t gemm_umma_image_bytes(int N, long K);
 #endif
 static int g_gemm_backend = 0;  // 0 = auto (tensor cores for wide shapes), 1 = FP32 FFMA tiles, 2 = tensor cores
 
@@ -157,8 +159,14 @@ __global__ void colsum_kernel(const float* __restrict__ X, long rows, long cols,
 
 using namespace cast;
 
-extern "C" size_t cast_gemm_workspace_bytes(long M, int N, int splits) {
-  return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+extern "C" size_t cast_gemm_workspace_bytes(long M, int N, long K, int splits) {
+  if (splits > 1) return (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
+#ifndef CAST_EMU
+  return gemm_umma_image_bytes(N, K);   // pre-split weight image of the tensor-core path
+#else
+  (void)K;
+  return 0;
+#endif
 }
 
 extern "C" int cast_gemm(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
@@ -174,15 +182,18 @@ extern "C" int cast_gemm(const float* A, long sam, long sak, const float* B, lon
   if (splits > 1) {
     if (bias || relu || drop_rate > 0.f || act || resid || row_ids || ldc != N)
       return set_error(CAST_ERR_BAD_ARG, "gemm: split-K supports no epilogue and needs ldc == N");
-    if (!workspace || workspace_bytes < cast_gemm_workspace_bytes(M, N, splits))
+    if (!workspace || workspace_bytes < cast_gemm_workspace_bytes(M, N, K, splits))
       return set_error(CAST_ERR_WORKSPACE, "gemm: workspace too small");
   }
 #ifndef CAST_EMU
-  const bool wide = N >= 64 && K >= 64 && M >= 64;
+  // measured on B200 (scripts/bench_gemm.py): the tcgen05 pipeline wins from ~0.5 GFLOP per call (25600 x 256 x 256:
+  // 37-80 us vs 128-187 us); below that both paths sit on the ~20 us latency floor and the FFMA tiles are a bit faster
+  const bool wide = N >= 64 && K >= 64 && M >= 64 && (double)M * N * K >= 2.5e8;
   if (g_gemm_backend == 2 || (g_gemm_backend == 0 && wide)) {
     UGemmEpi ue{bias, relu, drop_rate, seed, step, site, act, ld_act, act_scale, resid, ldr, row_ids};
     return gemm_umma_launch(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, ue, splits,
-                            splits > 1 ? static_cast<float*>(workspace) : nullptr, (cudaStream_t)stream);
+                            splits > 1 ? static_cast<float*>(workspace) : nullptr, splits > 1 ? nullptr : workspace,
+                            splits > 1 ? 0 : workspace_bytes, (cudaStream_t)stream);
   }
 #endif
   dim3 grid((unsigned)cdiv(M, TM), (unsigned)cdiv(N, TN), (unsigned)splits);

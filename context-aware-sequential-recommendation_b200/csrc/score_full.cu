@@ -296,6 +296,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) score_full_umma_kernel(ScoreFul
     // ================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma::idesc_tf32(SF_M, SF_N);
+      // descriptors are built once; inside the loops a k-step costs four 64-bit adds and three MMAs (the issuing
+      // thread is latency-bound on its own instruction stream)
+      uint64_t dA[SF_STAGES], dB[SF_STAGES];
+#pragma unroll
+      for (int s = 0; s < SF_STAGES; ++s) {
+        const unsigned char* st = ring + (size_t)s * stage_bytes;
+        dA[s] = umma::smem_desc(umma::smem_u32(a_res ? Ares + (size_t)s * SF_ABYTES : st), SF_A_PITCH, 128);
+        dB[s] = umma::smem_desc(umma::smem_u32(a_res ? st : st + SF_ABYTES), SF_B_PITCH, 128);
+      }
       uint32_t it = 0, tile_no = 0, units_done = 0;
       for (long unit = blockIdx.x; unit < a.nunits && !failed; unit += gridDim.x, ++units_done) {
         const long ut = unit / a.nsplit;
@@ -312,19 +321,22 @@ __global__ void __launch_bounds__(SF_THREADS, 1) score_full_umma_kernel(ScoreFul
             const int s = it % SF_STAGES;
             if (!umma::mbar_wait(&full[s], (it / SF_STAGES) & 1)) { failed = true; break; }
             umma::fence_after_sync();
-            const unsigned char* st = ring + (size_t)s * stage_bytes;
-            const uint32_t ab = umma::smem_u32(a_res ? Ares + (size_t)kc * SF_ABYTES : st);
-            const uint32_t bb = umma::smem_u32(a_res ? st : st + SF_ABYTES);
+            // resident user tile: chunk kc lives in slot kc (nkc <= SF_STAGES); streamed: in the ring stage
+            const uint64_t dah = a_res ? (kc == 0 ? dA[0] : dA[1]) : (s == 0 ? dA[0] : dA[1]);
+            const uint64_t dbh = s == 0 ? dB[0] : dB[1];
             const int kleft = a.kpad - kc * SF_KC;
             const int ksteps = (kleft < SF_KC ? kleft : SF_KC) / 8;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t dah = umma::smem_desc(ab + 2 * ks * SF_A_PITCH, SF_A_PITCH, 128);
-              const uint64_t dal = umma::smem_desc(ab + (SF_SLABS + 2 * ks) * SF_A_PITCH, SF_A_PITCH, 128);
-              const uint64_t dbh = umma::smem_desc(bb + 2 * ks * SF_B_PITCH, SF_B_PITCH, 128);
-              const uint64_t dbl = umma::smem_desc(bb + (SF_SLABS + 2 * ks) * SF_B_PITCH, SF_B_PITCH, 128);
-              umma::mma_tf32(dcol, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-              umma::mma_tf32(dcol, dah, dbl, idesc, 1u);
-              umma::mma_tf32(dcol, dah, dbh, idesc, 1u);
+#pragma unroll
+            for (int ks = 0; ks < SF_KC / 8; ++ks) {
+              if (ks < ksteps) {
+                const uint64_t ah = umma::desc_advance(dah, 2 * ks * SF_A_PITCH);
+                const uint64_t al = umma::desc_advance(dah, (SF_SLABS + 2 * ks) * SF_A_PITCH);
+                const uint64_t bh = umma::desc_advance(dbh, 2 * ks * SF_B_PITCH);
+                const uint64_t bl = umma::desc_advance(dbh, (SF_SLABS + 2 * ks) * SF_B_PITCH);
+                umma::mma_tf32(dcol, al, bh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                umma::mma_tf32(dcol, ah, bl, idesc, 1u);
+                umma::mma_tf32(dcol, ah, bh, idesc, 1u);
+              }
             }
             umma::mma_commit(&empty[s]);   // stage s may be refilled once these MMAs have read it
           }

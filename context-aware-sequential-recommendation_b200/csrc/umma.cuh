@@ -27,6 +27,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// the same descriptor `bytes` further into shared memory (bytes % 16 == 0; the 14-bit start-address field cannot
+// overflow for addresses below 256 KB).  One 64-bit add instead of rebuilding the descriptor: the single MMA-issuing
+// thread is latency-bound on its own instruction stream, so every instruction between two tcgen05.mma counts.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 // 32-bit instruction descriptor for kind::tf32: D = f32, A = B = tf32, both K-major, dense, no negate.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -263,7 +263,7 @@ class Engine:
         kmax = (len(self.plan.merge[0]) if self.plan.merge else 1) * H
         c.splits = int(max(1, min(296, N // 128)))
         ws = max(lib.cast_layernorm_bwd_workspace_bytes(N, H),
-                 lib.cast_gemm_workspace_bytes(kmax, kmax, c.splits),
+                 lib.cast_gemm_workspace_bytes(kmax, kmax, N, c.splits), lib.cast_gemm_workspace_bytes(N, kmax, kmax, 1),
                  lib.cast_colsum_workspace_bytes(N, kmax), lib.cast_colsum_workspace_bytes(B, T * H),
                  lib.cast_logits_loss_workspace_bytes(N), lib.cast_block_bwd_workspace_bytes(N, H))
         c.ws = torch.empty(ws // 4 + 16, dtype=torch.float32, device=dev)

@@ -88,14 +88,14 @@ int cast_layernorm_bwd(const float* dy, const float* x, const float* mean, const
  *   epi(c) = (((relu?max(c+bias[j],0):c+bias[j]) * dropout(i*N+j)) * (act[i,j]>0 ? act_scale : 0) + resid[i,j])
  *            * (row_ids[i] != 0)                      — every term optional (null / 0).
  * splits > 1: reduction dimension split across CTAs, partials summed in fixed order (no epilogue, ldc == N). */
-/* Backends: shapes with M, N, K >= 64 run on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 operand split,
+/* Backends: shapes with M, N, K >= 64 and M*N*K >= 2.5e8 run on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 operand split,
  * accumulator in TMEM — csrc/gemm_umma.cu), smaller ones on FP32 FFMA register tiles (csrc/gemm.cu).
  * cast_gemm_set_backend: 0 = that rule, 1 = always FFMA, 2 = always tensor cores (tests).
  * (The TMEM accumulator rounds toward zero; reductions longer than ~1k per CTA should use splits > 1.)
  * cast_gemm_tensor_status synchronises the stream and returns the tensor path's watchdog flag (0 = ok). */
 int cast_gemm_set_backend(int which);
 int cast_gemm_tensor_status(int* host_flag, void* stream);
-size_t cast_gemm_workspace_bytes(long M, int N, int splits);
+size_t cast_gemm_workspace_bytes(long M, int N, long K, int splits);
 int cast_gemm(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc, long M,
               int N, long K, const float* bias, int relu, float drop_rate, unsigned long long seed,
               const unsigned long long* step, int site, const float* act, long ld_act, float act_scale,

@@ -16,7 +16,7 @@ def call_gemm(lib, dev, A, sam, sak, Bm, sbk, sbn, M, N, K, bias=None, relu=0, a
     t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
     tA, tB, tb, tact, tres, trow = t(A), t(Bm), t(bias), t(act), t(resid), t(row_ids)
     out = torch.full((M, N), 7.0, dtype=torch.float32, device=dev)
-    wsb = lib.cast_gemm_workspace_bytes(M, N, splits)
+    wsb = lib.cast_gemm_workspace_bytes(M, N, K, splits)
     ws = torch.empty(wsb // 4 + 16, dtype=torch.float32, device=dev)
     p = lambda x: None if x is None else x.data_ptr()  # noqa: E731
     stream = torch.cuda.current_stream(dev).cuda_stream
