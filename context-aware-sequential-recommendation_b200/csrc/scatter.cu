@@ -307,27 +307,20 @@ extern "C" size_t cast_scatter_workspace_bytes(long N, int nsrc, int V) {
   return (size_t)(4 * total + 256 * nchunks) * sizeof(unsigned) + (size_t)nseg * 2 * sizeof(int) + 64;
 }
 
-extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float* const* rows,
-                                 const float* const* rowscale, const float* scale, int V, int H, float* dtable,
-                                 void* workspace, size_t workspace_bytes, void* partial, size_t partial_bytes,
+// Sort half of the scatter: depends on the ids only, so the engine runs it on a side stream at the start of the step,
+// concurrently with the forward pass; the sorted (key, entry) arrays stay in the workspace for cast_scatter_apply.
+extern "C" int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void* workspace, size_t workspace_bytes,
                                  void* stream) {
-  if (!keys || !rows || !scale || !dtable || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0 || H <= 0 || H > 1024)
-    return set_error(CAST_ERR_BAD_ARG, "scatter_rows");
+  if (!keys || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0) return set_error(CAST_ERR_BAD_ARG, "scatter_sort");
   const long total = N * nsrc;
-  if (total >= (1L << 32)) return set_error(CAST_ERR_UNSUPPORTED, "scatter_rows: too many entries");
+  if (total >= (1L << 32)) return set_error(CAST_ERR_UNSUPPORTED, "scatter_sort: too many entries");
   if (!workspace || workspace_bytes < cast_scatter_workspace_bytes(N, nsrc, V))
-    return set_error(CAST_ERR_WORKSPACE, "scatter_rows: workspace too small");
-  if (!partial || partial_bytes < cast_scatter_partial_bytes(N, nsrc, H))
-    return set_error(CAST_ERR_WORKSPACE, "scatter_rows: partial buffer too small");
+    return set_error(CAST_ERR_WORKSPACE, "scatter_sort: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int nchunks = (int)cdiv(total, RS_CHUNK);
-  unsigned* bufK[2];
-  unsigned* bufP[2];
   unsigned* base = static_cast<unsigned*>(workspace);
-  bufK[0] = base;
-  bufK[1] = base + total;
-  bufP[0] = base + 2 * total;
-  bufP[1] = base + 3 * total;
+  unsigned* bufK[2] = {base, base + total};
+  unsigned* bufP[2] = {base + 2 * total, base + 3 * total};
   unsigned* hist = base + 4 * total;
   const unsigned* kin = reinterpret_cast<const unsigned*>(keys);
   const unsigned* pin = nullptr;
@@ -349,6 +342,30 @@ extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float*
     kin = kout;
     pin = pout;
   }
+  return CAST_OK;
+}
+
+// Reduce half: fixed-order segment sums of the rows over the arrays cast_scatter_sort left in the workspace.
+extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, const float* const* rowscale,
+                                  const float* scale, int V, int H, float* dtable, void* workspace,
+                                  size_t workspace_bytes, void* partial, size_t partial_bytes, void* stream) {
+  if (!rows || !scale || !dtable || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0 || H <= 0 || H > 1024)
+    return set_error(CAST_ERR_BAD_ARG, "scatter_apply");
+  const long total = N * nsrc;
+  if (!workspace || workspace_bytes < cast_scatter_workspace_bytes(N, nsrc, V))
+    return set_error(CAST_ERR_WORKSPACE, "scatter_apply: workspace too small");
+  if (!partial || partial_bytes < cast_scatter_partial_bytes(N, nsrc, H))
+    return set_error(CAST_ERR_WORKSPACE, "scatter_apply: partial buffer too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = (int)cdiv(total, RS_CHUNK);
+  unsigned* base = static_cast<unsigned*>(workspace);
+  int passes, dbits;
+  key_plan(V, &passes, &dbits);
+  const int last = (passes - 1) & 1;   // buffer pair the final pass wrote
+  const unsigned* kin = base + (size_t)last * total;
+  const unsigned* pin = base + 2 * total + (size_t)last * total;
+  unsigned* hist = base + 4 * total;
+  int rc;
   ScatterSrc src;
   for (int s = 0; s < 4; ++s) {
     src.rows[s] = s < nsrc ? rows[s] : nullptr;
@@ -377,4 +394,14 @@ extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float*
   else CAST_SEG(32)
 #undef CAST_SEG
   return check_launch("segment_stitch");
+}
+
+extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float* const* rows,
+                                 const float* const* rowscale, const float* scale, int V, int H, float* dtable,
+                                 void* workspace, size_t workspace_bytes, void* partial, size_t partial_bytes,
+                                 void* stream) {
+  int rc = cast_scatter_sort(keys, nsrc, N, V, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return cast_scatter_apply(nsrc, N, rows, rowscale, scale, V, H, dtable, workspace, workspace_bytes, partial,
+                            partial_bytes, stream);
 }

@@ -335,6 +335,13 @@ class Engine:
         rows_a = (C.c_void_p * nsrc)(*[r.data_ptr() for r in rows])
         rs_a = (C.c_void_p * nsrc)(*[(r.data_ptr() if r is not None else None) for r in rowscale])
         sc_a = (C.c_float * nsrc)(*scale)
+        if table_name == "item_emb" and getattr(c, "presorted", False):
+            torch.cuda.current_stream(self.device).wait_stream(c.side)   # join the side-stream sort
+            c.presorted = False
+            self._call(self.lib.cast_scatter_apply, nsrc, N, rows_a, rs_a, sc_a, V, self.H,
+                       self.G[table_name].data_ptr(), c.sws.data_ptr(), c.sws_bytes, c.spart.data_ptr(),
+                       c.spart_bytes, self._stream())
+            return
         self._call(self.lib.cast_scatter_rows, keys.data_ptr(), nsrc, N, rows_a, rs_a, sc_a, V, self.H,
                    self.G[table_name].data_ptr(), c.sws.data_ptr(), c.sws_bytes, c.spart.data_ptr(), c.spart_bytes,
                    self._stream())
@@ -591,6 +598,20 @@ class Engine:
                    self.adam_state.data_ptr(), 1, self._stream())
 
     def launch_fwd_bwd(self, c):
+        # The sort of the (item id, entry) pairs for the embedding gradient depends on the ids only: it runs on a side
+        # stream while the forward pass computes (a parallel branch of the captured CUDA graph) and is joined right
+        # before the segment sums at the end of backward.
+        c.presorted = False
+        if self.device.type == "cuda" and self.timing is None:
+            main = torch.cuda.current_stream(self.device)
+            if getattr(c, "side", None) is None:
+                c.side = torch.cuda.Stream(device=self.device)
+            c.side.wait_stream(main)
+            with torch.cuda.stream(c.side):
+                V = self.P["item_emb"].shape[0]
+                self._call(self.lib.cast_scatter_sort, c.keys3.data_ptr(), 3, c.N, V, c.sws.data_ptr(), c.sws_bytes,
+                           c.side.cuda_stream)
+            c.presorted = True
         self.forward(c, train=True)
         self.loss_fwd_bwd(c, with_grad=True)
         self.backward(c)

@@ -171,6 +171,12 @@ int cast_logits_loss(const float* seq_emb, const float* table, int V, int H, lon
  * rows/rowscale/scale are HOST arrays of nsrc device pointers / floats (rowscale[s] may be null). */
 size_t cast_scatter_workspace_bytes(long N, int nsrc, int V);     /* integer scratch (sort buffers) */
 size_t cast_scatter_partial_bytes(long N, int nsrc, int H);       /* float scratch (chunk-crossing partial sums) */
+/* The two halves of cast_scatter_rows: the sort depends on the ids only (run it early, e.g. on a side stream while the
+ * forward pass computes), the apply consumes the sorted arrays left in `workspace`. */
+int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void* workspace, size_t workspace_bytes, void* stream);
+int cast_scatter_apply(int nsrc, long N, const float* const* rows, const float* const* rowscale, const float* scale,
+                       int V, int H, float* dtable, void* workspace, size_t workspace_bytes, void* partial,
+                       size_t partial_bytes, void* stream);
 int cast_scatter_rows(const int* keys /* [nsrc*N] */, int nsrc, long N, const float* const* rows,
                       const float* const* rowscale, const float* scale, int V, int H, float* dtable,
                       void* workspace, size_t workspace_bytes, void* partial, size_t partial_bytes, void* stream);
