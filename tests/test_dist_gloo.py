@@ -99,3 +99,55 @@ def test_row_sharded_item_table_update_equals_single_process(tmp_path):
     untouched = g_1[:n_item] == 0
     assert untouched.sum() > 1000
     assert np.array_equal(w_dp[:n_item][untouched], w_1[:n_item][untouched])
+
+
+def _eval_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import random
+    import cast_b200
+    from cast_b200 import data as cdata
+    from cast_b200 import dist as cdist
+    from cast_b200 import evaluation as cev
+    cdist.init_from_env("gloo")
+    lib, dev = backend("emu")
+    here = os.path.dirname(os.path.abspath(__file__))
+    dataset = cdata.data_partition(os.path.join(here, "golden", "ref_dataset.txt"), False)
+    args = make_args(hidden_units=12, maxlen=8, num_heads=1, num_blocks=1, dropout_rate=0.0)
+    args.test_model = None
+    args.test_seq_len = None
+    m = cast_b200.SASRec(dataset[3], dataset[4], args, device=dev, _lib=lib, use_graph=False, seed=3)
+    random.seed(5)
+    np.random.seed(5)
+    sharded = cev.evaluate(m, dataset, args, None, batch_users=16)       # users sharded over the 2 ranks
+    if rank == 0:
+        dist.barrier()
+        torch.save({"sharded": sharded}, out)
+    else:
+        dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.emu
+def test_user_sharded_evaluation_equals_single_process(tmp_path):
+    """evaluation.evaluate under world_size 2: users split contiguously, integer histogram all-reduce; HR@10 must be
+    identical to the single-process value and NDCG@10 equal up to float64 summation order."""
+    import random
+    import cast_b200
+    from cast_b200 import data as cdata
+    from cast_b200 import evaluation as cev
+    out = str(tmp_path / "ev.pt")
+    mp.spawn(_eval_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    lib, dev = backend("emu")
+    here = os.path.dirname(os.path.abspath(__file__))
+    dataset = cdata.data_partition(os.path.join(here, "golden", "ref_dataset.txt"), False)
+    args = make_args(hidden_units=12, maxlen=8, num_heads=1, num_blocks=1, dropout_rate=0.0)
+    args.test_model = None
+    args.test_seq_len = None
+    m = cast_b200.SASRec(dataset[3], dataset[4], args, device=dev, _lib=lib, use_graph=False, seed=3)
+    random.seed(5)
+    np.random.seed(5)
+    ndcg, hr = cev.evaluate(m, dataset, args, None, batch_users=16)
+    assert r["sharded"][1] == hr
+    assert abs(r["sharded"][0] - ndcg) < 1e-12
