@@ -40,8 +40,9 @@ SIGNATURES = {
     "cast_qkv_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, L, I, P, P, P, SZ, P]),
     "cast_colsum_workspace_bytes": (SZ, [L, L]),
     "cast_colsum": (I, [P, L, L, L, P, P, SZ, P]),
+    "cast_attn_set_chunk": (I, [I]),
     "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P, P]),
-    "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P]),
+    "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P, P, P]),
     "cast_logits_loss_workspace_bytes": (SZ, [L]),
     "cast_logits_loss": (I, [P, P, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),
     "cast_scatter_workspace_bytes": (SZ, [L, I, I]),
@@ -89,6 +90,8 @@ def load_library(path: str | None = None) -> C.CDLL:
             f"CUDA extension not found at {p}. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). This package has no CPU / PyTorch fallback.")
     lib = bind(C.CDLL(p))
+    if os.environ.get("CAST_ATTN_CHUNK"):  # tuning hook (32 or 64 columns per streamed attention chunk)
+        check(lib, lib.cast_attn_set_chunk(int(os.environ["CAST_ATTN_CHUNK"])), "cast_attn_set_chunk")
     if path is None:
         _LIB = lib
     return lib

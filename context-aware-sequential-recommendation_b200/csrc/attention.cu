@@ -24,6 +24,12 @@ extern template int dispatch_att<100>(int, const AttnFwdArgs*, const AttnBwdArgs
 extern template int dispatch_att<128>(int, const AttnFwdArgs*, const AttnBwdArgs*, const AttnDims&, cudaStream_t);
 extern template int dispatch_att<256>(int, const AttnFwdArgs*, const AttnBwdArgs*, const AttnDims&, cudaStream_t);
 
+bool attn_mma_supported(const AttnDims& dm);
+int dispatch_att_mma(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, const float* out, const float* resid,
+                     const AttnDims& dm, cudaStream_t stream);
+
+int attn_mma_set_chunk(int nt);
+
 static int dispatch_by_width(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, const AttnDims& dm,
                              cudaStream_t stream) {
   switch (dm.dpad) {
@@ -41,6 +47,8 @@ static int dispatch_by_width(int which, const AttnFwdArgs* fa, const AttnBwdArgs
 
 using namespace cast;
 
+extern "C" int cast_attn_set_chunk(int columns) { return attn_mma_set_chunk(columns / 8); }
+
 extern "C" int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv,
                              const float* queries, const float* kmask, const float* qmask, int B, int T, int H, int h,
                              float drop_rate, unsigned long long seed, const unsigned long long* step, int site,
@@ -52,7 +60,10 @@ extern "C" int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk,
   const AttnDims dm = make_dims(B, T, H, h);
   AttnFwdArgs args{Q, K, V, ldq, ldk, ldv, queries, kmask, qmask, out, skip_ids, attn_weights, row_max, row_linv,
                    drop_rate, seed, step, site};
-  int rc = dispatch_by_width(0, &args, nullptr, dm, (cudaStream_t)stream);
+  // tensor-core path (attention_mma.cu) unless the [h*B,T,T] weights are wanted or the head is wider than 64
+  int rc = (!attn_weights && attn_mma_supported(dm))
+               ? dispatch_att_mma(0, &args, nullptr, nullptr, nullptr, dm, (cudaStream_t)stream)
+               : dispatch_by_width(0, &args, nullptr, dm, (cudaStream_t)stream);
   if (rc) return rc;
   return check_launch("attn_fwd");
 }
@@ -62,7 +73,8 @@ extern "C" int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk,
                              const float* row_linv, const int* skip_ids, float* rowD, int B, int T, int H, int h,
                              float drop_rate, unsigned long long seed, const unsigned long long* step, int site,
                              float* dQ, long lddq,
-                             float* dK, long lddk, float* dV, long lddv, void* stream) {
+                             float* dK, long lddk, float* dV, long lddv, const float* out, const float* queries,
+                             void* stream) {
   if (!Q || !K || !V || !dO || !kmask || !qmask || !row_max || !row_linv || !rowD || !dQ || !dK || !dV || B <= 0 ||
       T <= 0 || H <= 0 || h <= 0 || H % h)
     return set_error(CAST_ERR_BAD_ARG, "attn_bwd");
@@ -70,10 +82,13 @@ extern "C" int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk,
   AttnBwdArgs args{Q, K, V, ldq, ldk, ldv, dO, kmask, qmask, row_max, row_linv, skip_ids, rowD, dQ, dK, dV, lddq, lddk,
                    lddv,
                    drop_rate, seed, step, site};
-  int rc = dispatch_by_width(1, nullptr, &args, dm, (cudaStream_t)stream);
+  const bool mma = out && queries && attn_mma_supported(dm);
+  int rc = mma ? dispatch_att_mma(1, nullptr, &args, out, queries, dm, (cudaStream_t)stream)
+               : dispatch_by_width(1, nullptr, &args, dm, (cudaStream_t)stream);
   if (rc) return rc;
   if ((rc = check_launch("attn_bwd_dq"))) return rc;
-  rc = dispatch_by_width(2, nullptr, &args, dm, (cudaStream_t)stream);
+  rc = mma ? dispatch_att_mma(2, nullptr, &args, out, queries, dm, (cudaStream_t)stream)
+           : dispatch_by_width(2, nullptr, &args, dm, (cudaStream_t)stream);
   if (rc) return rc;
   return check_launch("attn_bwd_dkv");
 }

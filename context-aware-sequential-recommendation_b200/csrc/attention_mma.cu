@@ -1,0 +1,678 @@
+// K4 on the tensor cores: causal multi-head attention (modules.py:208-269) forward and backward for head widths
+// d <= 64, as register-resident warp tiles of mma.sync m16n8k8 3xTF32 (mma_tf32.cuh).  Same mask semantics as the
+// FFMA kernels of attention.cuh (which remain for d > 64 and for the `attention_weights` output):
+//
+//   S = Q K^T / sqrt(d);  S = where(key masked | k > q, -2^32+1, S);  P = softmax(S) over all T keys;
+//   P *= query mask;  P = dropout(P);  O = P V + queries.
+//
+// Layout: CTA = 4 warps = 64 rows of one (batch element, head); a warp owns 16 rows and streams 8*NT-column chunks of
+// the other operand through a two-stage cp.async pipeline in shared memory (the next chunk is in flight while the
+// current one is multiplied).  Scores live only in the accumulator fragments: the forward pass keeps a
+// running row max / row sum (rescaling O when the max moves), and the C fragment of S is fed straight back as the A
+// fragment of P.V by relabelling the contraction index inside each k-step (mma_tf32.cuh), so probabilities never
+// touch shared memory.  Row tiles are aligned to the END of the sequence (sequences are left-padded: the ragged tile
+// is the cheap, mostly padded first one); the grid is tile-major, heaviest tiles first, so that the block scheduler's
+// round-robin fill hands every SM one tile of each weight.
+//
+// Backward = two deterministic kernels, no float atomics:
+//   dQ  per query tile:  S, dP = dO V^T -> dS = P (dP~ - D) / sqrt(d) -> dQ += dS K
+//   dKV per key tile:    S^T = K Q^T, dP^T = V dO^T -> dV += P~^T dO, dK += dS^T Q
+// with P recomputed from the saved row max / 1/rowsum and D_i = sum_j P_ij dP~_ij = dO_i . (out_i - queries_i)
+// (P~ V = out - queries), computed by the dQ kernel's prologue and handed to the dKV kernel through rowD.
+#include "attention.cuh"
+#include "mma_tf32.cuh"
+
+namespace cast {
+
+constexpr int AM_THREADS = 128;
+constexpr int AM_T = 64;  // rows per CTA (4 warps x 16)
+
+__device__ __forceinline__ void am_first2(const float* __restrict__ kmask_b, const int* __restrict__ ids_b, int T,
+                                          int* s2, int& first_key, int& qstart) {
+  if (threadIdx.x == 0) { s2[0] = T; s2[1] = ids_b ? T : 0; }
+  __syncthreads();
+  int mk = T, mq = T;
+  for (int j = threadIdx.x; j < T; j += AM_THREADS) {
+    if (mk == T && kmask_b[j] != 0.f) mk = j;
+    if (ids_b && mq == T && ids_b[j] != 0) mq = j;
+  }
+  if (mk < T) atomicMin(&s2[0], mk);
+  if (ids_b && mq < T) atomicMin(&s2[1], mq);
+  __syncthreads();
+  first_key = s2[0];
+  qstart = s2[1];
+}
+
+// asynchronous tile load: dst[r][c] = src[(row0 + r) * ld + c] for 0 <= row0 + r < T and c < d, zero rows outside the
+// sequence; columns d.. of dst are left alone (zeroed once by am_zero_pad).  One warp per row, 8-byte copies when the
+// rows allow it.
+template <int DS>
+__device__ __forceinline__ void am_load_rows_async(float* __restrict__ dst, const float* __restrict__ src, long ld,
+                                                   int row0, int nrows, int T, int d, bool vec2) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < nrows; r += AM_THREADS / 32) {
+    const int row = row0 + r;
+    const bool ok = row >= 0 && row < T;
+    const float* s = src + (long)(ok ? row : 0) * ld;
+    float* o = dst + r * DS;
+    if (vec2) {
+      for (int c = lane; 2 * c < d; c += 32) cp_async<8>(o + 2 * c, s + 2 * c, ok);
+    } else {
+      for (int c = lane; c < d; c += 32) cp_async<4>(o + c, s + c, ok);
+    }
+  }
+}
+
+__device__ __forceinline__ bool am_vec2_ok(const void* p, long ld, int d, int hh) {
+  return ((d | (int)(ld & 1)) & 1) == 0 && ((reinterpret_cast<uintptr_t>(p) + (uintptr_t)hh * d * 4) & 7) == 0;
+}
+
+// zero the columns d..DP-1 of `rows` consecutive tile rows (row stride DS)
+template <int DP, int DS>
+__device__ __forceinline__ void am_zero_pad(float* __restrict__ buf, int rows, int d) {
+  for (int r = threadIdx.x; r < rows; r += AM_THREADS)
+    for (int c = d; c < DP; ++c) buf[r * DS + c] = 0.f;
+}
+
+// acc[nt] (16 x 8 each, nt < NT) += A[16 x 8KS] * B[8NT x 8KS]^T for the n-tiles nt_lo <= nt < nt_hi (warp-uniform)
+template <int KS, int NT, int DS>
+__device__ __forceinline__ void am_rows_x_cols(float (&acc)[NT][4], const float* __restrict__ As,
+                                               const float* __restrict__ Bs, int nt_lo, int nt_hi, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    unsigned af[4], ah[4], al[4];
+    ldsm_a<DS>(af, As, ks * 8, lane);
+    tf32_split_n(af, ah, al);
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      if (2 * np + 1 >= nt_lo && 2 * np < nt_hi) {
+        unsigned bf[4], bh[4], bl[4];
+        ldsm_b2<DS>(bf, Bs + np * 16 * DS, ks * 8, lane);
+        tf32_split_n(bf, bh, bl);
+        if (2 * np >= nt_lo) mma_3x(acc[2 * np], ah, al, bh[0], bh[1], bl[0], bl[1]);
+        if (2 * np + 1 < nt_hi) mma_3x(acc[2 * np + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+  }
+}
+
+// out[no] (16 x 8 each, no < NTO) += P[16 x 8NT] * M[8NT x 8NTO], P given as C fragments p[kk] (kk = k-step = n-tile
+// of the product that made it), M row-major [k][n] in shared memory; k-steps kk_lo <= kk < kk_hi (warp-uniform)
+template <int NTO, int NT, int DS>
+__device__ __forceinline__ void am_frag_x_rows(float (&out)[NTO][4], const float (&p)[NT][4],
+                                               const float* __restrict__ Ms, int kk_lo, int kk_hi, int g, int tig) {
+#pragma unroll
+  for (int kk = 0; kk < NT; ++kk) {
+    if (kk >= kk_lo && kk < kk_hi) {
+      unsigned ah[4], al[4];
+      tf32_split(p[kk][0], ah[0], al[0]);  // (row g,   k-slot tig)     <- column 2 tig
+      tf32_split(p[kk][2], ah[1], al[1]);  // (row g+8, k-slot tig)
+      tf32_split(p[kk][1], ah[2], al[2]);  // (row g,   k-slot tig + 4) <- column 2 tig + 1
+      tf32_split(p[kk][3], ah[3], al[3]);  // (row g+8, k-slot tig + 4)
+      const float* m0 = Ms + (kk * 8 + 2 * tig) * DS + g;
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) {
+        unsigned bh0, bl0, bh1, bl1;
+        tf32_split(m0[no * 8], bh0, bl0);
+        tf32_split(m0[DS + no * 8], bh1, bl1);
+        mma_3x(out[no], ah, al, bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+}
+
+// row tiles / chunks of `width` rows aligned to the end of the sequence: index 0 starts at T - n*width (may be < 0)
+__device__ __forceinline__ int am_row0(int T, int n, int idx, int width) { return T - (n - idx) * width; }
+
+// grid = (B*h, ntile): blockIdx.x -> (b, head), blockIdx.y = 0 is the LAST (heaviest) row tile
+__device__ __forceinline__ void am_block(const AttnDims& dm, int& b, int& hh, int& ntile, int& tile) {
+  b = (int)blockIdx.x / dm.h;
+  hh = (int)blockIdx.x - b * dm.h;
+  ntile = (int)gridDim.y;
+  tile = ntile - 1 - (int)blockIdx.y;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int KS, int NT>
+__global__ void __launch_bounds__(AM_THREADS) attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
+  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TC = 8 * NT;
+  CAST_DYN_SMEM(float, sm);
+  __shared__ int s_first[2];
+  float* Qs = sm;                         // [64][DS]
+  float* Kst = Qs + AM_T * DS;            // [2][TC][DS]
+  float* Vst = Kst + 2 * TC * DS;         // [2][TC][DS]
+  float* kms = Vst + 2 * TC * DS;         // [2][TC] key mask of the chunk (0 outside the sequence)
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int T = dm.T, d = dm.d;
+  int b, hh, ntile, tile;
+  am_block(dm, b, hh, ntile, tile);
+  const int q0 = am_row0(T, ntile, tile, AM_T);
+  const long rowbase = (long)b * T;
+  int first_key, qstart;
+  am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
+  const long sbase = ((long)b * dm.h + hh) * T;
+  if (q0 + AM_T <= qstart) {  // every row of this tile is padding: output = residual only (block-uniform exit)
+    for (int idx = t; idx < AM_T * d; idx += AM_THREADS) {
+      const int i = q0 + idx / d, c = idx % d;
+      if (i >= 0) {
+        const long off = (rowbase + i) * dm.H + hh * d + c;
+        a.out[off] = a.resid[off];
+      }
+    }
+    for (int r = t; r < AM_T; r += AM_THREADS) {
+      const int i = q0 + r;
+      if (i >= 0) {
+        if (a.row_max) a.row_max[sbase + i] = 0.f;
+        if (a.row_linv) a.row_linv[sbase + i] = 0.f;
+      }
+    }
+    return;
+  }
+  const int qlo = q0 > qstart ? q0 : qstart;
+  const bool uni = qlo < first_key;  // tile holds fully-masked rows: they are uniform over all T keys
+  const int kend = uni ? T : q0 + AM_T;
+  const int kbeg = uni ? 0 : (first_key / TC) * TC;
+  const int nch = (kend - kbeg + TC - 1) / TC;
+  const int r0 = q0 + warp * 16;
+  const int iA = r0 + g, iB = iA + 8;
+  const bool wact = r0 + 16 > qstart;
+  const bool wuni = (r0 > qstart ? r0 : qstart) < first_key;
+  const int wkend = wuni ? T : r0 + 16;
+
+  const float* Qg = a.Q + rowbase * a.ldq + hh * d;
+  const float* Kg = a.K + rowbase * a.ldk + hh * d;
+  const float* Vg = a.V + rowbase * a.ldv + hh * d;
+  const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
+  auto issue = [&](int j0, int st) {
+    am_load_rows_async<DS>(Kst + st * TC * DS, Kg, a.ldk, j0, TC, T, d, vk);
+    am_load_rows_async<DS>(Vst + st * TC * DS, Vg, a.ldv, j0, TC, T, d, vv);
+    if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
+    cp_async_commit();
+  };
+  am_load_rows_async<DS>(Qs, Qg, a.ldq, q0, AM_T, T, d, vq);
+  issue(kbeg, 0);
+  am_zero_pad<DP, DS>(sm, AM_T + 4 * TC, d);
+
+  const Drop dr = make_drop(a.rate, a.seed, a.step, a.site);
+  const unsigned long long ibA = ((unsigned long long)((long)hh * dm.B + b) * T + (unsigned long long)(long)iA) * T;
+  const unsigned long long ibB = ibA + 8ull * T;
+  float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
+  float o[NTO][4];
+#pragma unroll
+  for (int no = 0; no < NTO; ++no)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[no][c] = 0.f;
+
+  for (int ci = 0; ci < nch; ++ci) {
+    const int j0 = kbeg + ci * TC, st = ci & 1;
+    if (ci + 1 < nch) {
+      issue(j0 + TC, st ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (wact && j0 < wkend) {
+      const float* Ks = Kst + st * TC * DS;
+      const float* Vs = Vst + st * TC * DS;
+      const float* km_s = kms + st * TC;
+      int ntl = (wkend - j0 + 7) >> 3;
+      if (ntl > NT) ntl = NT;
+      float s[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[nt][c] = 0.f;
+      am_rows_x_cols<KS, NT, DS>(s, Qs + warp * 16 * DS, Ks, 0, ntl, lane);
+      // ---- masks + running max
+      float cmA = -INFINITY, cmB = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt < ntl) {
+          const int jl = nt * 8 + 2 * tig;
+          const float2 km = *reinterpret_cast<const float2*>(km_s + jl);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = j0 + jl + (c & 1), i = (c < 2) ? iA : iB;
+            const bool keep = ((c & 1) ? km.y : km.x) != 0.f && j <= i;
+            float v = keep ? s[nt][c] * dm.inv_sqrt_d : CAST_NEG_FILL;
+            if (j >= T) v = -INFINITY;
+            s[nt][c] = v;
+            if (c < 2) cmA = fmaxf(cmA, v); else cmB = fmaxf(cmB, v);
+          }
+        }
+      }
+      cmA = quad_max(cmA);
+      cmB = quad_max(cmB);
+      const float nmA = fmaxf(mA, cmA), nmB = fmaxf(mB, cmB);
+      const float alA = __expf(mA - nmA), alB = __expf(mB - nmB);  // first chunk: exp(-inf) = 0
+      mA = nmA;
+      mB = nmB;
+      lA *= alA;
+      lB *= alB;
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) {
+        o[no][0] *= alA; o[no][1] *= alA; o[no][2] *= alB; o[no][3] *= alB;
+      }
+      // ---- exp, row sums (per-thread partials), dropout
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt < ntl) {
+          const int j = j0 + nt * 8 + 2 * tig;
+          float dA0, dA1, dB0, dB1;
+          drop_mul2(dr, ibA + j, dA0, dA1);
+          drop_mul2(dr, ibB + j, dB0, dB1);
+          const float e0 = __expf(s[nt][0] - mA), e1 = __expf(s[nt][1] - mA);
+          const float e2 = __expf(s[nt][2] - mB), e3 = __expf(s[nt][3] - mB);
+          lA += e0 + e1;
+          lB += e2 + e3;
+          s[nt][0] = e0 * dA0; s[nt][1] = e1 * dA1; s[nt][2] = e2 * dB0; s[nt][3] = e3 * dB1;
+        }
+      }
+      am_frag_x_rows<NTO, NT, DS>(o, s, Vs, 0, ntl, g, tig);
+    }
+    __syncthreads();  // stage st is free for the copy issued two iterations later
+  }
+  // ---- normalise, query mask, heads merged + residual (outputs += queries)
+  lA = quad_sum(lA);
+  lB = quad_sum(lB);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int i = half ? iB : iA;
+    if (i < 0) continue;
+    const bool live = wact && i >= qstart;
+    const float l = half ? lB : lA, m = half ? mB : mA;
+    const float linv = live ? 1.0f / l : 0.f;
+    const float f = live ? a.qmask[rowbase + i] * linv : 0.f;
+    if (tig == 0) {
+      if (a.row_max) a.row_max[sbase + i] = live ? m : 0.f;
+      if (a.row_linv) a.row_linv[sbase + i] = linv;
+    }
+#pragma unroll
+    for (int no = 0; no < NTO; ++no)
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = no * 8 + 2 * tig + cc;
+        if (c < d) {
+          const long off = (rowbase + i) * dm.H + hh * d + c;
+          a.out[off] = o[no][half * 2 + cc] * f + a.resid[off];
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dQ
+struct AttnBwdMmaArgs {
+  AttnBwdArgs b;
+  const float* out;    // forward output (P~ V + queries) [B*T, H]
+  const float* resid;  // queries = LN(x) [B*T, H]
+};
+
+template <int KS, int NT>
+__global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TC = 8 * NT;
+  const AttnBwdArgs& a = aa.b;
+  CAST_DYN_SMEM(float, sm);
+  __shared__ int s_first[2];
+  float* Qs = sm;                   // [64][DS]
+  float* dOs = Qs + AM_T * DS;      // [64][DS]
+  float* Kst = dOs + AM_T * DS;     // [2][TC][DS]
+  float* Vst = Kst + 2 * TC * DS;   // [2][TC][DS]
+  float* kms = Vst + 2 * TC * DS;   // [2][TC]
+  float* Dsm = kms + 2 * TC;        // [64] D_i of the tile's rows
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int T = dm.T, d = dm.d;
+  int b, hh, ntile, tile;
+  am_block(dm, b, hh, ntile, tile);
+  const int q0 = am_row0(T, ntile, tile, AM_T);
+  const long rowbase = (long)b * T;
+  const long sbase = ((long)b * dm.h + hh) * T;
+  int first_key, qstart;
+  am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
+  if (q0 + AM_T <= qstart) {  // padding-only tile: zero gradient
+    for (int idx = t; idx < AM_T * d; idx += AM_THREADS) {
+      const int i = q0 + idx / d, c = idx % d;
+      if (i >= 0) a.dQ[(rowbase + i) * a.lddq + hh * d + c] = 0.f;
+    }
+    for (int r = t; r < AM_T; r += AM_THREADS)
+      if (q0 + r >= 0) a.rowD[sbase + q0 + r] = 0.f;
+    return;
+  }
+  // only kept keys (first_key <= j <= i) carry dS; fully-masked (uniform) rows have dS == 0
+  const int kend = q0 + AM_T;
+  const int kbeg = (first_key / TC) * TC;
+  const int nch = kend > kbeg ? (kend - kbeg + TC - 1) / TC : 0;
+  const int r0 = q0 + warp * 16;
+  const int iA = r0 + g, iB = iA + 8;
+  const int rlive = qstart > first_key ? qstart : first_key;  // rows below have zero dQ
+  const bool wact = r0 + 16 > rlive;
+  const int wkend = r0 + 16;
+
+  const float* Kg = a.K + rowbase * a.ldk + hh * d;
+  const float* Vg = a.V + rowbase * a.ldv + hh * d;
+  const bool vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
+  auto issue = [&](int j0, int st) {
+    am_load_rows_async<DS>(Kst + st * TC * DS, Kg, a.ldk, j0, TC, T, d, vk);
+    am_load_rows_async<DS>(Vst + st * TC * DS, Vg, a.ldv, j0, TC, T, d, vv);
+    if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
+    cp_async_commit();
+  };
+  am_load_rows_async<DS>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, AM_T, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
+  am_load_rows_async<DS>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, AM_T, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
+  if (nch > 0) issue(kbeg, 0); else cp_async_commit();
+  am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
+  // D_i = dO_i . (out_i - queries_i) over this head's columns: one warp per row
+  for (int r = warp; r < AM_T; r += AM_THREADS / 32) {
+    const int i = q0 + r;
+    float acc = 0.f;
+    if (i >= qstart && i >= 0) {
+      const long off = (rowbase + i) * dm.H + hh * d;
+      for (int c = lane; c < d; c += 32) acc += a.dO[off + c] * (aa.out[off + c] - aa.resid[off + c]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      Dsm[r] = acc;
+      if (i >= 0) a.rowD[sbase + i] = acc;
+    }
+  }
+  const Drop dr = make_drop(a.rate, a.seed, a.step, a.site);
+  const unsigned long long ibA = ((unsigned long long)((long)hh * dm.B + b) * T + (unsigned long long)(long)iA) * T;
+  const unsigned long long ibB = ibA + 8ull * T;
+  const bool okA = iA >= rlive, okB = iB >= rlive;  // (rlive >= 0)
+  const float mxA = okA ? a.row_max[sbase + iA] : 0.f, mxB = okB ? a.row_max[sbase + iB] : 0.f;
+  const float liA = okA ? a.row_linv[sbase + iA] : 0.f, liB = okB ? a.row_linv[sbase + iB] : 0.f;
+  const float qmA = okA ? a.qmask[rowbase + iA] : 0.f, qmB = okB ? a.qmask[rowbase + iB] : 0.f;
+  float o[NTO][4];
+#pragma unroll
+  for (int no = 0; no < NTO; ++no)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[no][c] = 0.f;
+
+  for (int ci = 0; ci < nch; ++ci) {
+    const int j0 = kbeg + ci * TC, st = ci & 1;
+    if (ci + 1 < nch) {
+      issue(j0 + TC, st ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (wact && j0 < wkend) {
+      const float* Ks = Kst + st * TC * DS;
+      const float* Vs = Vst + st * TC * DS;
+      const float* km_s = kms + st * TC;
+      int ntl = (wkend - j0 + 7) >> 3;
+      if (ntl > NT) ntl = NT;
+      float s[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[nt][c] = dp[nt][c] = 0.f;
+      am_rows_x_cols<KS, NT, DS>(s, Qs + warp * 16 * DS, Ks, 0, ntl, lane);
+      am_rows_x_cols<KS, NT, DS>(dp, dOs + warp * 16 * DS, Vs, 0, ntl, lane);
+      const float DA = Dsm[warp * 16 + g], DB = Dsm[warp * 16 + g + 8];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt < ntl) {
+          const int jl = nt * 8 + 2 * tig;
+          const float2 km = *reinterpret_cast<const float2*>(km_s + jl);
+          float dm0[4];
+          drop_mul2(dr, ibA + j0 + jl, dm0[0], dm0[1]);
+          drop_mul2(dr, ibB + j0 + jl, dm0[2], dm0[3]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = j0 + jl + (c & 1), i = (c < 2) ? iA : iB;
+            const bool keep = ((c & 1) ? km.y : km.x) != 0.f && j <= i && i >= rlive;
+            const float mx = (c < 2) ? mxA : mxB, li = (c < 2) ? liA : liB, qm = (c < 2) ? qmA : qmB;
+            const float D = (c < 2) ? DA : DB;
+            const float p = __expf(s[nt][c] * dm.inv_sqrt_d - mx) * li;
+            const float dpt = dp[nt][c] * qm * dm0[c];
+            s[nt][c] = keep ? p * (dpt - D) * dm.inv_sqrt_d : 0.f;
+          }
+        }
+      }
+      am_frag_x_rows<NTO, NT, DS>(o, s, Ks, 0, ntl, g, tig);
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int i = half ? iB : iA;
+    if (i < 0) continue;
+    const bool live = wact && i >= rlive;
+#pragma unroll
+    for (int no = 0; no < NTO; ++no)
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = no * 8 + 2 * tig + cc;
+        if (c < d) a.dQ[(rowbase + i) * a.lddq + hh * d + c] = live ? o[no][half * 2 + cc] : 0.f;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dK, dV
+template <int KS, int NT>
+__global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TC = 8 * NT;
+  const AttnBwdArgs& a = aa.b;
+  CAST_DYN_SMEM(float, sm);
+  __shared__ int s_first[2];
+  float* Ks = sm;                    // [64][DS]
+  float* Vs = Ks + AM_T * DS;        // [64][DS]
+  float* Qst = Vs + AM_T * DS;       // [2][TC][DS]
+  float* dOst = Qst + 2 * TC * DS;   // [2][TC][DS]
+  float* stat = dOst + 2 * TC * DS;  // [2][4][TC]: row max, 1/rowsum, D, query mask of the chunk's queries
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int T = dm.T, d = dm.d;
+  int b, hh, ntile, tile;
+  am_block(dm, b, hh, ntile, tile);
+  const int k0 = am_row0(T, ntile, tile, AM_T);
+  const long rowbase = (long)b * T;
+  const long sbase = ((long)b * dm.h + hh) * T;
+  int first_key, qstart;
+  am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
+  const bool has_uniform = qstart < first_key;  // some computed (non-padding) row is fully masked
+  if (k0 + AM_T <= first_key && !has_uniform) {
+    // every key of this tile is masked and no row is uniform: P == 0 on the whole tile => zero gradients
+    for (int idx = t; idx < AM_T * d; idx += AM_THREADS) {
+      const int j = k0 + idx / d, c = idx % d;
+      if (j >= 0) {
+        a.dK[(rowbase + j) * a.lddk + hh * d + c] = 0.f;
+        a.dV[(rowbase + j) * a.lddv + hh * d + c] = 0.f;
+      }
+    }
+    return;
+  }
+  const Drop dr = make_drop(a.rate, a.seed, a.step, a.site);
+  // query chunks (TC rows, aligned to the end of the sequence) this key tile needs: those that hold queries >= k0, and
+  // those that hold uniform rows (which reach every key)
+  const int nchunk = (T + TC - 1) / TC;
+  auto needed = [&](int cc) {
+    const int c0 = am_row0(T, nchunk, cc, TC);
+    if (c0 + TC <= qstart) return false;                       // padding rows only
+    const bool cuni = has_uniform && c0 < first_key;
+    return cuni || c0 + TC > k0;
+  };
+  const float* Qg = a.Q + rowbase * a.ldq + hh * d;
+  const float* dOg = a.dO + rowbase * dm.H + hh * d;
+  const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vo = am_vec2_ok(a.dO, dm.H, d, hh);
+  auto issue = [&](int cc, int st) {
+    const int c0 = am_row0(T, nchunk, cc, TC);
+    am_load_rows_async<DS>(Qst + st * TC * DS, Qg, a.ldq, c0, TC, T, d, vq);
+    am_load_rows_async<DS>(dOst + st * TC * DS, dOg, dm.H, c0, TC, T, d, vo);
+    if (t < TC) {
+      const int i = c0 + t;
+      const bool ok = i >= qstart && i >= 0;
+      const long si = sbase + (ok ? i : 0), ri = rowbase + (ok ? i : 0);
+      float* sp = stat + st * 4 * TC + t;
+      cp_async<4>(sp, a.row_max + si, ok);
+      cp_async<4>(sp + TC, a.row_linv + si, ok);
+      cp_async<4>(sp + 2 * TC, a.rowD + si, ok);
+      cp_async<4>(sp + 3 * TC, a.qmask + ri, ok);
+    }
+    cp_async_commit();
+  };
+  auto next_needed = [&](int cc) {
+    while (cc < nchunk && !needed(cc)) ++cc;
+    return cc;
+  };
+  am_load_rows_async<DS>(Ks, a.K + rowbase * a.ldk + hh * d, a.ldk, k0, AM_T, T, d, am_vec2_ok(a.K, a.ldk, d, hh));
+  am_load_rows_async<DS>(Vs, a.V + rowbase * a.ldv + hh * d, a.ldv, k0, AM_T, T, d, am_vec2_ok(a.V, a.ldv, d, hh));
+  int cc = next_needed(0);
+  if (cc < nchunk) issue(cc, 0); else cp_async_commit();
+  am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
+
+  const int r0 = k0 + warp * 16;
+  const int jA = r0 + g, jB = jA + 8;
+  const bool kmA = jA >= 0 && a.kmask[rowbase + jA] != 0.f, kmB = jB >= 0 && a.kmask[rowbase + jB] != 0.f;
+  const int qs0 = qstart > 0 ? qstart : 0;
+  const unsigned long long hb = (unsigned long long)((long)hh * dm.B + b) * T;
+  float gk[NTO][4], gv[NTO][4];
+#pragma unroll
+  for (int no = 0; no < NTO; ++no)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) gk[no][c] = gv[no][c] = 0.f;
+
+  for (int it = 0; cc < nchunk; ++it) {
+    const int st = it & 1;
+    const int c0 = am_row0(T, nchunk, cc, TC);
+    const bool cuni = has_uniform && c0 < first_key;  // chunk holds uniform rows: they reach every key
+    const int cn = next_needed(cc + 1);
+    if (cn < nchunk) {
+      issue(cn, st ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    // queries before the warp's first key see none of its keys unless they are uniform rows
+    int nt0 = cuni ? 0 : (r0 - c0) >> 3;
+    if (nt0 < 0) nt0 = 0;
+    if (r0 + 16 > 0 && nt0 < NT) {
+      const float* Qc = Qst + st * TC * DS;
+      const float* dOc = dOst + st * TC * DS;
+      const float* sp = stat + st * 4 * TC;
+      float s[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[nt][c] = dp[nt][c] = 0.f;
+      am_rows_x_cols<KS, NT, DS>(s, Ks + warp * 16 * DS, Qc, nt0, NT, lane);
+      am_rows_x_cols<KS, NT, DS>(dp, Vs + warp * 16 * DS, dOc, nt0, NT, lane);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt >= nt0) {
+          const int il = nt * 8 + 2 * tig;
+          const float2 mx = *reinterpret_cast<const float2*>(sp + il);
+          const float2 li = *reinterpret_cast<const float2*>(sp + TC + il);
+          const float2 DD = *reinterpret_cast<const float2*>(sp + 2 * TC + il);
+          const float2 qm = *reinterpret_cast<const float2*>(sp + 3 * TC + il);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = c0 + il + (c & 1), j = (c < 2) ? jA : jB;
+            const bool keep = ((c < 2) ? kmA : kmB) && j <= i;
+            const float sv = keep ? s[nt][c] * dm.inv_sqrt_d : CAST_NEG_FILL;
+            // skipped rows (padding / before the sequence) carry nothing: never exp() them (inf * 0)
+            const float p = i >= qs0 ? __expf(sv - ((c & 1) ? mx.y : mx.x)) * ((c & 1) ? li.y : li.x) : 0.f;
+            const unsigned long long eidx = (hb + (unsigned long long)(long)i) * T + (unsigned long long)(long)j;
+            const float mul = ((c & 1) ? qm.y : qm.x) * drop_mul(dr, eidx);
+            const float dpt = dp[nt][c] * mul;
+            s[nt][c] = p * mul;
+            dp[nt][c] = keep ? p * (dpt - ((c & 1) ? DD.y : DD.x)) * dm.inv_sqrt_d : 0.f;
+          }
+        }
+      }
+      am_frag_x_rows<NTO, NT, DS>(gv, s, dOc, nt0, NT, g, tig);
+      am_frag_x_rows<NTO, NT, DS>(gk, dp, Qc, nt0, NT, g, tig);
+    }
+    __syncthreads();
+    cc = cn;
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int j = half ? jB : jA;
+    if (j < 0) continue;
+#pragma unroll
+    for (int no = 0; no < NTO; ++no)
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int c = no * 8 + 2 * tig + c2;
+        if (c < d) {
+          a.dK[(rowbase + j) * a.lddk + hh * d + c] = gk[no][half * 2 + c2];
+          a.dV[(rowbase + j) * a.lddv + hh * d + c] = gv[no][half * 2 + c2];
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+template <int KS, int NT>
+static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba, const AttnDims& dm,
+                      cudaStream_t stream) {
+  constexpr int DS = 8 * KS + 4, TC = 8 * NT;
+  static size_t cfg[3] = {48 * 1024, 48 * 1024, 48 * 1024};
+  const int ntile = (int)cdiv(dm.T, AM_T);
+  const dim3 grid((unsigned)(dm.B * dm.h), (unsigned)ntile);
+  const size_t row = sizeof(float) * DS;
+  if (which == 0) {
+    const size_t smem = (AM_T + 4 * TC) * row + sizeof(float) * 2 * TC;
+    auto kf = attn_fwd_mma_kernel<KS, NT>;
+    if (smem > cfg[0]) {
+      cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cfg[0] = smem;
+    }
+    CAST_LAUNCH(kf, grid, dim3(AM_THREADS), smem, stream, *fa, dm);
+  } else if (which == 1) {
+    const size_t smem = (2 * AM_T + 4 * TC) * row + sizeof(float) * (2 * TC + AM_T);
+    auto kf = attn_bwd_dq_mma_kernel<KS, NT>;
+    if (smem > cfg[1]) {
+      cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cfg[1] = smem;
+    }
+    CAST_LAUNCH(kf, grid, dim3(AM_THREADS), smem, stream, *ba, dm);
+  } else {
+    const size_t smem = (2 * AM_T + 4 * TC) * row + sizeof(float) * 8 * TC;
+    auto kf = attn_bwd_dkv_mma_kernel<KS, NT>;
+    if (smem > cfg[2]) {
+      cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cfg[2] = smem;
+    }
+    CAST_LAUNCH(kf, grid, dim3(AM_THREADS), smem, stream, *ba, dm);
+  }
+  return CAST_OK;
+}
+
+bool attn_mma_supported(const AttnDims& dm) { return dm.d >= 1 && dm.d <= 64 && (long)dm.B * dm.h < 2147483647L; }
+
+static int g_chunk_tiles = 4;  // columns per streamed chunk / 8 (4 or 8); cast_attn_set_chunk (tuning hook)
+int attn_mma_set_chunk(int nt) {
+  if (nt != 4 && nt != 8) return set_error(CAST_ERR_BAD_ARG, "attention (mma): chunk must be 32 or 64 columns");
+  g_chunk_tiles = nt;
+  return CAST_OK;
+}
+
+// which: 0 = forward (fa), 1 = backward dQ, 2 = backward dK/dV (ba + out/resid)
+int dispatch_att_mma(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, const float* out, const float* resid,
+                     const AttnDims& dm, cudaStream_t stream) {
+  AttnBwdMmaArgs bm{};
+  if (ba) { bm.b = *ba; bm.out = out; bm.resid = resid; }
+  const int ks = (dm.d + 7) / 8;
+  if (g_chunk_tiles == 8) {
+    switch (ks) {
+#define CAST_K(K) case K: return launch_mma<K, 8>(which, fa, &bm, dm, stream);
+      CAST_K(1) CAST_K(2) CAST_K(3) CAST_K(4) CAST_K(5) CAST_K(6) CAST_K(7) CAST_K(8)
+#undef CAST_K
+    }
+  } else {
+    switch (ks) {
+#define CAST_K(K) case K: return launch_mma<K, 4>(which, fa, &bm, dm, stream);
+      CAST_K(1) CAST_K(2) CAST_K(3) CAST_K(4) CAST_K(5) CAST_K(6) CAST_K(7) CAST_K(8)
+#undef CAST_K
+    }
+  }
+  return set_error(CAST_ERR_UNSUPPORTED, "attention (mma): head width > 64");
+}
+
+}  // namespace cast

@@ -42,12 +42,14 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- counter-based dropout ------------------------------------------------------------------------------
-// keep(site, idx) = hash(seed, step, site, idx) >= thresh, thresh = floor(rate * 2^32); scale = 1/(1-rate).
+// keep(site, idx) = field(idx & 1) of hash(seed, step, site, idx >> 1) >= thresh, thresh = floor(rate * 2^16);
+// scale = 1/(1-rate).  One 32-bit hash word serves two adjacent elements (16 bits each): kernels whose threads own
+// element pairs (the attention probabilities, B*h*T*T of them per block) pay half a hash per element.
 // Masks are a pure function of (seed, step, site, flat element index in the TF-shaped tensor), so the
 // backward kernels regenerate them and tests can hand the identical masks to the oracle.
 struct Drop {
   unsigned k0, k1;   // mixed (seed, step, site)
-  unsigned thresh;   // 0 => dropout disabled
+  unsigned thresh;   // 16-bit threshold; 0 => dropout disabled
   float scale;
 };
 
@@ -68,7 +70,7 @@ __device__ __forceinline__ Drop make_drop(float rate, unsigned long long seed, c
       mix64(seed + st * 0x9E3779B97F4A7C15ull) ^ mix64(0xD1B54A32D192ED03ull * (unsigned long long)(site + 1));
   d.k0 = (unsigned)key;
   d.k1 = (unsigned)(key >> 32);
-  d.thresh = rate > 0.f ? (unsigned)fmin(4294967295.0, floor((double)rate * 4294967296.0)) : 0u;
+  d.thresh = rate > 0.f ? (unsigned)fmin(65535.0, floor((double)rate * 65536.0)) : 0u;
   d.scale = rate > 0.f ? 1.0f / (1.0f - rate) : 1.0f;
   return d;
 }
@@ -88,7 +90,23 @@ __device__ __forceinline__ unsigned drop_hash(const Drop& d, unsigned long long 
   return x;
 }
 
-__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) { return drop_hash(d, idx) >= d.thresh; }
+__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  const unsigned h = drop_hash(d, idx >> 1);
+  return ((idx & 1ull) ? (h >> 16) : (h & 0xffffu)) >= d.thresh;
+}
+
+// multipliers of the adjacent elements idx, idx + 1 (idx even => one hash word)
+__device__ __forceinline__ void drop_mul2(const Drop& d, unsigned long long idx, float& m0, float& m1) {
+  if (d.thresh == 0u) { m0 = m1 = 1.0f; return; }
+  if ((idx & 1ull) == 0ull) {
+    const unsigned h = drop_hash(d, idx >> 1);
+    m0 = (h & 0xffffu) >= d.thresh ? d.scale : 0.0f;
+    m1 = (h >> 16) >= d.thresh ? d.scale : 0.0f;
+  } else {
+    m0 = drop_keep(d, idx) ? d.scale : 0.0f;
+    m1 = drop_keep(d, idx + 1) ? d.scale : 0.0f;
+  }
+}
 
 // multiplier applied by tf.layers.dropout at element idx (0 or 1/(1-rate)); 1 when disabled
 __device__ __forceinline__ float drop_mul(const Drop& d, unsigned long long idx) {

@@ -427,7 +427,7 @@ class Engine:
                            b.rlinv.data_ptr(), ids.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed,
                            self.step_ptr,
                            block_site(tower, i, 1), dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H,
-                           self._stream())
+                           b.y.data_ptr(), b.qn.data_ptr(), self._stream())
                 dst = tb.dx_in if i == 0 else t[0]
                 self._call(self.lib.cast_qkv_bwd, dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), dy.data_ptr(),
                            x_i.data_ptr(), b.qn.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
@@ -449,7 +449,8 @@ class Engine:
                        dy.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), b.rmax.data_ptr(), b.rlinv.data_ptr(),
                        ids.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed, self.step_ptr,
                        block_site(tower, i, 1),
-                       dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H, self._stream())
+                       dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H, b.y.data_ptr(), b.qn.data_ptr(),
+                       self._stream())
             self.linear_wgrad(c, b.qn, dQ, self.G[pre + "q.w"], self.G[pre + "q.b"])
             self.linear_wgrad(c, x_i, dK, self.G[pre + "k.w"], self.G[pre + "k.b"])
             self.linear_wgrad(c, x_i, dV, self.G[pre + "v.w"], self.G[pre + "v.b"])

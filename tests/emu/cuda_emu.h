@@ -79,6 +79,15 @@ inline uint64_t exchange(uint64_t v, int src_lane) {
   sync_warp();
   return r;
 }
+// every lane publishes one pointer; `reader(ptrs)` runs while all 32 pointers (and what they point to) are stable
+template <class F>
+inline void warp_publish(const void* mine, F&& reader) {
+  uint64_t* s = &t_ctx->slots[(size_t)(t_lin / 32) * 32];
+  s[t_lin % 32] = (uint64_t)(uintptr_t)mine;
+  sync_warp();
+  reader(s);
+  sync_warp();
+}
 }  // namespace cast_emu
 
 #define threadIdx cast_emu::t_threadIdx
