@@ -44,21 +44,32 @@ __device__ __forceinline__ void am_first2(const float* __restrict__ kmask_b, con
 }
 
 // asynchronous tile load: dst[r][c] = src[(row0 + r) * ld + c] for 0 <= row0 + r < T and c < d, zero rows outside the
-// sequence; columns d.. of dst are left alone (zeroed once by am_zero_pad).  One warp per row, 8-byte copies when the
-// rows allow it.
-template <int DS>
+// sequence; columns d.. of dst are left alone (zeroed once by am_zero_pad).  Warp w copies rows w, w+4, ..; lane l the
+// 8-byte column pair l (vec2: d even, rows 8-byte aligned), else 4-byte copies.
+template <int NROWS, int DS>
 __device__ __forceinline__ void am_load_rows_async(float* __restrict__ dst, const float* __restrict__ src, long ld,
-                                                   int row0, int nrows, int T, int d, bool vec2) {
+                                                   int row0, int T, int d, bool vec2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < nrows; r += AM_THREADS / 32) {
-    const int row = row0 + r;
-    const bool ok = row >= 0 && row < T;
-    const float* s = src + (long)(ok ? row : 0) * ld;
-    float* o = dst + r * DS;
-    if (vec2) {
-      for (int c = lane; 2 * c < d; c += 32) cp_async<8>(o + 2 * c, s + 2 * c, ok);
-    } else {
-      for (int c = lane; c < d; c += 32) cp_async<4>(o + c, s + c, ok);
+  if (vec2) {
+    if (2 * lane < d) {
+      float* o = dst + warp * DS + 2 * lane;
+      int row = row0 + warp;
+      const float* s = src + (long)row * ld + 2 * lane;
+#pragma unroll
+      for (int k = 0; k < NROWS / 4; ++k) {
+        const bool ok = (unsigned)row < (unsigned)T;
+        cp_async<8>(o, ok ? s : src, ok);
+        o += 4 * DS;
+        s += 4 * ld;
+        row += 4;
+      }
+    }
+  } else {
+    for (int r = warp; r < NROWS; r += AM_THREADS / 32) {
+      const int row = row0 + r;
+      const bool ok = (unsigned)row < (unsigned)T;
+      const float* s = src + (long)(ok ? row : 0) * ld;
+      for (int c = lane; c < d; c += 32) cp_async<4>(dst + r * DS + c, s + c, ok);
     }
   }
 }
@@ -74,7 +85,8 @@ __device__ __forceinline__ void am_zero_pad(float* __restrict__ buf, int rows, i
     for (int c = d; c < DP; ++c) buf[r * DS + c] = 0.f;
 }
 
-// acc[nt] (16 x 8 each, nt < NT) += A[16 x 8KS] * B[8NT x 8KS]^T for the n-tiles nt_lo <= nt < nt_hi (warp-uniform)
+// acc[nt] (16 x 8 each, nt < NT) += A[16 x 8KS] * B[8NT x 8KS]^T for the n-tiles nt_lo <= nt < nt_hi (warp-uniform).
+// The three TF32 passes run across all n-tiles before the next pass, so dependent MMAs are NT instructions apart.
 template <int KS, int NT, int DS>
 __device__ __forceinline__ void am_rows_x_cols(float (&acc)[NT][4], const float* __restrict__ As,
                                                const float* __restrict__ Bs, int nt_lo, int nt_hi, int lane) {
@@ -83,16 +95,27 @@ __device__ __forceinline__ void am_rows_x_cols(float (&acc)[NT][4], const float*
     unsigned af[4], ah[4], al[4];
     ldsm_a<DS>(af, As, ks * 8, lane);
     tf32_split_n(af, ah, al);
+    unsigned bh[NT][2], bl[NT][2];
 #pragma unroll
     for (int np = 0; np < NT / 2; ++np) {
       if (2 * np + 1 >= nt_lo && 2 * np < nt_hi) {
-        unsigned bf[4], bh[4], bl[4];
+        unsigned bf[4];
         ldsm_b2<DS>(bf, Bs + np * 16 * DS, ks * 8, lane);
-        tf32_split_n(bf, bh, bl);
-        if (2 * np >= nt_lo) mma_3x(acc[2 * np], ah, al, bh[0], bh[1], bl[0], bl[1]);
-        if (2 * np + 1 < nt_hi) mma_3x(acc[2 * np + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+        tf32_split(__uint_as_float(bf[0]), bh[2 * np][0], bl[2 * np][0]);
+        tf32_split(__uint_as_float(bf[1]), bh[2 * np][1], bl[2 * np][1]);
+        tf32_split(__uint_as_float(bf[2]), bh[2 * np + 1][0], bl[2 * np + 1][0]);
+        tf32_split(__uint_as_float(bf[3]), bh[2 * np + 1][1], bl[2 * np + 1][1]);
       }
     }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      if (nt >= nt_lo && nt < nt_hi) mma_tf32(acc[nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      if (nt >= nt_lo && nt < nt_hi) mma_tf32(acc[nt], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      if (nt >= nt_lo && nt < nt_hi) mma_tf32(acc[nt], ah, bh[nt][0], bh[nt][1]);
   }
 }
 
@@ -110,13 +133,18 @@ __device__ __forceinline__ void am_frag_x_rows(float (&out)[NTO][4], const float
       tf32_split(p[kk][1], ah[2], al[2]);  // (row g,   k-slot tig + 4) <- column 2 tig + 1
       tf32_split(p[kk][3], ah[3], al[3]);  // (row g+8, k-slot tig + 4)
       const float* m0 = Ms + (kk * 8 + 2 * tig) * DS + g;
+      unsigned bh[NTO][2], bl[NTO][2];
 #pragma unroll
       for (int no = 0; no < NTO; ++no) {
-        unsigned bh0, bl0, bh1, bl1;
-        tf32_split(m0[no * 8], bh0, bl0);
-        tf32_split(m0[DS + no * 8], bh1, bl1);
-        mma_3x(out[no], ah, al, bh0, bh1, bl0, bl1);
+        tf32_split(m0[no * 8], bh[no][0], bl[no][0]);
+        tf32_split(m0[DS + no * 8], bh[no][1], bl[no][1]);
       }
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) mma_tf32(out[no], al, bh[no][0], bh[no][1]);
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) mma_tf32(out[no], ah, bl[no][0], bl[no][1]);
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) mma_tf32(out[no], ah, bh[no][0], bh[no][1]);
     }
   }
 }
@@ -134,7 +162,7 @@ __device__ __forceinline__ void am_block(const AttnDims& dm, int& b, int& hh, in
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int KS, int NT>
-__global__ void __launch_bounds__(AM_THREADS) attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
+__global__ void __launch_bounds__(AM_THREADS, (KS <= 7 && NT == 4) ? 4 : 1) attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TC = 8 * NT;
   CAST_DYN_SMEM(float, sm);
   __shared__ int s_first[2];
@@ -184,12 +212,12 @@ __global__ void __launch_bounds__(AM_THREADS) attn_fwd_mma_kernel(AttnFwdArgs a,
   const float* Vg = a.V + rowbase * a.ldv + hh * d;
   const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
   auto issue = [&](int j0, int st) {
-    am_load_rows_async<DS>(Kst + st * TC * DS, Kg, a.ldk, j0, TC, T, d, vk);
-    am_load_rows_async<DS>(Vst + st * TC * DS, Vg, a.ldv, j0, TC, T, d, vv);
+    am_load_rows_async<TC, DS>(Kst + st * TC * DS, Kg, a.ldk, j0, T, d, vk);
+    am_load_rows_async<TC, DS>(Vst + st * TC * DS, Vg, a.ldv, j0, T, d, vv);
     if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
     cp_async_commit();
   };
-  am_load_rows_async<DS>(Qs, Qg, a.ldq, q0, AM_T, T, d, vq);
+  am_load_rows_async<AM_T, DS>(Qs, Qg, a.ldq, q0, T, d, vq);
   issue(kbeg, 0);
   am_zero_pad<DP, DS>(sm, AM_T + 4 * TC, d);
 
@@ -203,14 +231,21 @@ __global__ void __launch_bounds__(AM_THREADS) attn_fwd_mma_kernel(AttnFwdArgs a,
 #pragma unroll
     for (int c = 0; c < 4; ++c) o[no][c] = 0.f;
 
+  // the residual tile (queries) rides in the stage that is free during the last chunk: rows [0,TC) in the K stage,
+  // rows [TC,64) in the V stage (TC = 32) -- the epilogue then reads it from shared memory
+  const float* Rg = a.resid + rowbase * dm.H + hh * d;
+  const bool vr = am_vec2_ok(a.resid, dm.H, d, hh);
+  const int rst = nch & 1;  // stage not used by the last chunk
   for (int ci = 0; ci < nch; ++ci) {
     const int j0 = kbeg + ci * TC, st = ci & 1;
     if (ci + 1 < nch) {
       issue(j0 + TC, st ^ 1);
-      cp_async_wait<1>();
     } else {
-      cp_async_wait<0>();
+      am_load_rows_async<TC, DS>(Kst + rst * TC * DS, Rg, dm.H, q0, T, d, vr);
+      if (TC < AM_T) am_load_rows_async<TC, DS>(Vst + rst * TC * DS, Rg, dm.H, q0 + TC, T, d, vr);
+      cp_async_commit();
     }
+    cp_async_wait<1>();
     __syncthreads();
     if (wact && j0 < wkend) {
       const float* Ks = Kst + st * TC * DS;
@@ -274,12 +309,16 @@ __global__ void __launch_bounds__(AM_THREADS) attn_fwd_mma_kernel(AttnFwdArgs a,
     __syncthreads();  // stage st is free for the copy issued two iterations later
   }
   // ---- normalise, query mask, heads merged + residual (outputs += queries)
+  cp_async_wait<0>();
+  __syncthreads();
   lA = quad_sum(lA);
   lB = quad_sum(lB);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int i = half ? iB : iA;
     if (i < 0) continue;
+    const int rr = warp * 16 + g + half * 8;
+    const float* rrow = (rr < TC ? Kst + rst * TC * DS + rr * DS : Vst + rst * TC * DS + (rr - TC) * DS);
     const bool live = wact && i >= qstart;
     const float l = half ? lB : lA, m = half ? mB : mA;
     const float linv = live ? 1.0f / l : 0.f;
@@ -295,7 +334,7 @@ __global__ void __launch_bounds__(AM_THREADS) attn_fwd_mma_kernel(AttnFwdArgs a,
         const int c = no * 8 + 2 * tig + cc;
         if (c < d) {
           const long off = (rowbase + i) * dm.H + hh * d + c;
-          a.out[off] = o[no][half * 2 + cc] * f + a.resid[off];
+          a.out[off] = o[no][half * 2 + cc] * f + rrow[c];
         }
       }
   }
@@ -352,13 +391,13 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaA
   const float* Vg = a.V + rowbase * a.ldv + hh * d;
   const bool vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
   auto issue = [&](int j0, int st) {
-    am_load_rows_async<DS>(Kst + st * TC * DS, Kg, a.ldk, j0, TC, T, d, vk);
-    am_load_rows_async<DS>(Vst + st * TC * DS, Vg, a.ldv, j0, TC, T, d, vv);
+    am_load_rows_async<TC, DS>(Kst + st * TC * DS, Kg, a.ldk, j0, T, d, vk);
+    am_load_rows_async<TC, DS>(Vst + st * TC * DS, Vg, a.ldv, j0, T, d, vv);
     if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
     cp_async_commit();
   };
-  am_load_rows_async<DS>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, AM_T, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
-  am_load_rows_async<DS>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, AM_T, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
+  am_load_rows_async<AM_T, DS>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
+  am_load_rows_async<AM_T, DS>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
   if (nch > 0) issue(kbeg, 0); else cp_async_commit();
   am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
   // D_i = dO_i . (out_i - queries_i) over this head's columns: one warp per row
@@ -499,8 +538,8 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
   const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vo = am_vec2_ok(a.dO, dm.H, d, hh);
   auto issue = [&](int cc, int st) {
     const int c0 = am_row0(T, nchunk, cc, TC);
-    am_load_rows_async<DS>(Qst + st * TC * DS, Qg, a.ldq, c0, TC, T, d, vq);
-    am_load_rows_async<DS>(dOst + st * TC * DS, dOg, dm.H, c0, TC, T, d, vo);
+    am_load_rows_async<TC, DS>(Qst + st * TC * DS, Qg, a.ldq, c0, T, d, vq);
+    am_load_rows_async<TC, DS>(dOst + st * TC * DS, dOg, dm.H, c0, T, d, vo);
     if (t < TC) {
       const int i = c0 + t;
       const bool ok = i >= qstart && i >= 0;
@@ -517,8 +556,8 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
     while (cc < nchunk && !needed(cc)) ++cc;
     return cc;
   };
-  am_load_rows_async<DS>(Ks, a.K + rowbase * a.ldk + hh * d, a.ldk, k0, AM_T, T, d, am_vec2_ok(a.K, a.ldk, d, hh));
-  am_load_rows_async<DS>(Vs, a.V + rowbase * a.ldv + hh * d, a.ldv, k0, AM_T, T, d, am_vec2_ok(a.V, a.ldv, d, hh));
+  am_load_rows_async<AM_T, DS>(Ks, a.K + rowbase * a.ldk + hh * d, a.ldk, k0, T, d, am_vec2_ok(a.K, a.ldk, d, hh));
+  am_load_rows_async<AM_T, DS>(Vs, a.V + rowbase * a.ldv + hh * d, a.ldv, k0, T, d, am_vec2_ok(a.V, a.ldv, d, hh));
   int cc = next_needed(0);
   if (cc < nchunk) issue(cc, 0); else cp_async_commit();
   am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);

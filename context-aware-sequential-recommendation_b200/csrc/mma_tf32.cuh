@@ -32,8 +32,9 @@ __device__ __forceinline__ void tf32_split_n(const unsigned (&x)[N], unsigned (&
 
 #ifndef CAST_EMU
 
+// (not volatile: a pure function of its register operands, so the scheduler may interleave independent chains)
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
