@@ -41,6 +41,7 @@ SIGNATURES = {
     "cast_colsum_workspace_bytes": (SZ, [L, L]),
     "cast_colsum": (I, [P, L, L, L, P, P, SZ, P]),
     "cast_attn_set_chunk": (I, [I]),
+    "cast_fused_set_backend": (I, [I]),
     "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P, P]),
     "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P, P, P]),
     "cast_logits_loss_workspace_bytes": (SZ, [L]),
@@ -92,6 +93,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib = bind(C.CDLL(p))
     if os.environ.get("CAST_ATTN_CHUNK"):  # tuning hook (32 or 64 columns per streamed attention chunk)
         check(lib, lib.cast_attn_set_chunk(int(os.environ["CAST_ATTN_CHUNK"])), "cast_attn_set_chunk")
+    if os.environ.get("CAST_FUSED_BACKEND"):  # A/B hook: 0 = FFMA row kernels, 1 = tensor-core row kernels
+        check(lib, lib.cast_fused_set_backend(int(os.environ["CAST_FUSED_BACKEND"])), "cast_fused_set_backend")
     if path is None:
         _LIB = lib
     return lib

@@ -191,6 +191,8 @@ attn_fwd_kernel(AttnFwdArgs a, AttnDims dm) {
     const float qm = a.qmask[rowbase + i] * linv;
     const unsigned long long ibase = ((unsigned long long)((long)hh * dm.B + b) * T + i) * T;
     float* arow = a.attn ? a.attn + ibase : nullptr;
+    if (arow)  // keys before the first kept one are skipped by the tile loop: their weight is exactly 0
+      for (int j = lane; j < kbeg; j += 32) arow[j] = 0.f;
     for (int j = kbeg + lane; j < dm.Tp4; j += 32) {
       float p = 0.f;
       if (j < kend) p = Sr[j] * qm * drop_mul(dr, ibase + j);

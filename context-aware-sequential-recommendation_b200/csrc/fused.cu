@@ -526,6 +526,10 @@ __global__ void __launch_bounds__(FT) qkv_bwd_kernel(QkvBwdArgs a, FDims d) {
   if (grp < 3 && (t & 63) < H) P[2 * H + grp * (H * H + H) + H * H + (t & 63)] = vb;
 }
 
+}  // namespace cast
+#include "fused_mma.cuh"
+namespace cast {
+
 // persistent grids: one wave of resident CTAs on the 148 SMs of a B200 (ffn_bwd: 2 CTAs/SM; qkv_bwd: 1 CTA/SM — 160
 // registers x 256 threads), so no CTA waits for a slot and the number of weight-gradient partials stays minimal
 constexpr int NUM_SMS = 148;
@@ -549,6 +553,54 @@ using namespace cast;
 
 extern "C" int cast_fused_supported(int H) { return H > 0 && H <= 64; }
 
+// 1 (default): backward row kernels on the tensor cores (fused_mma.cuh); 0: the FP32 FFMA kernels above
+static int g_fused_backend = 1;
+extern "C" int cast_fused_set_backend(int backend) {
+  if (backend != 0 && backend != 1) return set_error(CAST_ERR_BAD_ARG, "fused_set_backend");
+  g_fused_backend = backend;
+  return CAST_OK;
+}
+
+template <int KS>
+static void launch_qkv_bwd_mma(const QkvBwdArgs& a, FDims d, int grid, cudaStream_t stream) {
+  d.HS = 8 * KS + 4;
+  const size_t smem = qkv_bwd_mma_smem<KS>();
+  auto kf = qkv_bwd_mma_kernel<KS>;
+  CAST_FUSED_SMEM(kf, smem)
+  CAST_LAUNCH(kf, dim3(grid), dim3(FT), smem, stream, a, d);
+}
+template <int KS>
+static void launch_ffn_bwd_mma(const FfnBwdArgs& a, FDims d, int grid, cudaStream_t stream) {
+  d.HS = 8 * KS + 4;
+  const size_t smem = ffn_bwd_mma_smem<KS>();
+  auto kf = ffn_bwd_mma_kernel<KS>;
+  CAST_FUSED_SMEM(kf, smem)
+  CAST_LAUNCH(kf, dim3(grid), dim3(FT), smem, stream, a, d);
+}
+template <int KS>
+static void launch_ln_qkv_fwd_mma(const LnQkvArgs& a, FDims d, cudaStream_t stream) {
+  d.HS = 8 * KS + 4;
+  const long ntiles = cdiv(d.N, FR);
+  const size_t smem = ln_qkv_fwd_mma_smem<KS>();
+  auto kf = ln_qkv_fwd_mma_kernel<KS>;
+  CAST_FUSED_SMEM(kf, smem)
+  CAST_LAUNCH(kf, dim3(bwd_grid(ntiles, 1)), dim3(FT), smem, stream, a, d, ntiles);
+}
+template <int KS>
+static void launch_ln_ffn_fwd_mma(const LnFfnArgs& a, FDims d, cudaStream_t stream) {
+  d.HS = 8 * KS + 4;
+  const long ntiles = cdiv(d.N, FR);
+  const size_t smem = ln_ffn_fwd_mma_smem<KS>();
+  auto kf = ln_ffn_fwd_mma_kernel<KS>;
+  CAST_FUSED_SMEM(kf, smem)
+  CAST_LAUNCH(kf, dim3(bwd_grid(ntiles, 1)), dim3(FT), smem, stream, a, d, ntiles);
+}
+#define CAST_KS_SWITCH(H, CALL)                                                          \
+  switch (((H) + 7) / 8) {                                                               \
+    case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; \
+    case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; default: CALL(8); break; \
+  }
+
 extern "C" int cast_ln_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* Wq, const float* bq,
                                const float* Wk, const float* bk, const float* Wv, const float* bv, long N, int H,
                                float eps, float* qn, float* Q, float* K, float* V, float* mean, float* rstd,
@@ -558,6 +610,12 @@ extern "C" int cast_ln_qkv_fwd(const float* x, const float* gamma, const float* 
   if (!cast_fused_supported(H)) return set_error(CAST_ERR_UNSUPPORTED, "ln_qkv_fwd: H > 64");
   const FDims d = fdims(N, H);
   LnQkvArgs a{x, gamma, beta, {Wq, Wk, Wv}, {bq, bk, bv}, eps, qn, {Q, K, V}, mean, rstd, kmask, qmask};
+  if (g_fused_backend == 1) {
+#define CAST_CALL(K) launch_ln_qkv_fwd_mma<K>(a, d, (cudaStream_t)stream)
+    CAST_KS_SWITCH(H, CAST_CALL)
+#undef CAST_CALL
+    return check_launch("ln_qkv_fwd");
+  }
   const size_t smem = sizeof(float) * ((size_t)2 * FR * d.HS + (size_t)d.HP4 * d.HS);
   CAST_FUSED_SMEM(ln_qkv_fwd_kernel, smem)
   CAST_LAUNCH(ln_qkv_fwd_kernel, dim3((unsigned)cdiv(N, FR)), dim3(FT), smem, (cudaStream_t)stream, a, d);
@@ -576,6 +634,12 @@ extern "C" int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* 
   const FDims d = fdims(N, H);
   LnFfnArgs a{y, gamma, beta, W1, b1, W2, b2, ids, eps, drop_rate, seed, step, site_hidden, site_out,
               zn, h1d, xout, mean, rstd};
+  if (g_fused_backend == 1) {
+#define CAST_CALL(K) launch_ln_ffn_fwd_mma<K>(a, d, (cudaStream_t)stream)
+    CAST_KS_SWITCH(H, CAST_CALL)
+#undef CAST_CALL
+    return check_launch("ln_ffn_fwd");
+  }
   const size_t smem = sizeof(float) * ((size_t)2 * FR * d.HS + (size_t)d.HP4 * d.HS);
   CAST_FUSED_SMEM(ln_ffn_fwd_kernel, smem)
   CAST_LAUNCH(ln_ffn_fwd_kernel, dim3((unsigned)cdiv(N, FR)), dim3(FT), smem, (cudaStream_t)stream, a, d);
@@ -599,13 +663,19 @@ extern "C" int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, co
     return set_error(CAST_ERR_WORKSPACE, "ffn_bwd: workspace too small");
   const FDims d = fdims(N, H);
   const long ntiles = cdiv(N, FR);
-  const int grid = bwd_grid(ntiles);
+  const int grid = bwd_grid(ntiles, g_fused_backend == 1 ? 1 : 2);
   FfnBwdArgs a{dx, zn, h1d, y, mean, rstd, gamma, W1, W2, ids, drop_rate, seed, step, site_out, dy,
                static_cast<float*>(workspace), ntiles};
-  const size_t smem = sizeof(float) * ((size_t)4 * FR * d.HS + (size_t)2 * d.HP4 * FTS + (size_t)2 * d.HP4 * d.HS +
-                                       (size_t)FR * 4);
-  CAST_FUSED_SMEM(ffn_bwd_kernel, smem)
-  CAST_LAUNCH(ffn_bwd_kernel, dim3(grid), dim3(FT), smem, (cudaStream_t)stream, a, d);
+  if (g_fused_backend == 1) {
+#define CAST_CALL(K) launch_ffn_bwd_mma<K>(a, d, grid, (cudaStream_t)stream)
+    CAST_KS_SWITCH(H, CAST_CALL)
+#undef CAST_CALL
+  } else {
+    const size_t smem = sizeof(float) * ((size_t)4 * FR * d.HS + (size_t)2 * d.HP4 * FTS + (size_t)2 * d.HP4 * d.HS +
+                                         (size_t)FR * 4);
+    CAST_FUSED_SMEM(ffn_bwd_kernel, smem)
+    CAST_LAUNCH(ffn_bwd_kernel, dim3(grid), dim3(FT), smem, (cudaStream_t)stream, a, d);
+  }
   int rc = check_launch("ffn_bwd");
   if (rc) return rc;
   const long count = 2L * H + 2L * ((long)H * H + H);
@@ -627,10 +697,16 @@ extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, c
   const long ntiles = cdiv(N, FR);
   const int grid = bwd_grid(ntiles, 1);
   QkvBwdArgs a{dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv, dx, static_cast<float*>(workspace), ntiles};
-  const size_t smem = sizeof(float) * ((size_t)3 * FR * d.HS + (size_t)2 * d.HP4 * FTS + (size_t)3 * d.HP4 * d.HS +
-                                       (size_t)FR * 4);
-  CAST_FUSED_SMEM(qkv_bwd_kernel, smem)
-  CAST_LAUNCH(qkv_bwd_kernel, dim3(grid), dim3(FT), smem, (cudaStream_t)stream, a, d);
+  if (g_fused_backend == 1) {
+#define CAST_CALL(K) launch_qkv_bwd_mma<K>(a, d, grid, (cudaStream_t)stream)
+    CAST_KS_SWITCH(H, CAST_CALL)
+#undef CAST_CALL
+  } else {
+    const size_t smem = sizeof(float) * ((size_t)3 * FR * d.HS + (size_t)2 * d.HP4 * FTS + (size_t)3 * d.HP4 * d.HS +
+                                         (size_t)FR * 4);
+    CAST_FUSED_SMEM(qkv_bwd_kernel, smem)
+    CAST_LAUNCH(qkv_bwd_kernel, dim3(grid), dim3(FT), smem, (cudaStream_t)stream, a, d);
+  }
   int rc = check_launch("qkv_bwd");
   if (rc) return rc;
   const long count = 2L * H + 3L * ((long)H * H + H);

@@ -1,0 +1,601 @@
+// Tensor-core versions of the fused row-tile kernels of fused.cu (included from there, after its helpers): same
+// arithmetic and gradient layout, contractions as mma.sync m16n8k8 3xTF32 (mma_tf32.cuh), tiles streamed through a
+// two-stage cp.async pipeline so the next 64-row tile loads while the current one is multiplied.
+//
+//   CTA = 256 threads = 8 warps on one 64-row tile; warp w owns the 16-row block (w & 3) and the column half (w >> 2)
+//   of every 64 x H product, and the same (16 x 32) block of every H x H weight gradient.
+//   Tiles are row-major with stride S = 8*ceil(H/8) + 4 floats (16-byte rows, S/4 odd: ldmatrix conflict-free);
+//   weights sit in shared memory in their natural [in][out] layout:
+//     forward  C = A W      : B[k][n] = W[k][n]            -> per-lane LDS.32 fragments
+//     dgrad    dX = dY W^T  : B^T[n'][k] = W[n'][k]        -> ldmatrix fragments (contraction along a weight row)
+//     wgrad    dW = X^T dY  : A^T and B straight from the two row-major tiles (contraction over the 64 rows)
+#pragma once
+#include "mma_tf32.cuh"
+
+namespace cast {
+
+// asynchronous copy of the 64-row tile starting at row0 of a row-major [N, H] tensor into dst (stride S); rows >= N
+// are zero-filled, columns >= H untouched (zeroed once at kernel start).  Warp w copies rows w, w+8, ...
+template <int S>
+__device__ __forceinline__ void rm_load_tile_async(float* __restrict__ dst, const float* __restrict__ src, long row0,
+                                                   long N, int H, bool vec2) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (vec2) {
+    if (2 * lane < H) {
+      float* o = dst + warp * S + 2 * lane;
+      long row = row0 + warp;
+      const float* s = src + row * H + 2 * lane;
+#pragma unroll
+      for (int k = 0; k < FR / 8; ++k) {
+        const bool ok = row < N;
+        cp_async<8>(o, ok ? s : src, ok);
+        o += 8 * S;
+        s += 8 * (long)H;
+        row += 8;
+      }
+    }
+  } else {
+    for (int r = warp; r < FR; r += FT / 32) {
+      const long row = row0 + r;
+      const bool ok = row < N;
+      const float* s = src + (ok ? row : 0) * H;
+      for (int c = lane; c < H; c += 32) cp_async<4>(dst + r * S + c, s + c, ok);
+    }
+  }
+}
+
+__device__ __forceinline__ bool rm_vec2_ok(const void* p, int H) {
+  return (H & 1) == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0;
+}
+
+// W[H][H] row-major (global) -> Ws[k][n] stride S; the caller zeroed the buffer (64 rows) beforehand
+template <int S>
+__device__ __forceinline__ void rm_load_w(float* __restrict__ Ws, const float* __restrict__ W, int H) {
+  for (int idx = threadIdx.x; idx < H * H; idx += FT) {
+    const int k = idx / H, n = idx - k * H;
+    Ws[k * S + n] = W[idx];
+  }
+}
+
+// acc[nt] += A[16 x 8KS] * Bt^T, Bt[n][k] row-major (k contiguous), n-tiles nt < nact (warp-uniform, <= 4)
+template <int KS, int S>
+__device__ __forceinline__ void rm_mm_bt(float (&acc)[4][4], const float* __restrict__ As,
+                                         const float* __restrict__ Bt, int nact, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    unsigned af[4], ah[4], al[4];
+    ldsm_a<S>(af, As, ks * 8, lane);
+    tf32_split_n(af, ah, al);
+    unsigned bh[4][2], bl[4][2];
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      if (2 * np < nact) {
+        unsigned bf[4];
+        ldsm_b2<S>(bf, Bt + np * 16 * S, ks * 8, lane);
+        tf32_split(__uint_as_float(bf[0]), bh[2 * np][0], bl[2 * np][0]);
+        tf32_split(__uint_as_float(bf[1]), bh[2 * np][1], bl[2 * np][1]);
+        tf32_split(__uint_as_float(bf[2]), bh[2 * np + 1][0], bl[2 * np + 1][0]);
+        tf32_split(__uint_as_float(bf[3]), bh[2 * np + 1][1], bl[2 * np + 1][1]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], ah, bh[nt][0], bh[nt][1]);
+  }
+}
+
+// acc[nt] += A[16 x 8KS] * B, B[k][n] row-major (n contiguous; column block starts at Bn), n-tiles nt < nact
+template <int KS, int S>
+__device__ __forceinline__ void rm_mm_b(float (&acc)[4][4], const float* __restrict__ As, const float* __restrict__ Bn,
+                                        int nact, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    unsigned af[4], ah[4], al[4];
+    ldsm_a<S>(af, As, ks * 8, lane);
+    tf32_split_n(af, ah, al);
+    const float* b0 = Bn + (ks * 8 + tig) * S + g;
+    unsigned bh[4][2], bl[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt < nact) {
+        tf32_split(b0[nt * 8], bh[nt][0], bl[nt][0]);
+        tf32_split(b0[4 * S + nt * 8], bh[nt][1], bl[nt][1]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], ah, bh[nt][0], bh[nt][1]);
+  }
+}
+
+// weight gradients: acc_j[nt][.] += sum_{r<64} X[r][m0 + .] * G_j[r][n0 + 8nt + .] for NB gradient tiles sharing X.
+// Fragments come straight from the row-major tiles (A^T: a0 = X[r0+tig][m0+g], ...).
+template <int NB, int S>
+__device__ __forceinline__ void rm_wgrad(float (&acc)[NB][4][4], const float* __restrict__ X, int m0,
+                                         const float* const (&G)[NB], int n0, int nact, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll 2
+  for (int r0 = 0; r0 < FR; r0 += 8) {
+    const float* xa = X + (r0 + tig) * S + m0 + g;
+    unsigned ah[4], al[4];
+    tf32_split(xa[0], ah[0], al[0]);
+    tf32_split(xa[8], ah[1], al[1]);
+    tf32_split(xa[4 * S], ah[2], al[2]);
+    tf32_split(xa[4 * S + 8], ah[3], al[3]);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const float* gb = G[j] + (r0 + tig) * S + n0 + g;
+      unsigned bh[4][2], bl[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt < nact) {
+          tf32_split(gb[nt * 8], bh[nt][0], bl[nt][0]);
+          tf32_split(gb[4 * S + nt * 8], bh[nt][1], bl[nt][1]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (nt < nact) mma_tf32(acc[j][nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (nt < nact) mma_tf32(acc[j][nt], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (nt < nact) mma_tf32(acc[j][nt], ah, bh[nt][0], bh[nt][1]);
+    }
+  }
+}
+
+__device__ __forceinline__ void rm_zero(float (&acc)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
+
+// per-CTA weight-gradient partial from the warp's fragment block: P[k * H + n]
+__device__ __forceinline__ void rm_store_wpartial(float* __restrict__ P, const float (&acc)[4][4], int m0, int n0,
+                                                  int nact, int H, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    if (nt >= nact) continue;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = m0 + g + (e >> 1) * 8, n = n0 + nt * 8 + 2 * tig + (e & 1);
+      if (k < H && n < H) P[k * H + n] = acc[nt][e];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ qkv backward
+template <int KS>
+__global__ void __launch_bounds__(FT, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims d) {
+  constexpr int S = 8 * KS + 4, TILE = FR * S, STAGE = 5 * TILE;
+  CAST_DYN_SMEM(float, sm);
+  float* Wsm = sm + 2 * STAGE;      // Wq | Wk | Wv, each [64][S] natural layout, zero padded
+  float* rowstat = Wsm + 3 * TILE;  // [FR][4]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int H = d.H;
+  int nact = KS - 4 * nh;
+  nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
+  const int m0 = mt * 16, n0 = nh * 32;
+  for (int i = t; i < 2 * STAGE + 3 * TILE; i += FT) sm[i] = 0.f;
+  __syncthreads();
+  rm_load_w<S>(Wsm, a.Wq, H);
+  rm_load_w<S>(Wsm + TILE, a.Wk, H);
+  rm_load_w<S>(Wsm + 2 * TILE, a.Wv, H);
+  const bool v0 = rm_vec2_ok(a.dQ, H), v1 = rm_vec2_ok(a.dK, H), v2 = rm_vec2_ok(a.dV, H), v3 = rm_vec2_ok(a.x, H),
+             v4 = rm_vec2_ok(a.qn, H);
+  auto issue = [&](long tile, int st) {
+    float* b = sm + st * STAGE;
+    const long row0 = tile * FR;
+    rm_load_tile_async<S>(b, a.dQ, row0, d.N, H, v0);
+    rm_load_tile_async<S>(b + TILE, a.dK, row0, d.N, H, v1);
+    rm_load_tile_async<S>(b + 2 * TILE, a.dV, row0, d.N, H, v2);
+    rm_load_tile_async<S>(b + 3 * TILE, a.x, row0, d.N, H, v3);
+    rm_load_tile_async<S>(b + 4 * TILE, a.qn, row0, d.N, H, v4);
+    cp_async_commit();
+  };
+  float gWq[1][4][4], gWkv[2][4][4];
+  rm_zero(gWq[0]);
+  rm_zero(gWkv[0]);
+  rm_zero(gWkv[1]);
+  float vb = 0.f;  // group 0 -> dbq, 1 -> dbk, 2 -> dbv
+  float dgam = 0.f, dbet = 0.f;
+  if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    float* Gq = sm + st * STAGE;
+    float* Gk = Gq + TILE;
+    float* Gv = Gk + TILE;
+    float* X = Gv + TILE;
+    float* Qn = X + TILE;
+    const long row0 = tile * FR;
+    __syncthreads();  // the other stage is free (its last readers finished the previous tile)
+    if (tile + gridDim.x < a.ntiles) {
+      issue(tile + gridDim.x, st ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    // gradient of `outputs += queries` for this thread's fragment of dqn (fetched early, consumed after the products)
+    float dres[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long row = row0 + m0 + g + (e >> 1) * 8;
+        const int c = n0 + nt * 8 + 2 * tig + (e & 1);
+        dres[nt][e] = (nt < nact && c < H && row < d.N) ? a.dres[row * H + c] : 0.f;
+      }
+    {
+      const float* const gq[1] = {Gq};
+      rm_wgrad<1, S>(gWq, Qn, m0, gq, n0, nact, lane);
+      const float* const gkv[2] = {Gk, Gv};
+      rm_wgrad<2, S>(gWkv, X, m0, gkv, n0, nact, lane);
+    }
+    float accq[4][4], acck[4][4];
+    rm_zero(accq);
+    rm_zero(acck);
+    rm_mm_bt<KS, S>(accq, Gq + m0 * S, Wsm + n0 * S, nact, lane);             // dqn (without the residual)
+    rm_mm_bt<KS, S>(acck, Gk + m0 * S, Wsm + TILE + n0 * S, nact, lane);      // dx through K ...
+    rm_mm_bt<KS, S>(acck, Gv + m0 * S, Wsm + 2 * TILE + n0 * S, nact, lane);  // ... and V
+    f_colsum(Gq, 0, d, vb);
+    f_colsum(Gk, 1, d, vb);
+    f_colsum(Gv, 2, d, vb);
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt >= nact) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+        const bool ok = c < H && row0 + r < d.N;
+        Gq[r * S + c] = ok ? accq[nt][e] + dres[nt][e] : 0.f;
+        Gk[r * S + c] = ok ? acck[nt][e] : 0.f;
+      }
+    }
+    __syncthreads();
+    f_ln_bwd_rows(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet);
+  }
+  float* P = a.partial + (long)blockIdx.x * (2L * H + 3L * (H * H + H));
+  if (t < 64 && t < H) P[H + t] = dgam;
+  if (t >= 64 && t < 128 && (t & 63) < H) P[t & 63] = dbet;
+  rm_store_wpartial(P + 2 * H, gWq[0], m0, n0, nact, H, lane);
+  rm_store_wpartial(P + 2 * H + (H * H + H), gWkv[0], m0, n0, nact, H, lane);
+  rm_store_wpartial(P + 2 * H + 2 * (H * H + H), gWkv[1], m0, n0, nact, H, lane);
+  const int grp = t >> 6;
+  if (grp < 3 && (t & 63) < H) P[2 * H + grp * (H * H + H) + H * H + (t & 63)] = vb;
+}
+
+// ------------------------------------------------------------------------------------------------ ffn backward
+template <int KS>
+__global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims d) {
+  constexpr int S = 8 * KS + 4, TILE = FR * S, STAGE = 4 * TILE;
+  CAST_DYN_SMEM(float, sm);
+  float* Gd = sm + 2 * STAGE;  // dx * mask * dropout, later dzn
+  float* Dh = Gd + TILE;       // gradient at the FFN hidden pre-activation
+  float* W1s = Dh + TILE;      // [64][S] natural
+  float* W2s = W1s + TILE;
+  float* rowstat = W2s + TILE;  // [FR][4]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int H = d.H;
+  int nact = KS - 4 * nh;
+  nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
+  const int m0 = mt * 16, n0 = nh * 32;
+  const float scale = a.rate > 0.f ? 1.0f / (1.0f - a.rate) : 1.0f;
+  const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
+  for (int i = t; i < 2 * STAGE + 4 * TILE; i += FT) sm[i] = 0.f;
+  __syncthreads();
+  rm_load_w<S>(W1s, a.W1, H);
+  rm_load_w<S>(W2s, a.W2, H);
+  const bool v0 = rm_vec2_ok(a.dx, H), v1 = rm_vec2_ok(a.zn, H), v2 = rm_vec2_ok(a.h1d, H), v3 = rm_vec2_ok(a.y, H);
+  auto issue = [&](long tile, int st) {
+    float* b = sm + st * STAGE;
+    const long row0 = tile * FR;
+    rm_load_tile_async<S>(b, a.dx, row0, d.N, H, v0);
+    rm_load_tile_async<S>(b + TILE, a.zn, row0, d.N, H, v1);
+    rm_load_tile_async<S>(b + 2 * TILE, a.h1d, row0, d.N, H, v2);
+    rm_load_tile_async<S>(b + 3 * TILE, a.y, row0, d.N, H, v3);
+    cp_async_commit();
+  };
+  float gW1[1][4][4], gW2[1][4][4];
+  rm_zero(gW1[0]);
+  rm_zero(gW2[0]);
+  float vb = 0.f;  // thread-owned vector gradient: group 0 -> db2, 1 -> db1 (tid/64), column tid%64
+  float dgam = 0.f, dbet = 0.f;
+  if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    float* Gm = sm + st * STAGE;  // dx, masked in place
+    float* Zn = Gm + TILE;
+    float* Hd = Zn + TILE;
+    float* Yr = Hd + TILE;
+    const long row0 = tile * FR;
+    __syncthreads();
+    if (tile + gridDim.x < a.ntiles) {
+      issue(tile + gridDim.x, st ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    // masked / dropped upstream gradient
+    for (int r = warp; r < FR; r += FT / 32) {
+      const long row = row0 + r;
+      const bool ok = row < d.N;
+      const float m = (ok && (!a.ids || a.ids[row] != 0)) ? 1.f : 0.f;
+      for (int c = lane; c < H; c += 32) {
+        const float gg = Gm[r * S + c] * m;
+        Gm[r * S + c] = gg;
+        Gd[r * S + c] = ok ? gg * drop_mul(dout, (unsigned long long)(row * H + c)) : 0.f;
+      }
+    }
+    __syncthreads();
+    // dW2 += h1d^T Gd ; db2 += colsum(Gd) ; dh = (Gd W2^T) * relu/dropout mask
+    {
+      const float* const gb[1] = {Gd};
+      rm_wgrad<1, S>(gW2, Hd, m0, gb, n0, nact, lane);
+      float acc[4][4];
+      rm_zero(acc);
+      rm_mm_bt<KS, S>(acc, Gd + m0 * S, W2s + n0 * S, nact, lane);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt >= nact) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+          Dh[r * S + c] = (c < H && Hd[r * S + c] > 0.f) ? acc[nt][e] * scale : 0.f;
+        }
+      }
+    }
+    f_colsum(Gd, 0, d, vb);
+    __syncthreads();
+    // dW1 += zn^T Dh ; db1 += colsum(Dh) ; dzn = Dh W1^T + Gm  (stored over Gd)
+    {
+      const float* const gb[1] = {Dh};
+      rm_wgrad<1, S>(gW1, Zn, m0, gb, n0, nact, lane);
+      float acc[4][4];
+      rm_zero(acc);
+      rm_mm_bt<KS, S>(acc, Dh + m0 * S, W1s + n0 * S, nact, lane);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt >= nact) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+          Gd[r * S + c] = c < H ? acc[nt][e] + Gm[r * S + c] : 0.f;
+        }
+      }
+    }
+    f_colsum(Dh, 1, d, vb);
+    __syncthreads();
+    f_ln_bwd_rows(Gd, Yr, S, 1, nullptr, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dy, dgam, dbet);
+  }
+  float* P = a.partial + (long)blockIdx.x * (2L * H + 2L * (H * H + H));
+  if (t < 64 && t < H) P[H + t] = dgam;
+  if (t >= 64 && t < 128 && (t & 63) < H) P[t & 63] = dbet;
+  rm_store_wpartial(P + 2 * H, gW1[0], m0, n0, nact, H, lane);
+  rm_store_wpartial(P + 2 * H + H * H + H, gW2[0], m0, n0, nact, H, lane);
+  if ((t >> 6) == 1 && (t & 63) < H) P[2 * H + H * H + (t & 63)] = vb;              // db1
+  if ((t >> 6) == 0 && (t & 63) < H) P[2 * H + H * H + H + H * H + (t & 63)] = vb;  // db2
+}
+
+// ------------------------------------------------------------------------------------------------ forward kernels
+// stride of the forward weights: W[k][n] is read as B fragments b0 = W[k0+tig][n0+g], conflict-free when SW % 32 == 8
+__host__ __device__ constexpr int rm_wstride(int hp8) { return hp8 <= 8 ? 8 : (hp8 <= 40 ? 40 : 72); }
+
+template <int SW>
+__device__ __forceinline__ void rm_load_w_fwd(float* __restrict__ Ws, const float* __restrict__ W, int H) {
+  for (int idx = threadIdx.x; idx < H * H; idx += FT) {
+    const int k = idx / H, n = idx - k * H;
+    Ws[k * SW + n] = W[idx];
+  }
+}
+
+// like rm_mm_b with its own weight stride
+template <int KS, int S, int SW>
+__device__ __forceinline__ void rm_mm_w(float (&acc)[4][4], const float* __restrict__ As, const float* __restrict__ Wn,
+                                        int nact, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    unsigned af[4], ah[4], al[4];
+    ldsm_a<S>(af, As, ks * 8, lane);
+    tf32_split_n(af, ah, al);
+    const float* b0 = Wn + (ks * 8 + tig) * SW + g;
+    unsigned bh[4][2], bl[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt < nact) {
+        tf32_split(b0[nt * 8], bh[nt][0], bl[nt][0]);
+        tf32_split(b0[4 * SW + nt * 8], bh[nt][1], bl[nt][1]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (nt < nact) mma_tf32(acc[nt], ah, bh[nt][0], bh[nt][1]);
+  }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(FT, 1) ln_qkv_fwd_mma_kernel(LnQkvArgs a, FDims d, long ntiles) {
+  constexpr int HP8 = 8 * KS, S = HP8 + 4, TILE = FR * S, SW = rm_wstride(HP8), WT = HP8 * SW;
+  CAST_DYN_SMEM(float, sm);
+  float* Ns = sm + 2 * TILE;  // LN(x) tile
+  float* Wsm = Ns + TILE;     // Wq | Wk | Wv, [HP8][SW] natural layout, zero padded
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int H = d.H;
+  int nact = KS - 4 * nh;
+  nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
+  const int m0 = mt * 16, n0 = nh * 32;
+  for (int i = t; i < 3 * TILE + 3 * WT; i += FT) sm[i] = 0.f;
+  __syncthreads();
+  for (int m = 0; m < 3; ++m) rm_load_w_fwd<SW>(Wsm + m * WT, a.W[m], H);
+  const bool vx = rm_vec2_ok(a.x, H);
+  if ((long)blockIdx.x < ntiles) {
+    rm_load_tile_async<S>(sm, a.x, (long)blockIdx.x * FR, d.N, H, vx);
+    cp_async_commit();
+  }
+  int it = 0;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    float* Xs = sm + st * TILE;
+    const long row0 = tile * FR;
+    __syncthreads();
+    if (tile + gridDim.x < ntiles) {
+      rm_load_tile_async<S>(sm + (st ^ 1) * TILE, a.x, (tile + gridDim.x) * FR, d.N, H, vx);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    f_layernorm_rows(Xs, Ns, a.gamma, a.beta, a.eps, row0, d, a.qn, a.mean, a.rstd, a.kmask, a.qmask);
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      float acc[4][4];
+      rm_zero(acc);
+      rm_mm_w<KS, S, SW>(acc, (m == 0 ? Ns : Xs) + m0 * S, Wsm + m * WT + n0, nact, lane);
+      const float* bias = a.b[m];
+      float* out = a.out[m];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt >= nact) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long row = row0 + m0 + g + (e >> 1) * 8;
+          const int c = n0 + nt * 8 + 2 * tig + (e & 1);
+          if (c < H && row < d.N) out[row * H + c] = acc[nt][e] + bias[c];
+        }
+      }
+    }
+  }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(FT, 1) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDims d, long ntiles) {
+  constexpr int HP8 = 8 * KS, S = HP8 + 4, TILE = FR * S, SW = rm_wstride(HP8), WT = HP8 * SW;
+  CAST_DYN_SMEM(float, sm);
+  float* Ns = sm + 2 * TILE;  // LN(y) tile
+  float* Hs = Ns + TILE;      // hidden activation (after relu + dropout)
+  float* Wsm = Hs + TILE;     // W1 | W2
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int H = d.H;
+  int nact = KS - 4 * nh;
+  nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
+  const int m0 = mt * 16, n0 = nh * 32;
+  for (int i = t; i < 4 * TILE + 2 * WT; i += FT) sm[i] = 0.f;
+  __syncthreads();
+  rm_load_w_fwd<SW>(Wsm, a.W1, H);
+  rm_load_w_fwd<SW>(Wsm + WT, a.W2, H);
+  const Drop dh = make_drop(a.rate, a.seed, a.step, a.site_h);
+  const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
+  const bool vy = rm_vec2_ok(a.y, H);
+  if ((long)blockIdx.x < ntiles) {
+    rm_load_tile_async<S>(sm, a.y, (long)blockIdx.x * FR, d.N, H, vy);
+    cp_async_commit();
+  }
+  int it = 0;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    float* Ys = sm + st * TILE;
+    const long row0 = tile * FR;
+    __syncthreads();
+    if (tile + gridDim.x < ntiles) {
+      rm_load_tile_async<S>(sm + (st ^ 1) * TILE, a.y, (tile + gridDim.x) * FR, d.N, H, vy);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    f_layernorm_rows(Ys, Ns, a.gamma, a.beta, a.eps, row0, d, a.zn, a.mean, a.rstd, nullptr, nullptr);
+    __syncthreads();
+    {
+      float acc[4][4];
+      rm_zero(acc);
+      rm_mm_w<KS, S, SW>(acc, Ns + m0 * S, Wsm + n0, nact, lane);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt >= nact) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+          const long row = row0 + r;
+          float h = 0.f;
+          if (c < H && row < d.N) {
+            h = fmaxf(acc[nt][e] + a.b1[c], 0.f) * drop_mul(dh, (unsigned long long)(row * H + c));
+            a.h1d[row * H + c] = h;
+          }
+          Hs[r * S + c] = h;
+        }
+      }
+    }
+    __syncthreads();
+    {
+      float acc[4][4];
+      rm_zero(acc);
+      rm_mm_w<KS, S, SW>(acc, Hs + m0 * S, Wsm + WT + n0, nact, lane);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt >= nact) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+          const long row = row0 + r;
+          if (c < H && row < d.N) {
+            const float m = a.ids ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;
+            float o = (acc[nt][e] + a.b2[c]) * drop_mul(dout, (unsigned long long)(row * H + c));
+            o += Ns[r * S + c];
+            a.xout[row * H + c] = o * m;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int KS>
+static size_t ln_qkv_fwd_mma_smem() {
+  return sizeof(float) * ((size_t)3 * FR * (8 * KS + 4) + (size_t)3 * 8 * KS * rm_wstride(8 * KS));
+}
+template <int KS>
+static size_t ln_ffn_fwd_mma_smem() {
+  return sizeof(float) * ((size_t)4 * FR * (8 * KS + 4) + (size_t)2 * 8 * KS * rm_wstride(8 * KS));
+}
+
+template <int KS>
+static size_t qkv_bwd_mma_smem() { return sizeof(float) * ((size_t)(10 + 3) * FR * (8 * KS + 4) + FR * 4); }
+template <int KS>
+static size_t ffn_bwd_mma_smem() { return sizeof(float) * ((size_t)(8 + 4) * FR * (8 * KS + 4) + FR * 4); }
+
+}  // namespace cast

@@ -121,6 +121,8 @@ int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* beta, const
                     const float* W2, const float* b2, const int* ids, float drop_rate, unsigned long long seed,
                     const unsigned long long* step, int site_hidden, int site_out, long N, int H, float eps, float* zn,
                     float* h1d, float* xout, float* mean, float* rstd, void* stream);
+/* 1 (default): backward row kernels on the tensor cores (mma.sync 3xTF32); 0: FP32 FFMA kernels (A/B testing). */
+int cast_fused_set_backend(int backend);
 size_t cast_block_bwd_workspace_bytes(long N, int H);
 int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, const float* h1d, const float* y, const float* mean,
                  const float* rstd, const float* gamma, const float* W1, const float* W2, float drop_rate,

@@ -58,7 +58,7 @@ def check_step(eng, p, grads_o, ref, s, tol=TOL):
 
 
 EMU_CASES = [("sasrec", 3, 12, 20, 2, 0.25), ("sasrec_static", 7, 11, 12, 1, 0.2), ("cast_1", 2, 10, 12, 1, 0.3), ("cast_4", 2, 10, 12, 2, 0.2),
-             ("cast_6", 2, 8, 12, 1, 0.2), ("cast_9", 2, 8, 8, 2, 0.1)]
+             ("cast_6", 2, 8, 12, 1, 0.2), ("cast_9", 2, 8, 8, 2, 0.1), ("sasrec", 2, 9, 40, 2, 0.2)]
 
 
 @pytest.mark.emu
