@@ -553,10 +553,10 @@ using namespace cast;
 
 extern "C" int cast_fused_supported(int H) { return H > 0 && H <= 64; }
 
-// 1 (default): backward row kernels on the tensor cores (fused_mma.cuh); 0: the FP32 FFMA kernels above
-static int g_fused_backend = 1;
+// bit 0: backward row kernels on the tensor cores (fused_mma.cuh), bit 1: forward row kernels; 0: FP32 FFMA kernels
+static int g_fused_backend = 3;
 extern "C" int cast_fused_set_backend(int backend) {
-  if (backend != 0 && backend != 1) return set_error(CAST_ERR_BAD_ARG, "fused_set_backend");
+  if (backend < 0 || backend > 3) return set_error(CAST_ERR_BAD_ARG, "fused_set_backend");
   g_fused_backend = backend;
   return CAST_OK;
 }
@@ -584,7 +584,7 @@ static void launch_ln_qkv_fwd_mma(const LnQkvArgs& a, FDims d, cudaStream_t stre
   const size_t smem = ln_qkv_fwd_mma_smem<KS>();
   auto kf = ln_qkv_fwd_mma_kernel<KS>;
   CAST_FUSED_SMEM(kf, smem)
-  CAST_LAUNCH(kf, dim3(bwd_grid(ntiles, 1)), dim3(FT), smem, stream, a, d, ntiles);
+  CAST_LAUNCH(kf, dim3((unsigned)ntiles), dim3(FT), smem, stream, a, d);
 }
 template <int KS>
 static void launch_ln_ffn_fwd_mma(const LnFfnArgs& a, FDims d, cudaStream_t stream) {
@@ -593,7 +593,7 @@ static void launch_ln_ffn_fwd_mma(const LnFfnArgs& a, FDims d, cudaStream_t stre
   const size_t smem = ln_ffn_fwd_mma_smem<KS>();
   auto kf = ln_ffn_fwd_mma_kernel<KS>;
   CAST_FUSED_SMEM(kf, smem)
-  CAST_LAUNCH(kf, dim3(bwd_grid(ntiles, 1)), dim3(FT), smem, stream, a, d, ntiles);
+  CAST_LAUNCH(kf, dim3((unsigned)ntiles), dim3(FT), smem, stream, a, d);
 }
 #define CAST_KS_SWITCH(H, CALL)                                                          \
   switch (((H) + 7) / 8) {                                                               \
@@ -610,7 +610,7 @@ extern "C" int cast_ln_qkv_fwd(const float* x, const float* gamma, const float* 
   if (!cast_fused_supported(H)) return set_error(CAST_ERR_UNSUPPORTED, "ln_qkv_fwd: H > 64");
   const FDims d = fdims(N, H);
   LnQkvArgs a{x, gamma, beta, {Wq, Wk, Wv}, {bq, bk, bv}, eps, qn, {Q, K, V}, mean, rstd, kmask, qmask};
-  if (g_fused_backend == 1) {
+  if (g_fused_backend & 2) {
 #define CAST_CALL(K) launch_ln_qkv_fwd_mma<K>(a, d, (cudaStream_t)stream)
     CAST_KS_SWITCH(H, CAST_CALL)
 #undef CAST_CALL
@@ -634,7 +634,7 @@ extern "C" int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* 
   const FDims d = fdims(N, H);
   LnFfnArgs a{y, gamma, beta, W1, b1, W2, b2, ids, eps, drop_rate, seed, step, site_hidden, site_out,
               zn, h1d, xout, mean, rstd};
-  if (g_fused_backend == 1) {
+  if (g_fused_backend & 2) {
 #define CAST_CALL(K) launch_ln_ffn_fwd_mma<K>(a, d, (cudaStream_t)stream)
     CAST_KS_SWITCH(H, CAST_CALL)
 #undef CAST_CALL
@@ -663,10 +663,10 @@ extern "C" int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, co
     return set_error(CAST_ERR_WORKSPACE, "ffn_bwd: workspace too small");
   const FDims d = fdims(N, H);
   const long ntiles = cdiv(N, FR);
-  const int grid = bwd_grid(ntiles, g_fused_backend == 1 ? 1 : 2);
+  const int grid = bwd_grid(ntiles, (g_fused_backend & 1) ? 1 : 2);
   FfnBwdArgs a{dx, zn, h1d, y, mean, rstd, gamma, W1, W2, ids, drop_rate, seed, step, site_out, dy,
                static_cast<float*>(workspace), ntiles};
-  if (g_fused_backend == 1) {
+  if (g_fused_backend & 1) {
 #define CAST_CALL(K) launch_ffn_bwd_mma<K>(a, d, grid, (cudaStream_t)stream)
     CAST_KS_SWITCH(H, CAST_CALL)
 #undef CAST_CALL
@@ -697,7 +697,7 @@ extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, c
   const long ntiles = cdiv(N, FR);
   const int grid = bwd_grid(ntiles, 1);
   QkvBwdArgs a{dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv, dx, static_cast<float*>(workspace), ntiles};
-  if (g_fused_backend == 1) {
+  if (g_fused_backend & 1) {
 #define CAST_CALL(K) launch_qkv_bwd_mma<K>(a, d, grid, (cudaStream_t)stream)
     CAST_KS_SWITCH(H, CAST_CALL)
 #undef CAST_CALL

@@ -401,34 +401,40 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
 }
 
 // ------------------------------------------------------------------------------------------------ forward kernels
-// stride of the forward weights: W[k][n] is read as B fragments b0 = W[k0+tig][n0+g], conflict-free when SW % 32 == 8
-__host__ __device__ constexpr int rm_wstride(int hp8) { return hp8 <= 8 ? 8 : (hp8 <= 40 ? 40 : 72); }
+// One 64-row tile per CTA, ~70 KB of shared memory => 3 CTAs per SM overlap each other's load / LayerNorm / product /
+// store phases.  Weights are staged transposed, Wt[n][k] (stride S), so that B fragments come from ldmatrix.
 
-template <int SW>
-__device__ __forceinline__ void rm_load_w_fwd(float* __restrict__ Ws, const float* __restrict__ W, int H) {
+// Wt[n][k] = W[k][n] for k, n < H; the caller zeroed the [8KS][S] buffer
+template <int S>
+__device__ __forceinline__ void rm_load_w_t(float* __restrict__ Wt, const float* __restrict__ W, int H) {
   for (int idx = threadIdx.x; idx < H * H; idx += FT) {
     const int k = idx / H, n = idx - k * H;
-    Ws[k * SW + n] = W[idx];
+    Wt[n * S + k] = W[idx];
   }
 }
 
-// like rm_mm_b with its own weight stride
-template <int KS, int S, int SW>
-__device__ __forceinline__ void rm_mm_w(float (&acc)[4][4], const float* __restrict__ As, const float* __restrict__ Wn,
-                                        int nact, int lane) {
-  const int g = lane >> 2, tig = lane & 3;
+// rm_mm_bt for a Bt buffer that ends after the last real n-tile: when nact is odd the ldmatrix rows of the missing
+// n-tile are redirected to the previous one (loaded twice, used once)
+template <int KS, int S>
+__device__ __forceinline__ void rm_mm_bt_tight(float (&acc)[4][4], const float* __restrict__ As,
+                                               const float* __restrict__ Bt, int nact, int lane) {
+  const int blk = lane >> 3, rr = lane & 7;
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
     unsigned af[4], ah[4], al[4];
     ldsm_a<S>(af, As, ks * 8, lane);
     tf32_split_n(af, ah, al);
-    const float* b0 = Wn + (ks * 8 + tig) * SW + g;
     unsigned bh[4][2], bl[4][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      if (nt < nact) {
-        tf32_split(b0[nt * 8], bh[nt][0], bl[nt][0]);
-        tf32_split(b0[4 * SW + nt * 8], bh[nt][1], bl[nt][1]);
+    for (int np = 0; np < 2; ++np) {
+      if (2 * np < nact) {
+        unsigned bf[4];
+        const int second = (2 * np + 1 < nact) ? (blk >> 1) : 0;
+        ldsm4(bf, Bt + (np * 16 + second * 8 + rr) * S + ks * 8 + (blk & 1) * 4);
+        tf32_split(__uint_as_float(bf[0]), bh[2 * np][0], bl[2 * np][0]);
+        tf32_split(__uint_as_float(bf[1]), bh[2 * np][1], bl[2 * np][1]);
+        tf32_split(__uint_as_float(bf[2]), bh[2 * np + 1][0], bl[2 * np + 1][0]);
+        tf32_split(__uint_as_float(bf[3]), bh[2 * np + 1][1], bl[2 * np + 1][1]);
       }
     }
 #pragma unroll
@@ -444,141 +450,107 @@ __device__ __forceinline__ void rm_mm_w(float (&acc)[4][4], const float* __restr
 }
 
 template <int KS>
-__global__ void __launch_bounds__(FT, 1) ln_qkv_fwd_mma_kernel(LnQkvArgs a, FDims d, long ntiles) {
-  constexpr int HP8 = 8 * KS, S = HP8 + 4, TILE = FR * S, SW = rm_wstride(HP8), WT = HP8 * SW;
+__global__ void __launch_bounds__(FT, 3) ln_qkv_fwd_mma_kernel(LnQkvArgs a, FDims d) {
+  constexpr int HP8 = 8 * KS, S = HP8 + 4, TILE = FR * S, WT = HP8 * S;
   CAST_DYN_SMEM(float, sm);
-  float* Ns = sm + 2 * TILE;  // LN(x) tile
-  float* Wsm = Ns + TILE;     // Wq | Wk | Wv, [HP8][SW] natural layout, zero padded
+  float* Xs = sm;
+  float* Ns = Xs + TILE;   // LN(x) tile
+  float* Wsm = Ns + TILE;  // Wq^T | Wk^T | Wv^T, [HP8][S]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
   const int mt = warp & 3, nh = warp >> 2;
   const int H = d.H;
   int nact = KS - 4 * nh;
   nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
   const int m0 = mt * 16, n0 = nh * 32;
-  for (int i = t; i < 3 * TILE + 3 * WT; i += FT) sm[i] = 0.f;
+  const long row0 = (long)blockIdx.x * FR;
+  for (int i = t; i < 2 * TILE + 3 * WT; i += FT) sm[i] = 0.f;
   __syncthreads();
-  for (int m = 0; m < 3; ++m) rm_load_w_fwd<SW>(Wsm + m * WT, a.W[m], H);
-  const bool vx = rm_vec2_ok(a.x, H);
-  if ((long)blockIdx.x < ntiles) {
-    rm_load_tile_async<S>(sm, a.x, (long)blockIdx.x * FR, d.N, H, vx);
-    cp_async_commit();
-  }
-  int it = 0;
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int st = it & 1;
-    float* Xs = sm + st * TILE;
-    const long row0 = tile * FR;
-    __syncthreads();
-    if (tile + gridDim.x < ntiles) {
-      rm_load_tile_async<S>(sm + (st ^ 1) * TILE, a.x, (tile + gridDim.x) * FR, d.N, H, vx);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    f_layernorm_rows(Xs, Ns, a.gamma, a.beta, a.eps, row0, d, a.qn, a.mean, a.rstd, a.kmask, a.qmask);
-    __syncthreads();
+  rm_load_tile_async<S>(Xs, a.x, row0, d.N, H, rm_vec2_ok(a.x, H));
+  cp_async_commit();
+  for (int m = 0; m < 3; ++m) rm_load_w_t<S>(Wsm + m * WT, a.W[m], H);
+  cp_async_wait<0>();
+  __syncthreads();
+  f_layernorm_rows(Xs, Ns, a.gamma, a.beta, a.eps, row0, d, a.qn, a.mean, a.rstd, a.kmask, a.qmask);
+  __syncthreads();
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      float acc[4][4];
-      rm_zero(acc);
-      rm_mm_w<KS, S, SW>(acc, (m == 0 ? Ns : Xs) + m0 * S, Wsm + m * WT + n0, nact, lane);
-      const float* bias = a.b[m];
-      float* out = a.out[m];
+  for (int m = 0; m < 3; ++m) {
+    float acc[4][4];
+    rm_zero(acc);
+    rm_mm_bt_tight<KS, S>(acc, (m == 0 ? Ns : Xs) + m0 * S, Wsm + m * WT + n0 * S, nact, lane);
+    const float* bias = a.b[m];
+    float* out = a.out[m];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (nt >= nact) continue;
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt >= nact) continue;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const long row = row0 + m0 + g + (e >> 1) * 8;
-          const int c = n0 + nt * 8 + 2 * tig + (e & 1);
-          if (c < H && row < d.N) out[row * H + c] = acc[nt][e] + bias[c];
-        }
+      for (int e = 0; e < 4; ++e) {
+        const long row = row0 + m0 + g + (e >> 1) * 8;
+        const int c = n0 + nt * 8 + 2 * tig + (e & 1);
+        if (c < H && row < d.N) out[row * H + c] = acc[nt][e] + bias[c];
       }
     }
   }
 }
 
 template <int KS>
-__global__ void __launch_bounds__(FT, 1) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDims d, long ntiles) {
-  constexpr int HP8 = 8 * KS, S = HP8 + 4, TILE = FR * S, SW = rm_wstride(HP8), WT = HP8 * SW;
+__global__ void __launch_bounds__(FT, 3) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDims d) {
+  constexpr int HP8 = 8 * KS, S = HP8 + 4, TILE = FR * S, WT = HP8 * S;
   CAST_DYN_SMEM(float, sm);
-  float* Ns = sm + 2 * TILE;  // LN(y) tile
-  float* Hs = Ns + TILE;      // hidden activation (after relu + dropout)
-  float* Wsm = Hs + TILE;     // W1 | W2
+  float* Ys = sm;          // y tile, later the hidden activation
+  float* Ns = Ys + TILE;   // LN(y) tile
+  float* Wsm = Ns + TILE;  // W1^T | W2^T
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
   const int mt = warp & 3, nh = warp >> 2;
   const int H = d.H;
   int nact = KS - 4 * nh;
   nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
   const int m0 = mt * 16, n0 = nh * 32;
-  for (int i = t; i < 4 * TILE + 2 * WT; i += FT) sm[i] = 0.f;
+  const long row0 = (long)blockIdx.x * FR;
+  for (int i = t; i < 2 * TILE + 2 * WT; i += FT) sm[i] = 0.f;
   __syncthreads();
-  rm_load_w_fwd<SW>(Wsm, a.W1, H);
-  rm_load_w_fwd<SW>(Wsm + WT, a.W2, H);
+  rm_load_tile_async<S>(Ys, a.y, row0, d.N, H, rm_vec2_ok(a.y, H));
+  cp_async_commit();
+  rm_load_w_t<S>(Wsm, a.W1, H);
+  rm_load_w_t<S>(Wsm + WT, a.W2, H);
   const Drop dh = make_drop(a.rate, a.seed, a.step, a.site_h);
   const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
-  const bool vy = rm_vec2_ok(a.y, H);
-  if ((long)blockIdx.x < ntiles) {
-    rm_load_tile_async<S>(sm, a.y, (long)blockIdx.x * FR, d.N, H, vy);
-    cp_async_commit();
-  }
-  int it = 0;
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int st = it & 1;
-    float* Ys = sm + st * TILE;
-    const long row0 = tile * FR;
-    __syncthreads();
-    if (tile + gridDim.x < ntiles) {
-      rm_load_tile_async<S>(sm + (st ^ 1) * TILE, a.y, (tile + gridDim.x) * FR, d.N, H, vy);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    f_layernorm_rows(Ys, Ns, a.gamma, a.beta, a.eps, row0, d, a.zn, a.mean, a.rstd, nullptr, nullptr);
-    __syncthreads();
-    {
-      float acc[4][4];
-      rm_zero(acc);
-      rm_mm_w<KS, S, SW>(acc, Ns + m0 * S, Wsm + n0, nact, lane);
+  cp_async_wait<0>();
+  __syncthreads();
+  f_layernorm_rows(Ys, Ns, a.gamma, a.beta, a.eps, row0, d, a.zn, a.mean, a.rstd, nullptr, nullptr);
+  __syncthreads();  // everybody is done with Ys (LN input): it becomes the hidden tile
+  float acc[4][4];
+  rm_zero(acc);
+  rm_mm_bt_tight<KS, S>(acc, Ns + m0 * S, Wsm + n0 * S, nact, lane);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (nt >= nact) continue;
+  for (int nt = 0; nt < 4; ++nt) {
+    if (nt >= nact) continue;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
-          const long row = row0 + r;
-          float h = 0.f;
-          if (c < H && row < d.N) {
-            h = fmaxf(acc[nt][e] + a.b1[c], 0.f) * drop_mul(dh, (unsigned long long)(row * H + c));
-            a.h1d[row * H + c] = h;
-          }
-          Hs[r * S + c] = h;
-        }
+    for (int e = 0; e < 4; ++e) {
+      const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+      const long row = row0 + r;
+      float h = 0.f;
+      if (c < H && row < d.N) {
+        h = fmaxf(acc[nt][e] + a.b1[c], 0.f) * drop_mul(dh, (unsigned long long)(row * H + c));
+        a.h1d[row * H + c] = h;
       }
+      Ys[r * S + c] = h;
     }
-    __syncthreads();
-    {
-      float acc[4][4];
-      rm_zero(acc);
-      rm_mm_w<KS, S, SW>(acc, Hs + m0 * S, Wsm + WT + n0, nact, lane);
+  }
+  __syncthreads();
+  rm_zero(acc);
+  rm_mm_bt_tight<KS, S>(acc, Ys + m0 * S, Wsm + WT + n0 * S, nact, lane);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (nt >= nact) continue;
+  for (int nt = 0; nt < 4; ++nt) {
+    if (nt >= nact) continue;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
-          const long row = row0 + r;
-          if (c < H && row < d.N) {
-            const float m = a.ids ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;
-            float o = (acc[nt][e] + a.b2[c]) * drop_mul(dout, (unsigned long long)(row * H + c));
-            o += Ns[r * S + c];
-            a.xout[row * H + c] = o * m;
-          }
-        }
+    for (int e = 0; e < 4; ++e) {
+      const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+      const long row = row0 + r;
+      if (c < H && row < d.N) {
+        const float m = a.ids ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;
+        float o = (acc[nt][e] + a.b2[c]) * drop_mul(dout, (unsigned long long)(row * H + c));
+        o += Ns[r * S + c];
+        a.xout[row * H + c] = o * m;
       }
     }
   }
@@ -586,11 +558,11 @@ __global__ void __launch_bounds__(FT, 1) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDim
 
 template <int KS>
 static size_t ln_qkv_fwd_mma_smem() {
-  return sizeof(float) * ((size_t)3 * FR * (8 * KS + 4) + (size_t)3 * 8 * KS * rm_wstride(8 * KS));
+  return sizeof(float) * ((size_t)2 * FR * (8 * KS + 4) + (size_t)3 * 8 * KS * (8 * KS + 4));
 }
 template <int KS>
 static size_t ln_ffn_fwd_mma_smem() {
-  return sizeof(float) * ((size_t)4 * FR * (8 * KS + 4) + (size_t)2 * 8 * KS * rm_wstride(8 * KS));
+  return sizeof(float) * ((size_t)2 * FR * (8 * KS + 4) + (size_t)2 * 8 * KS * (8 * KS + 4));
 }
 
 template <int KS>

@@ -121,7 +121,8 @@ int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* beta, const
                     const float* W2, const float* b2, const int* ids, float drop_rate, unsigned long long seed,
                     const unsigned long long* step, int site_hidden, int site_out, long N, int H, float eps, float* zn,
                     float* h1d, float* xout, float* mean, float* rstd, void* stream);
-/* 1 (default): backward row kernels on the tensor cores (mma.sync 3xTF32); 0: FP32 FFMA kernels (A/B testing). */
+/* Row-kernel backend (A/B testing): bit 0 = backward kernels on the tensor cores (mma.sync 3xTF32), bit 1 = forward
+ * kernels; default 3; 0 = FP32 FFMA kernels. */
 int cast_fused_set_backend(int backend);
 size_t cast_block_bwd_workspace_bytes(long N, int H);
 int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, const float* h1d, const float* y, const float* mean,
