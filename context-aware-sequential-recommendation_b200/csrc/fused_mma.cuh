@@ -404,13 +404,21 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
 // One 64-row tile per CTA, ~70 KB of shared memory => 3 CTAs per SM overlap each other's load / LayerNorm / product /
 // store phases.  Weights are staged transposed, Wt[n][k] (stride S), so that B fragments come from ldmatrix.
 
-// Wt[n][k] = W[k][n] for k, n < H; the caller zeroed the [8KS][S] buffer
-template <int S>
+// Wt[n][k] = W[k][n] for k, n < H, zeros for the padding up to [HP8][HP8]; warp per weight row, lanes along n
+template <int HP8, int S>
 __device__ __forceinline__ void rm_load_w_t(float* __restrict__ Wt, const float* __restrict__ W, int H) {
-  for (int idx = threadIdx.x; idx < H * H; idx += FT) {
-    const int k = idx / H, n = idx - k * H;
-    Wt[n * S + k] = W[idx];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < HP8; k += FT / 32) {
+    const float* w = W + k * H;
+    for (int n = lane; n < HP8; n += 32) Wt[n * S + k] = (k < H && n < H) ? w[n] : 0.f;
   }
+}
+
+// zero the padding columns H..HP8-1 of `rows` tile rows
+template <int HP8, int S>
+__device__ __forceinline__ void rm_zero_pad(float* __restrict__ buf, int rows, int H) {
+  for (int r = threadIdx.x; r < rows; r += FT)
+    for (int c = H; c < HP8; ++c) buf[r * S + c] = 0.f;
 }
 
 // rm_mm_bt for a Bt buffer that ends after the last real n-tile: when nact is odd the ldmatrix rows of the missing
@@ -463,11 +471,10 @@ __global__ void __launch_bounds__(FT, 3) ln_qkv_fwd_mma_kernel(LnQkvArgs a, FDim
   nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
   const int m0 = mt * 16, n0 = nh * 32;
   const long row0 = (long)blockIdx.x * FR;
-  for (int i = t; i < 2 * TILE + 3 * WT; i += FT) sm[i] = 0.f;
-  __syncthreads();
   rm_load_tile_async<S>(Xs, a.x, row0, d.N, H, rm_vec2_ok(a.x, H));
   cp_async_commit();
-  for (int m = 0; m < 3; ++m) rm_load_w_t<S>(Wsm + m * WT, a.W[m], H);
+  rm_zero_pad<HP8, S>(sm, 2 * FR, H);
+  for (int m = 0; m < 3; ++m) rm_load_w_t<HP8, S>(Wsm + m * WT, a.W[m], H);
   cp_async_wait<0>();
   __syncthreads();
   f_layernorm_rows(Xs, Ns, a.gamma, a.beta, a.eps, row0, d, a.qn, a.mean, a.rstd, a.kmask, a.qmask);
@@ -506,12 +513,11 @@ __global__ void __launch_bounds__(FT, 3) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDim
   nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
   const int m0 = mt * 16, n0 = nh * 32;
   const long row0 = (long)blockIdx.x * FR;
-  for (int i = t; i < 2 * TILE + 2 * WT; i += FT) sm[i] = 0.f;
-  __syncthreads();
   rm_load_tile_async<S>(Ys, a.y, row0, d.N, H, rm_vec2_ok(a.y, H));
   cp_async_commit();
-  rm_load_w_t<S>(Wsm, a.W1, H);
-  rm_load_w_t<S>(Wsm + WT, a.W2, H);
+  rm_zero_pad<HP8, S>(sm, 2 * FR, H);
+  rm_load_w_t<HP8, S>(Wsm, a.W1, H);
+  rm_load_w_t<HP8, S>(Wsm + WT, a.W2, H);
   const Drop dh = make_drop(a.rate, a.seed, a.step, a.site_h);
   const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
   cp_async_wait<0>();
