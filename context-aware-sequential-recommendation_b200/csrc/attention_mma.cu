@@ -32,7 +32,7 @@ __device__ __forceinline__ void am_first2(const float* __restrict__ kmask_b, con
   if (threadIdx.x == 0) { s2[0] = T; s2[1] = ids_b ? T : 0; }
   __syncthreads();
   int mk = T, mq = T;
-  for (int j = threadIdx.x; j < T; j += AM_THREADS) {
+  for (int j = threadIdx.x; j < T; j += (int)blockDim.x) {
     if (mk == T && kmask_b[j] != 0.f) mk = j;
     if (ids_b && mq == T && ids_b[j] != 0) mq = j;
   }
@@ -46,7 +46,7 @@ __device__ __forceinline__ void am_first2(const float* __restrict__ kmask_b, con
 // asynchronous tile load: dst[r][c] = src[(row0 + r) * ld + c] for 0 <= row0 + r < T and c < d, zero rows outside the
 // sequence; columns d.. of dst are left alone (zeroed once by am_zero_pad).  Warp w copies rows w, w+4, ..; lane l the
 // 8-byte column pair l (vec2: d even, rows 8-byte aligned), else 4-byte copies.
-template <int NROWS, int DS>
+template <int NROWS, int DS, int NW = 4>
 __device__ __forceinline__ void am_load_rows_async(float* __restrict__ dst, const float* __restrict__ src, long ld,
                                                    int row0, int T, int d, bool vec2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -56,16 +56,16 @@ __device__ __forceinline__ void am_load_rows_async(float* __restrict__ dst, cons
       int row = row0 + warp;
       const float* s = src + (long)row * ld + 2 * lane;
 #pragma unroll
-      for (int k = 0; k < NROWS / 4; ++k) {
+      for (int k = 0; k < NROWS / NW; ++k) {
         const bool ok = (unsigned)row < (unsigned)T;
         cp_async<8>(o, ok ? s : src, ok);
-        o += 4 * DS;
-        s += 4 * ld;
-        row += 4;
+        o += NW * DS;
+        s += NW * ld;
+        row += NW;
       }
     }
   } else {
-    for (int r = warp; r < NROWS; r += AM_THREADS / 32) {
+    for (int r = warp; r < NROWS; r += NW) {
       const int row = row0 + r;
       const bool ok = (unsigned)row < (unsigned)T;
       const float* s = src + (long)(ok ? row : 0) * ld;
@@ -81,7 +81,7 @@ __device__ __forceinline__ bool am_vec2_ok(const void* p, long ld, int d, int hh
 // zero the columns d..DP-1 of `rows` consecutive tile rows (row stride DS)
 template <int DP, int DS>
 __device__ __forceinline__ void am_zero_pad(float* __restrict__ buf, int rows, int d) {
-  for (int r = threadIdx.x; r < rows; r += AM_THREADS)
+  for (int r = threadIdx.x; r < rows; r += (int)blockDim.x)
     for (int c = d; c < DP; ++c) buf[r * DS + c] = 0.f;
 }
 
@@ -161,16 +161,20 @@ __device__ __forceinline__ void am_block(const AttnDims& dm, int& b, int& hh, in
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int KS, int NT>
-__global__ void __launch_bounds__(AM_THREADS, (KS <= 7 && NT == 4) ? 4 : 1) attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
-  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TC = 8 * NT;
+// KG = 1: 4 warps, each streams whole chunks.  KG = 2: 8 warps; warps w and w+4 own the same 16 rows and split every
+// staged chunk of 16*NT keys in halves (each keeps its own running max / sum / O), merged through shared memory at the
+// end -- the critical path of the late (long) row tiles halves.
+template <int KS, int NT, int KG>
+__global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4) ? (KG == 1 ? 4 : 2) : 1)
+attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
+  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   CAST_DYN_SMEM(float, sm);
   __shared__ int s_first[2];
   float* Qs = sm;                         // [64][DS]
   float* Kst = Qs + AM_T * DS;            // [2][TC][DS]
   float* Vst = Kst + 2 * TC * DS;         // [2][TC][DS]
   float* kms = Vst + 2 * TC * DS;         // [2][TC] key mask of the chunk (0 outside the sequence)
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, warp = wid & 3, kg = wid >> 2, g = lane >> 2, tig = lane & 3;
   const int T = dm.T, d = dm.d;
   int b, hh, ntile, tile;
   am_block(dm, b, hh, ntile, tile);
@@ -180,14 +184,14 @@ __global__ void __launch_bounds__(AM_THREADS, (KS <= 7 && NT == 4) ? 4 : 1) attn
   am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
   const long sbase = ((long)b * dm.h + hh) * T;
   if (q0 + AM_T <= qstart) {  // every row of this tile is padding: output = residual only (block-uniform exit)
-    for (int idx = t; idx < AM_T * d; idx += AM_THREADS) {
+    for (int idx = t; idx < AM_T * d; idx += NTHR) {
       const int i = q0 + idx / d, c = idx % d;
       if (i >= 0) {
         const long off = (rowbase + i) * dm.H + hh * d + c;
         a.out[off] = a.resid[off];
       }
     }
-    for (int r = t; r < AM_T; r += AM_THREADS) {
+    for (int r = t; r < AM_T; r += NTHR) {
       const int i = q0 + r;
       if (i >= 0) {
         if (a.row_max) a.row_max[sbase + i] = 0.f;
@@ -212,12 +216,12 @@ __global__ void __launch_bounds__(AM_THREADS, (KS <= 7 && NT == 4) ? 4 : 1) attn
   const float* Vg = a.V + rowbase * a.ldv + hh * d;
   const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
   auto issue = [&](int j0, int st) {
-    am_load_rows_async<TC, DS>(Kst + st * TC * DS, Kg, a.ldk, j0, T, d, vk);
-    am_load_rows_async<TC, DS>(Vst + st * TC * DS, Vg, a.ldv, j0, T, d, vv);
+    am_load_rows_async<TC, DS, NW>(Kst + st * TC * DS, Kg, a.ldk, j0, T, d, vk);
+    am_load_rows_async<TC, DS, NW>(Vst + st * TC * DS, Vg, a.ldv, j0, T, d, vv);
     if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
     cp_async_commit();
   };
-  am_load_rows_async<AM_T, DS>(Qs, Qg, a.ldq, q0, T, d, vq);
+  am_load_rows_async<AM_T, DS, NW>(Qs, Qg, a.ldq, q0, T, d, vq);
   issue(kbeg, 0);
   am_zero_pad<DP, DS>(sm, AM_T + 4 * TC, d);
 
@@ -237,20 +241,21 @@ __global__ void __launch_bounds__(AM_THREADS, (KS <= 7 && NT == 4) ? 4 : 1) attn
   const bool vr = am_vec2_ok(a.resid, dm.H, d, hh);
   const int rst = nch & 1;  // stage not used by the last chunk
   for (int ci = 0; ci < nch; ++ci) {
-    const int j0 = kbeg + ci * TC, st = ci & 1;
+    const int j0s = kbeg + ci * TC, st = ci & 1;
+    const int j0 = j0s + kg * TW;  // this warp's half of the staged chunk
     if (ci + 1 < nch) {
-      issue(j0 + TC, st ^ 1);
+      issue(j0s + TC, st ^ 1);
     } else {
-      am_load_rows_async<TC, DS>(Kst + rst * TC * DS, Rg, dm.H, q0, T, d, vr);
-      if (TC < AM_T) am_load_rows_async<TC, DS>(Vst + rst * TC * DS, Rg, dm.H, q0 + TC, T, d, vr);
+      am_load_rows_async<TC, DS, NW>(Kst + rst * TC * DS, Rg, dm.H, q0, T, d, vr);
+      if (TC < AM_T) am_load_rows_async<TC, DS, NW>(Vst + rst * TC * DS, Rg, dm.H, q0 + TC, T, d, vr);
       cp_async_commit();
     }
     cp_async_wait<1>();
     __syncthreads();
     if (wact && j0 < wkend) {
-      const float* Ks = Kst + st * TC * DS;
-      const float* Vs = Vst + st * TC * DS;
-      const float* km_s = kms + st * TC;
+      const float* Ks = Kst + (st * TC + kg * TW) * DS;
+      const float* Vs = Vst + (st * TC + kg * TW) * DS;
+      const float* km_s = kms + st * TC + kg * TW;
       int ntl = (wkend - j0 + 7) >> 3;
       if (ntl > NT) ntl = NT;
       float s[NT][4];
@@ -313,6 +318,36 @@ __global__ void __launch_bounds__(AM_THREADS, (KS <= 7 && NT == 4) ? 4 : 1) attn
   __syncthreads();
   lA = quad_sum(lA);
   lB = quad_sum(lB);
+  if (KG == 2) {  // fold the second key group's (max, sum, O) into the first through the stage the last chunk used
+    float* mo = Kst + ((nch - 1) & 1) * TC * DS;  // [128 threads][4 * NTO]
+    float* ml = Vst + ((nch - 1) & 1) * TC * DS;  // [128 threads][4]
+    const int slot = warp * 32 + lane;
+    if (kg == 1) {
+#pragma unroll
+      for (int no = 0; no < NTO; ++no)
+        *reinterpret_cast<float4*>(mo + (slot * NTO + no) * 4) = make_float4(o[no][0], o[no][1], o[no][2], o[no][3]);
+      *reinterpret_cast<float4*>(ml + slot * 4) = make_float4(mA, mB, lA, lB);
+    }
+    __syncthreads();
+    if (kg == 1) return;
+    const float4 st1 = *reinterpret_cast<const float4*>(ml + slot * 4);
+    const float nmA = fmaxf(mA, st1.x), nmB = fmaxf(mB, st1.y);
+    // a group that saw no chunk has max = -inf, sum = 0: its factor is exp(-inf) = 0 (nm is finite for live rows)
+    const float a0A = nmA == -INFINITY ? 0.f : __expf(mA - nmA), a1A = nmA == -INFINITY ? 0.f : __expf(st1.x - nmA);
+    const float a0B = nmB == -INFINITY ? 0.f : __expf(mB - nmB), a1B = nmB == -INFINITY ? 0.f : __expf(st1.y - nmB);
+    lA = lA * a0A + st1.z * a1A;
+    lB = lB * a0B + st1.w * a1B;
+    mA = nmA;
+    mB = nmB;
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) {
+      const float4 o1 = *reinterpret_cast<const float4*>(mo + (slot * NTO + no) * 4);
+      o[no][0] = o[no][0] * a0A + o1.x * a1A;
+      o[no][1] = o[no][1] * a0A + o1.y * a1A;
+      o[no][2] = o[no][2] * a0B + o1.z * a1B;
+      o[no][3] = o[no][3] * a0B + o1.w * a1B;
+    }
+  }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int i = half ? iB : iA;
@@ -347,9 +382,9 @@ struct AttnBwdMmaArgs {
   const float* resid;  // queries = LN(x) [B*T, H]
 };
 
-template <int KS, int NT>
-__global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
-  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TC = 8 * NT;
+template <int KS, int NT, int KG>
+__global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 2) ? 2 : 1) attn_bwd_dq_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
   __shared__ int s_first[2];
@@ -359,7 +394,7 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaA
   float* Vst = Kst + 2 * TC * DS;   // [2][TC][DS]
   float* kms = Vst + 2 * TC * DS;   // [2][TC]
   float* Dsm = kms + 2 * TC;        // [64] D_i of the tile's rows
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, warp = wid & 3, kg = wid >> 2, g = lane >> 2, tig = lane & 3;
   const int T = dm.T, d = dm.d;
   int b, hh, ntile, tile;
   am_block(dm, b, hh, ntile, tile);
@@ -369,11 +404,11 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaA
   int first_key, qstart;
   am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
   if (q0 + AM_T <= qstart) {  // padding-only tile: zero gradient
-    for (int idx = t; idx < AM_T * d; idx += AM_THREADS) {
+    for (int idx = t; idx < AM_T * d; idx += NTHR) {
       const int i = q0 + idx / d, c = idx % d;
       if (i >= 0) a.dQ[(rowbase + i) * a.lddq + hh * d + c] = 0.f;
     }
-    for (int r = t; r < AM_T; r += AM_THREADS)
+    for (int r = t; r < AM_T; r += NTHR)
       if (q0 + r >= 0) a.rowD[sbase + q0 + r] = 0.f;
     return;
   }
@@ -391,17 +426,17 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaA
   const float* Vg = a.V + rowbase * a.ldv + hh * d;
   const bool vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
   auto issue = [&](int j0, int st) {
-    am_load_rows_async<TC, DS>(Kst + st * TC * DS, Kg, a.ldk, j0, T, d, vk);
-    am_load_rows_async<TC, DS>(Vst + st * TC * DS, Vg, a.ldv, j0, T, d, vv);
+    am_load_rows_async<TC, DS, NW>(Kst + st * TC * DS, Kg, a.ldk, j0, T, d, vk);
+    am_load_rows_async<TC, DS, NW>(Vst + st * TC * DS, Vg, a.ldv, j0, T, d, vv);
     if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
     cp_async_commit();
   };
-  am_load_rows_async<AM_T, DS>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
-  am_load_rows_async<AM_T, DS>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
+  am_load_rows_async<AM_T, DS, NW>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
+  am_load_rows_async<AM_T, DS, NW>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
   if (nch > 0) issue(kbeg, 0); else cp_async_commit();
   am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
   // D_i = dO_i . (out_i - queries_i) over this head's columns: one warp per row
-  for (int r = warp; r < AM_T; r += AM_THREADS / 32) {
+  for (int r = wid; r < AM_T; r += NW) {
     const int i = q0 + r;
     float acc = 0.f;
     if (i >= qstart && i >= 0) {
@@ -428,18 +463,19 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaA
     for (int c = 0; c < 4; ++c) o[no][c] = 0.f;
 
   for (int ci = 0; ci < nch; ++ci) {
-    const int j0 = kbeg + ci * TC, st = ci & 1;
+    const int j0s = kbeg + ci * TC, st = ci & 1;
+    const int j0 = j0s + kg * TW;  // this warp's half of the staged chunk
     if (ci + 1 < nch) {
-      issue(j0 + TC, st ^ 1);
+      issue(j0s + TC, st ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
     if (wact && j0 < wkend) {
-      const float* Ks = Kst + st * TC * DS;
-      const float* Vs = Vst + st * TC * DS;
-      const float* km_s = kms + st * TC;
+      const float* Ks = Kst + (st * TC + kg * TW) * DS;
+      const float* Vs = Vst + (st * TC + kg * TW) * DS;
+      const float* km_s = kms + st * TC + kg * TW;
       int ntl = (wkend - j0 + 7) >> 3;
       if (ntl > NT) ntl = NT;
       float s[NT][4], dp[NT][4];
@@ -475,6 +511,23 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaA
     __syncthreads();
   }
   cp_async_wait<0>();
+  if (KG == 2) {  // dQ = sum of the two key groups' partial products
+    __syncthreads();
+    float* mo = Kst;  // [128 threads][4 * NTO]
+    const int slot = warp * 32 + lane;
+    if (kg == 1) {
+#pragma unroll
+      for (int no = 0; no < NTO; ++no)
+        *reinterpret_cast<float4*>(mo + (slot * NTO + no) * 4) = make_float4(o[no][0], o[no][1], o[no][2], o[no][3]);
+    }
+    __syncthreads();
+    if (kg == 1) return;
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) {
+      const float4 o1 = *reinterpret_cast<const float4*>(mo + (slot * NTO + no) * 4);
+      o[no][0] += o1.x; o[no][1] += o1.y; o[no][2] += o1.z; o[no][3] += o1.w;
+    }
+  }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int i = half ? iB : iA;
@@ -491,9 +544,9 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dq_mma_kernel(AttnBwdMmaA
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
-template <int KS, int NT>
-__global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
-  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TC = 8 * NT;
+template <int KS, int NT, int KG>
+__global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 2) ? 2 : 1) attn_bwd_dkv_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
   __shared__ int s_first[2];
@@ -502,7 +555,7 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
   float* Qst = Vs + AM_T * DS;       // [2][TC][DS]
   float* dOst = Qst + 2 * TC * DS;   // [2][TC][DS]
   float* stat = dOst + 2 * TC * DS;  // [2][4][TC]: row max, 1/rowsum, D, query mask of the chunk's queries
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, warp = wid & 3, kg = wid >> 2, g = lane >> 2, tig = lane & 3;
   const int T = dm.T, d = dm.d;
   int b, hh, ntile, tile;
   am_block(dm, b, hh, ntile, tile);
@@ -514,7 +567,7 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
   const bool has_uniform = qstart < first_key;  // some computed (non-padding) row is fully masked
   if (k0 + AM_T <= first_key && !has_uniform) {
     // every key of this tile is masked and no row is uniform: P == 0 on the whole tile => zero gradients
-    for (int idx = t; idx < AM_T * d; idx += AM_THREADS) {
+    for (int idx = t; idx < AM_T * d; idx += NTHR) {
       const int j = k0 + idx / d, c = idx % d;
       if (j >= 0) {
         a.dK[(rowbase + j) * a.lddk + hh * d + c] = 0.f;
@@ -538,8 +591,8 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
   const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vo = am_vec2_ok(a.dO, dm.H, d, hh);
   auto issue = [&](int cc, int st) {
     const int c0 = am_row0(T, nchunk, cc, TC);
-    am_load_rows_async<TC, DS>(Qst + st * TC * DS, Qg, a.ldq, c0, T, d, vq);
-    am_load_rows_async<TC, DS>(dOst + st * TC * DS, dOg, dm.H, c0, T, d, vo);
+    am_load_rows_async<TC, DS, NW>(Qst + st * TC * DS, Qg, a.ldq, c0, T, d, vq);
+    am_load_rows_async<TC, DS, NW>(dOst + st * TC * DS, dOg, dm.H, c0, T, d, vo);
     if (t < TC) {
       const int i = c0 + t;
       const bool ok = i >= qstart && i >= 0;
@@ -556,8 +609,8 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
     while (cc < nchunk && !needed(cc)) ++cc;
     return cc;
   };
-  am_load_rows_async<AM_T, DS>(Ks, a.K + rowbase * a.ldk + hh * d, a.ldk, k0, T, d, am_vec2_ok(a.K, a.ldk, d, hh));
-  am_load_rows_async<AM_T, DS>(Vs, a.V + rowbase * a.ldv + hh * d, a.ldv, k0, T, d, am_vec2_ok(a.V, a.ldv, d, hh));
+  am_load_rows_async<AM_T, DS, NW>(Ks, a.K + rowbase * a.ldk + hh * d, a.ldk, k0, T, d, am_vec2_ok(a.K, a.ldk, d, hh));
+  am_load_rows_async<AM_T, DS, NW>(Vs, a.V + rowbase * a.ldv + hh * d, a.ldv, k0, T, d, am_vec2_ok(a.V, a.ldv, d, hh));
   int cc = next_needed(0);
   if (cc < nchunk) issue(cc, 0); else cp_async_commit();
   am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
@@ -575,8 +628,9 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
 
   for (int it = 0; cc < nchunk; ++it) {
     const int st = it & 1;
-    const int c0 = am_row0(T, nchunk, cc, TC);
-    const bool cuni = has_uniform && c0 < first_key;  // chunk holds uniform rows: they reach every key
+    const int c0s = am_row0(T, nchunk, cc, TC);
+    const int c0 = c0s + kg * TW;                      // this warp's half of the staged query chunk
+    const bool cuni = has_uniform && c0s < first_key;  // chunk holds uniform rows: they reach every key
     const int cn = next_needed(cc + 1);
     if (cn < nchunk) {
       issue(cn, st ^ 1);
@@ -589,9 +643,9 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
     int nt0 = cuni ? 0 : (r0 - c0) >> 3;
     if (nt0 < 0) nt0 = 0;
     if (r0 + 16 > 0 && nt0 < NT) {
-      const float* Qc = Qst + st * TC * DS;
-      const float* dOc = dOst + st * TC * DS;
-      const float* sp = stat + st * 4 * TC;
+      const float* Qc = Qst + (st * TC + kg * TW) * DS;
+      const float* dOc = dOst + (st * TC + kg * TW) * DS;
+      const float* sp = stat + st * 4 * TC + kg * TW;
       float s[NT][4], dp[NT][4];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
@@ -629,6 +683,28 @@ __global__ void __launch_bounds__(AM_THREADS) attn_bwd_dkv_mma_kernel(AttnBwdMma
     cc = cn;
   }
   cp_async_wait<0>();
+  if (KG == 2) {  // dK, dV = sums of the two query groups' partial products
+    __syncthreads();
+    float* mk = Qst;   // [128 threads][4 * NTO]
+    float* mv = dOst;
+    const int slot = warp * 32 + lane;
+    if (kg == 1) {
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) {
+        *reinterpret_cast<float4*>(mk + (slot * NTO + no) * 4) = make_float4(gk[no][0], gk[no][1], gk[no][2], gk[no][3]);
+        *reinterpret_cast<float4*>(mv + (slot * NTO + no) * 4) = make_float4(gv[no][0], gv[no][1], gv[no][2], gv[no][3]);
+      }
+    }
+    __syncthreads();
+    if (kg == 1) return;
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) {
+      const float4 k1 = *reinterpret_cast<const float4*>(mk + (slot * NTO + no) * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(mv + (slot * NTO + no) * 4);
+      gk[no][0] += k1.x; gk[no][1] += k1.y; gk[no][2] += k1.z; gk[no][3] += k1.w;
+      gv[no][0] += v1.x; gv[no][1] += v1.y; gv[no][2] += v1.z; gv[no][3] += v1.w;
+    }
+  }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int j = half ? jB : jA;
@@ -656,29 +732,35 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
   const dim3 grid((unsigned)(dm.B * dm.h), (unsigned)ntile);
   const size_t row = sizeof(float) * DS;
   if (which == 0) {
-    const size_t smem = (AM_T + 4 * TC) * row + sizeof(float) * 2 * TC;
-    auto kf = attn_fwd_mma_kernel<KS, NT>;
+    constexpr int KGF = (NT == 4) ? 2 : 1;  // 8 warps: two key groups per row block
+    constexpr int TCF = TC * KGF;
+    const size_t smem = (AM_T + 4 * TCF) * row + sizeof(float) * 2 * TCF;
+    auto kf = attn_fwd_mma_kernel<KS, NT, KGF>;
     if (smem > cfg[0]) {
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg[0] = smem;
     }
-    CAST_LAUNCH(kf, grid, dim3(AM_THREADS), smem, stream, *fa, dm);
+    CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGF), smem, stream, *fa, dm);
   } else if (which == 1) {
-    const size_t smem = (2 * AM_T + 4 * TC) * row + sizeof(float) * (2 * TC + AM_T);
-    auto kf = attn_bwd_dq_mma_kernel<KS, NT>;
+    constexpr int KGB = (NT == 4) ? 2 : 1;
+    constexpr int TCB = TC * KGB;
+    const size_t smem = (2 * AM_T + 4 * TCB) * row + sizeof(float) * (2 * TCB + AM_T);
+    auto kf = attn_bwd_dq_mma_kernel<KS, NT, KGB>;
     if (smem > cfg[1]) {
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg[1] = smem;
     }
-    CAST_LAUNCH(kf, grid, dim3(AM_THREADS), smem, stream, *ba, dm);
+    CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
   } else {
-    const size_t smem = (2 * AM_T + 4 * TC) * row + sizeof(float) * 8 * TC;
-    auto kf = attn_bwd_dkv_mma_kernel<KS, NT>;
+    constexpr int KGB = (NT == 4) ? 2 : 1;
+    constexpr int TCB = TC * KGB;
+    const size_t smem = (2 * AM_T + 4 * TCB) * row + sizeof(float) * 8 * TCB;
+    auto kf = attn_bwd_dkv_mma_kernel<KS, NT, KGB>;
     if (smem > cfg[2]) {
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg[2] = smem;
     }
-    CAST_LAUNCH(kf, grid, dim3(AM_THREADS), smem, stream, *ba, dm);
+    CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
   }
   return CAST_OK;
 }
