@@ -344,10 +344,17 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
       const long row = row0 + r;
       const bool ok = row < d.N;
       const float m = (ok && (!a.ids || a.ids[row] != 0)) ? 1.f : 0.f;
-      for (int c = lane; c < H; c += 32) {
-        const float gg = Gm[r * S + c] * m;
-        Gm[r * S + c] = gg;
-        Gd[r * S + c] = ok ? gg * drop_mul(dout, (unsigned long long)(row * H + c)) : 0.f;
+      for (int c = 2 * lane; c < H; c += 64) {  // a lane owns a column pair: one dropout hash word
+        float dm2[2];
+        drop_mul2(dout, (unsigned long long)(row * H + c), dm2[0], dm2[1]);
+        const float g0 = Gm[r * S + c] * m;
+        Gm[r * S + c] = g0;
+        Gd[r * S + c] = ok ? g0 * dm2[0] : 0.f;
+        if (c + 1 < H) {
+          const float g1 = Gm[r * S + c + 1] * m;
+          Gm[r * S + c + 1] = g1;
+          Gd[r * S + c + 1] = ok ? g1 * dm2[1] : 0.f;
+        }
       }
     }
     __syncthreads();
@@ -408,9 +415,25 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
 template <int HP8, int S>
 __device__ __forceinline__ void rm_load_w_t(float* __restrict__ Wt, const float* __restrict__ W, int H) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < HP8; k += FT / 32) {
-    const float* w = W + k * H;
-    for (int n = lane; n < HP8; n += 32) Wt[n * S + k] = (k < H && n < H) ? w[n] : 0.f;
+  constexpr int RW = HP8 / 8;  // weight rows per warp
+  float v[RW][2];
+#pragma unroll
+  for (int i = 0; i < RW; ++i) {  // all loads first (independent, in flight together), then the transposing stores
+    const int k = warp + 8 * i;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = lane + 32 * j;
+      v[i][j] = (k < H && n < H) ? W[k * H + n] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RW; ++i) {
+    const int k = warp + 8 * i;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = lane + 32 * j;
+      if (n < HP8) Wt[n * S + k] = v[i][j];
+    }
   }
 }
 
@@ -531,15 +554,21 @@ __global__ void __launch_bounds__(FT, 3) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDim
   for (int nt = 0; nt < 4; ++nt) {
     if (nt >= nact) continue;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+    for (int hf = 0; hf < 2; ++hf) {
+      const int r = m0 + g + hf * 8, c0 = n0 + nt * 8 + 2 * tig;
       const long row = row0 + r;
-      float h = 0.f;
-      if (c < H && row < d.N) {
-        h = fmaxf(acc[nt][e] + a.b1[c], 0.f) * drop_mul(dh, (unsigned long long)(row * H + c));
-        a.h1d[row * H + c] = h;
+      float dm2[2];
+      drop_mul2(dh, (unsigned long long)(row * H + c0), dm2[0], dm2[1]);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = c0 + cc;
+        float h = 0.f;
+        if (c < H && row < d.N) {
+          h = fmaxf(acc[nt][hf * 2 + cc] + a.b1[c], 0.f) * dm2[cc];
+          a.h1d[row * H + c] = h;
+        }
+        Ys[r * S + c] = h;
       }
-      Ys[r * S + c] = h;
     }
   }
   __syncthreads();
@@ -549,14 +578,21 @@ __global__ void __launch_bounds__(FT, 3) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDim
   for (int nt = 0; nt < 4; ++nt) {
     if (nt >= nact) continue;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int r = m0 + g + (e >> 1) * 8, c = n0 + nt * 8 + 2 * tig + (e & 1);
+    for (int hf = 0; hf < 2; ++hf) {
+      const int r = m0 + g + hf * 8, c0 = n0 + nt * 8 + 2 * tig;
       const long row = row0 + r;
-      if (c < H && row < d.N) {
-        const float m = a.ids ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;
-        float o = (acc[nt][e] + a.b2[c]) * drop_mul(dout, (unsigned long long)(row * H + c));
-        o += Ns[r * S + c];
-        a.xout[row * H + c] = o * m;
+      if (row >= d.N) continue;
+      const float m = a.ids ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;
+      float dm2[2];
+      drop_mul2(dout, (unsigned long long)(row * H + c0), dm2[0], dm2[1]);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = c0 + cc;
+        if (c < H) {
+          float o = (acc[nt][hf * 2 + cc] + a.b2[c]) * dm2[cc];
+          o += Ns[r * S + c];
+          a.xout[row * H + c] = o * m;
+        }
       }
     }
   }
