@@ -242,6 +242,7 @@ struct LnBwdOut {
   float dgamma, dbeta;  // column owned by thread (tid % 64) for tid < 128: tid/64 == 0 -> dgamma, == 1 -> dbeta
 };
 
+template <int NWARP = FT / 32>
 __device__ __forceinline__ void f_ln_bwd_rows(const float* __restrict__ Gs, const float* __restrict__ Xr, int sxr,
                                               int sxc, const float* __restrict__ Add,
                                               const float* __restrict__ gamma,
@@ -255,7 +256,7 @@ __device__ __forceinline__ void f_ln_bwd_rows(const float* __restrict__ Gs, cons
     const int lane = t & 31;
     const int c0 = lane, c1 = lane + 32;
     const float g0 = c0 < d.H ? gamma[c0] : 0.f, g1 = c1 < d.H ? gamma[c1] : 0.f;
-    for (int r = t >> 5; r < FR; r += FT / 32) {
+    for (int r = t >> 5; r < FR; r += NWARP) {
       const long row = row0 + r;
       float mu = 0.f, rs = 0.f;
       if (row < d.N) { mu = mean[row]; rs = rstd[row]; }
@@ -565,17 +566,17 @@ template <int KS>
 static void launch_qkv_bwd_mma(const QkvBwdArgs& a, FDims d, int grid, cudaStream_t stream) {
   d.HS = 8 * KS + 4;
   const size_t smem = qkv_bwd_mma_smem<KS>();
-  auto kf = qkv_bwd_mma_kernel<KS>;
+  auto kf = qkv_bwd_mma_kernel<KS, RM_BWD_NG>;
   CAST_FUSED_SMEM(kf, smem)
-  CAST_LAUNCH(kf, dim3(grid), dim3(FT), smem, stream, a, d);
+  CAST_LAUNCH(kf, dim3(grid), dim3(128 * RM_BWD_NG), smem, stream, a, d);
 }
 template <int KS>
 static void launch_ffn_bwd_mma(const FfnBwdArgs& a, FDims d, int grid, cudaStream_t stream) {
   d.HS = 8 * KS + 4;
   const size_t smem = ffn_bwd_mma_smem<KS>();
-  auto kf = ffn_bwd_mma_kernel<KS>;
+  auto kf = ffn_bwd_mma_kernel<KS, RM_BWD_NG>;
   CAST_FUSED_SMEM(kf, smem)
-  CAST_LAUNCH(kf, dim3(grid), dim3(FT), smem, stream, a, d);
+  CAST_LAUNCH(kf, dim3(grid), dim3(128 * RM_BWD_NG), smem, stream, a, d);
 }
 template <int KS>
 static void launch_ln_qkv_fwd_mma(const LnQkvArgs& a, FDims d, cudaStream_t stream) {

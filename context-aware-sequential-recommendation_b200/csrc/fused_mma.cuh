@@ -2,8 +2,8 @@
 // arithmetic and gradient layout, contractions as mma.sync m16n8k8 3xTF32 (mma_tf32.cuh), tiles streamed through a
 // two-stage cp.async pipeline so the next 64-row tile loads while the current one is multiplied.
 //
-//   CTA = 256 threads = 8 warps on one 64-row tile; warp w owns the 16-row block (w & 3) and the column half (w >> 2)
-//   of every 64 x H product, and the same (16 x 32) block of every H x H weight gradient.
+//   CTA = 8 warps (forward) or 16 warps (backward) on one 64-row tile; warp w owns the 16-row block (w & 3) and the
+//   column group (w >> 2: 32 or 16 columns) of every 64 x H product, and the same block of every H x H weight gradient.
 //   Tiles are row-major with stride S = 8*ceil(H/8) + 4 floats (16-byte rows, S/4 odd: ldmatrix conflict-free);
 //   weights sit in shared memory in their natural [in][out] layout:
 //     forward  C = A W      : B[k][n] = W[k][n]            -> per-lane LDS.32 fragments
@@ -16,7 +16,7 @@ namespace cast {
 
 // asynchronous copy of the 64-row tile starting at row0 of a row-major [N, H] tensor into dst (stride S); rows >= N
 // are zero-filled, columns >= H untouched (zeroed once at kernel start).  Warp w copies rows w, w+8, ...
-template <int S>
+template <int S, int NW = FT / 32>
 __device__ __forceinline__ void rm_load_tile_async(float* __restrict__ dst, const float* __restrict__ src, long row0,
                                                    long N, int H, bool vec2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -26,16 +26,16 @@ __device__ __forceinline__ void rm_load_tile_async(float* __restrict__ dst, cons
       long row = row0 + warp;
       const float* s = src + row * H + 2 * lane;
 #pragma unroll
-      for (int k = 0; k < FR / 8; ++k) {
+      for (int k = 0; k < FR / NW; ++k) {
         const bool ok = row < N;
         cp_async<8>(o, ok ? s : src, ok);
-        o += 8 * S;
-        s += 8 * (long)H;
-        row += 8;
+        o += NW * S;
+        s += NW * (long)H;
+        row += NW;
       }
     }
   } else {
-    for (int r = warp; r < FR; r += FT / 32) {
+    for (int r = warp; r < FR; r += NW) {
       const long row = row0 + r;
       const bool ok = row < N;
       const float* s = src + (ok ? row : 0) * H;
@@ -51,24 +51,24 @@ __device__ __forceinline__ bool rm_vec2_ok(const void* p, int H) {
 // W[H][H] row-major (global) -> Ws[k][n] stride S; the caller zeroed the buffer (64 rows) beforehand
 template <int S>
 __device__ __forceinline__ void rm_load_w(float* __restrict__ Ws, const float* __restrict__ W, int H) {
-  for (int idx = threadIdx.x; idx < H * H; idx += FT) {
+  for (int idx = threadIdx.x; idx < H * H; idx += (int)blockDim.x) {
     const int k = idx / H, n = idx - k * H;
     Ws[k * S + n] = W[idx];
   }
 }
 
 // acc[nt] += A[16 x 8KS] * Bt^T, Bt[n][k] row-major (k contiguous), n-tiles nt < nact (warp-uniform, <= 4)
-template <int KS, int S>
-__device__ __forceinline__ void rm_mm_bt(float (&acc)[4][4], const float* __restrict__ As,
+template <int KS, int S, int NTW = 4>
+__device__ __forceinline__ void rm_mm_bt(float (&acc)[NTW][4], const float* __restrict__ As,
                                          const float* __restrict__ Bt, int nact, int lane) {
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
     unsigned af[4], ah[4], al[4];
     ldsm_a<S>(af, As, ks * 8, lane);
     tf32_split_n(af, ah, al);
-    unsigned bh[4][2], bl[4][2];
+    unsigned bh[NTW][2], bl[NTW][2];
 #pragma unroll
-    for (int np = 0; np < 2; ++np) {
+    for (int np = 0; np < NTW / 2; ++np) {
       if (2 * np < nact) {
         unsigned bf[4];
         ldsm_b2<S>(bf, Bt + np * 16 * S, ks * 8, lane);
@@ -79,13 +79,13 @@ __device__ __forceinline__ void rm_mm_bt(float (&acc)[4][4], const float* __rest
       }
     }
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NTW; ++nt)
       if (nt < nact) mma_tf32(acc[nt], al, bh[nt][0], bh[nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NTW; ++nt)
       if (nt < nact) mma_tf32(acc[nt], ah, bl[nt][0], bl[nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NTW; ++nt)
       if (nt < nact) mma_tf32(acc[nt], ah, bh[nt][0], bh[nt][1]);
   }
 }
@@ -123,8 +123,8 @@ __device__ __forceinline__ void rm_mm_b(float (&acc)[4][4], const float* __restr
 
 // weight gradients: acc_j[nt][.] += sum_{r<64} X[r][m0 + .] * G_j[r][n0 + 8nt + .] for NB gradient tiles sharing X.
 // Fragments come straight from the row-major tiles (A^T: a0 = X[r0+tig][m0+g], ...).
-template <int NB, int S>
-__device__ __forceinline__ void rm_wgrad(float (&acc)[NB][4][4], const float* __restrict__ X, int m0,
+template <int NB, int S, int NTW = 4>
+__device__ __forceinline__ void rm_wgrad(float (&acc)[NB][NTW][4], const float* __restrict__ X, int m0,
                                          const float* const (&G)[NB], int n0, int nact, int lane) {
   const int g = lane >> 2, tig = lane & 3;
 #pragma unroll 2
@@ -138,40 +138,42 @@ __device__ __forceinline__ void rm_wgrad(float (&acc)[NB][4][4], const float* __
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const float* gb = G[j] + (r0 + tig) * S + n0 + g;
-      unsigned bh[4][2], bl[4][2];
+      unsigned bh[NTW][2], bl[NTW][2];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NTW; ++nt) {
         if (nt < nact) {
           tf32_split(gb[nt * 8], bh[nt][0], bl[nt][0]);
           tf32_split(gb[4 * S + nt * 8], bh[nt][1], bl[nt][1]);
         }
       }
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < NTW; ++nt)
         if (nt < nact) mma_tf32(acc[j][nt], al, bh[nt][0], bh[nt][1]);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < NTW; ++nt)
         if (nt < nact) mma_tf32(acc[j][nt], ah, bl[nt][0], bl[nt][1]);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < NTW; ++nt)
         if (nt < nact) mma_tf32(acc[j][nt], ah, bh[nt][0], bh[nt][1]);
     }
   }
 }
 
-__device__ __forceinline__ void rm_zero(float (&acc)[4][4]) {
+template <int NTW>
+__device__ __forceinline__ void rm_zero(float (&acc)[NTW][4]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NTW; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 }
 
 // per-CTA weight-gradient partial from the warp's fragment block: P[k * H + n]
-__device__ __forceinline__ void rm_store_wpartial(float* __restrict__ P, const float (&acc)[4][4], int m0, int n0,
+template <int NTW>
+__device__ __forceinline__ void rm_store_wpartial(float* __restrict__ P, const float (&acc)[NTW][4], int m0, int n0,
                                                   int nact, int H, int lane) {
   const int g = lane >> 2, tig = lane & 3;
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
+  for (int nt = 0; nt < NTW; ++nt) {
     if (nt >= nact) continue;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -182,19 +184,20 @@ __device__ __forceinline__ void rm_store_wpartial(float* __restrict__ P, const f
 }
 
 // ------------------------------------------------------------------------------------------------ qkv backward
-template <int KS>
-__global__ void __launch_bounds__(FT, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims d) {
-  constexpr int S = 8 * KS + 4, TILE = FR * S, STAGE = 5 * TILE;
+// NG column groups per row block: 2 => 8 warps x (16 rows x 32 columns), 4 => 16 warps x (16 x 16)
+template <int KS, int NG>
+__global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims d) {
+  constexpr int S = 8 * KS + 4, TILE = FR * S, STAGE = 5 * TILE, BT = 128 * NG, NW = 4 * NG, NTW = 8 / NG;
   CAST_DYN_SMEM(float, sm);
   float* Wsm = sm + 2 * STAGE;      // Wq | Wk | Wv, each [64][S] natural layout, zero padded
   float* rowstat = Wsm + 3 * TILE;  // [FR][4]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
   const int mt = warp & 3, nh = warp >> 2;
   const int H = d.H;
-  int nact = KS - 4 * nh;
-  nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
-  const int m0 = mt * 16, n0 = nh * 32;
-  for (int i = t; i < 2 * STAGE + 3 * TILE; i += FT) sm[i] = 0.f;
+  int nact = KS - NTW * nh;
+  nact = nact < 0 ? 0 : (nact > NTW ? NTW : nact);
+  const int m0 = mt * 16, n0 = nh * NTW * 8;
+  for (int i = t; i < 2 * STAGE + 3 * TILE; i += BT) sm[i] = 0.f;
   __syncthreads();
   rm_load_w<S>(Wsm, a.Wq, H);
   rm_load_w<S>(Wsm + TILE, a.Wk, H);
@@ -204,14 +207,14 @@ __global__ void __launch_bounds__(FT, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims 
   auto issue = [&](long tile, int st) {
     float* b = sm + st * STAGE;
     const long row0 = tile * FR;
-    rm_load_tile_async<S>(b, a.dQ, row0, d.N, H, v0);
-    rm_load_tile_async<S>(b + TILE, a.dK, row0, d.N, H, v1);
-    rm_load_tile_async<S>(b + 2 * TILE, a.dV, row0, d.N, H, v2);
-    rm_load_tile_async<S>(b + 3 * TILE, a.x, row0, d.N, H, v3);
-    rm_load_tile_async<S>(b + 4 * TILE, a.qn, row0, d.N, H, v4);
+    rm_load_tile_async<S, NW>(b, a.dQ, row0, d.N, H, v0);
+    rm_load_tile_async<S, NW>(b + TILE, a.dK, row0, d.N, H, v1);
+    rm_load_tile_async<S, NW>(b + 2 * TILE, a.dV, row0, d.N, H, v2);
+    rm_load_tile_async<S, NW>(b + 3 * TILE, a.x, row0, d.N, H, v3);
+    rm_load_tile_async<S, NW>(b + 4 * TILE, a.qn, row0, d.N, H, v4);
     cp_async_commit();
   };
-  float gWq[1][4][4], gWkv[2][4][4];
+  float gWq[1][NTW][4], gWkv[2][NTW][4];
   rm_zero(gWq[0]);
   rm_zero(gWkv[0]);
   rm_zero(gWkv[1]);
@@ -236,9 +239,9 @@ __global__ void __launch_bounds__(FT, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims 
     }
     __syncthreads();
     // gradient of `outputs += queries` for this thread's fragment of dqn (fetched early, consumed after the products)
-    float dres[4][4];
+    float dres[NTW][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const long row = row0 + m0 + g + (e >> 1) * 8;
@@ -247,22 +250,22 @@ __global__ void __launch_bounds__(FT, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims 
       }
     {
       const float* const gq[1] = {Gq};
-      rm_wgrad<1, S>(gWq, Qn, m0, gq, n0, nact, lane);
+      rm_wgrad<1, S, NTW>(gWq, Qn, m0, gq, n0, nact, lane);
       const float* const gkv[2] = {Gk, Gv};
-      rm_wgrad<2, S>(gWkv, X, m0, gkv, n0, nact, lane);
+      rm_wgrad<2, S, NTW>(gWkv, X, m0, gkv, n0, nact, lane);
     }
-    float accq[4][4], acck[4][4];
+    float accq[NTW][4], acck[NTW][4];
     rm_zero(accq);
     rm_zero(acck);
-    rm_mm_bt<KS, S>(accq, Gq + m0 * S, Wsm + n0 * S, nact, lane);             // dqn (without the residual)
-    rm_mm_bt<KS, S>(acck, Gk + m0 * S, Wsm + TILE + n0 * S, nact, lane);      // dx through K ...
-    rm_mm_bt<KS, S>(acck, Gv + m0 * S, Wsm + 2 * TILE + n0 * S, nact, lane);  // ... and V
+    rm_mm_bt<KS, S, NTW>(accq, Gq + m0 * S, Wsm + n0 * S, nact, lane);             // dqn (without the residual)
+    rm_mm_bt<KS, S, NTW>(acck, Gk + m0 * S, Wsm + TILE + n0 * S, nact, lane);      // dx through K ...
+    rm_mm_bt<KS, S, NTW>(acck, Gv + m0 * S, Wsm + 2 * TILE + n0 * S, nact, lane);  // ... and V
     f_colsum(Gq, 0, d, vb);
     f_colsum(Gk, 1, d, vb);
     f_colsum(Gv, 2, d, vb);
     __syncthreads();
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < NTW; ++nt) {
       if (nt >= nact) continue;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(FT, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims 
       }
     }
     __syncthreads();
-    f_ln_bwd_rows(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet);
+    f_ln_bwd_rows<NW>(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet);
   }
   float* P = a.partial + (long)blockIdx.x * (2L * H + 3L * (H * H + H));
   if (t < 64 && t < H) P[H + t] = dgam;
@@ -286,9 +289,9 @@ __global__ void __launch_bounds__(FT, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, FDims 
 }
 
 // ------------------------------------------------------------------------------------------------ ffn backward
-template <int KS>
-__global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims d) {
-  constexpr int S = 8 * KS + 4, TILE = FR * S, STAGE = 4 * TILE;
+template <int KS, int NG>
+__global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims d) {
+  constexpr int S = 8 * KS + 4, TILE = FR * S, STAGE = 4 * TILE, BT = 128 * NG, NW = 4 * NG, NTW = 8 / NG;
   CAST_DYN_SMEM(float, sm);
   float* Gd = sm + 2 * STAGE;  // dx * mask * dropout, later dzn
   float* Dh = Gd + TILE;       // gradient at the FFN hidden pre-activation
@@ -298,12 +301,12 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
   const int mt = warp & 3, nh = warp >> 2;
   const int H = d.H;
-  int nact = KS - 4 * nh;
-  nact = nact < 0 ? 0 : (nact > 4 ? 4 : nact);
-  const int m0 = mt * 16, n0 = nh * 32;
+  int nact = KS - NTW * nh;
+  nact = nact < 0 ? 0 : (nact > NTW ? NTW : nact);
+  const int m0 = mt * 16, n0 = nh * NTW * 8;
   const float scale = a.rate > 0.f ? 1.0f / (1.0f - a.rate) : 1.0f;
   const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
-  for (int i = t; i < 2 * STAGE + 4 * TILE; i += FT) sm[i] = 0.f;
+  for (int i = t; i < 2 * STAGE + 4 * TILE; i += BT) sm[i] = 0.f;
   __syncthreads();
   rm_load_w<S>(W1s, a.W1, H);
   rm_load_w<S>(W2s, a.W2, H);
@@ -311,13 +314,13 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
   auto issue = [&](long tile, int st) {
     float* b = sm + st * STAGE;
     const long row0 = tile * FR;
-    rm_load_tile_async<S>(b, a.dx, row0, d.N, H, v0);
-    rm_load_tile_async<S>(b + TILE, a.zn, row0, d.N, H, v1);
-    rm_load_tile_async<S>(b + 2 * TILE, a.h1d, row0, d.N, H, v2);
-    rm_load_tile_async<S>(b + 3 * TILE, a.y, row0, d.N, H, v3);
+    rm_load_tile_async<S, NW>(b, a.dx, row0, d.N, H, v0);
+    rm_load_tile_async<S, NW>(b + TILE, a.zn, row0, d.N, H, v1);
+    rm_load_tile_async<S, NW>(b + 2 * TILE, a.h1d, row0, d.N, H, v2);
+    rm_load_tile_async<S, NW>(b + 3 * TILE, a.y, row0, d.N, H, v3);
     cp_async_commit();
   };
-  float gW1[1][4][4], gW2[1][4][4];
+  float gW1[1][NTW][4], gW2[1][NTW][4];
   rm_zero(gW1[0]);
   rm_zero(gW2[0]);
   float vb = 0.f;  // thread-owned vector gradient: group 0 -> db2, 1 -> db1 (tid/64), column tid%64
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
     }
     __syncthreads();
     // masked / dropped upstream gradient
-    for (int r = warp; r < FR; r += FT / 32) {
+    for (int r = warp; r < FR; r += NW) {
       const long row = row0 + r;
       const bool ok = row < d.N;
       const float m = (ok && (!a.ids || a.ids[row] != 0)) ? 1.f : 0.f;
@@ -361,12 +364,12 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
     // dW2 += h1d^T Gd ; db2 += colsum(Gd) ; dh = (Gd W2^T) * relu/dropout mask
     {
       const float* const gb[1] = {Gd};
-      rm_wgrad<1, S>(gW2, Hd, m0, gb, n0, nact, lane);
-      float acc[4][4];
+      rm_wgrad<1, S, NTW>(gW2, Hd, m0, gb, n0, nact, lane);
+      float acc[NTW][4];
       rm_zero(acc);
-      rm_mm_bt<KS, S>(acc, Gd + m0 * S, W2s + n0 * S, nact, lane);
+      rm_mm_bt<KS, S, NTW>(acc, Gd + m0 * S, W2s + n0 * S, nact, lane);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NTW; ++nt) {
         if (nt >= nact) continue;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -380,12 +383,12 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
     // dW1 += zn^T Dh ; db1 += colsum(Dh) ; dzn = Dh W1^T + Gm  (stored over Gd)
     {
       const float* const gb[1] = {Dh};
-      rm_wgrad<1, S>(gW1, Zn, m0, gb, n0, nact, lane);
-      float acc[4][4];
+      rm_wgrad<1, S, NTW>(gW1, Zn, m0, gb, n0, nact, lane);
+      float acc[NTW][4];
       rm_zero(acc);
-      rm_mm_bt<KS, S>(acc, Dh + m0 * S, W1s + n0 * S, nact, lane);
+      rm_mm_bt<KS, S, NTW>(acc, Dh + m0 * S, W1s + n0 * S, nact, lane);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NTW; ++nt) {
         if (nt >= nact) continue;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(FT, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, FDims 
     }
     f_colsum(Dh, 1, d, vb);
     __syncthreads();
-    f_ln_bwd_rows(Gd, Yr, S, 1, nullptr, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dy, dgam, dbet);
+    f_ln_bwd_rows<NW>(Gd, Yr, S, 1, nullptr, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dy, dgam, dbet);
   }
   float* P = a.partial + (long)blockIdx.x * (2L * H + 2L * (H * H + H));
   if (t < 64 && t < H) P[H + t] = dgam;
@@ -606,6 +609,8 @@ template <int KS>
 static size_t ln_ffn_fwd_mma_smem() {
   return sizeof(float) * ((size_t)2 * FR * (8 * KS + 4) + (size_t)2 * 8 * KS * (8 * KS + 4));
 }
+
+constexpr int RM_BWD_NG = 4;  // column groups (x4 row blocks = 16 warps) of the backward row kernels
 
 template <int KS>
 static size_t qkv_bwd_mma_smem() { return sizeof(float) * ((size_t)(10 + 3) * FR * (8 * KS + 4) + FR * 4); }
