@@ -647,6 +647,11 @@ extern "C" int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* 
   return check_launch("ln_ffn_fwd");
 }
 
+/* number of per-CTA partial blocks cast_ffn_bwd / cast_qkv_bwd leave in their workspace for N rows */
+extern "C" int cast_block_bwd_parts(long N, int which) {  // which: 0 = cast_ffn_bwd, 1 = cast_qkv_bwd
+  return bwd_grid(cdiv(N, FR), (which == 1 || (g_fused_backend & 1)) ? 1 : 2);
+}
+
 extern "C" size_t cast_block_bwd_workspace_bytes(long N, int H) {
   const long ntiles = cdiv(N, FR);
   return (size_t)bwd_grid(ntiles) * (size_t)(2L * H + 3L * ((long)H * H + H)) * sizeof(float);
@@ -657,7 +662,7 @@ extern "C" int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, co
                             float drop_rate, unsigned long long seed, const unsigned long long* step, int site_out,
                             long N, int H, float* dy, float* grads_out, void* workspace, size_t workspace_bytes,
                             void* stream) {
-  if (!dx || !zn || !h1d || !y || !mean || !rstd || !gamma || !W1 || !W2 || !dy || !grads_out || N <= 0)
+  if (!dx || !zn || !h1d || !y || !mean || !rstd || !gamma || !W1 || !W2 || !dy || N <= 0)
     return set_error(CAST_ERR_BAD_ARG, "ffn_bwd");
   if (!cast_fused_supported(H)) return set_error(CAST_ERR_UNSUPPORTED, "ffn_bwd: H > 64");
   if (!workspace || workspace_bytes < cast_block_bwd_workspace_bytes(N, H))
@@ -678,7 +683,7 @@ extern "C" int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, co
     CAST_LAUNCH(ffn_bwd_kernel, dim3(grid), dim3(FT), smem, (cudaStream_t)stream, a, d);
   }
   int rc = check_launch("ffn_bwd");
-  if (rc) return rc;
+  if (rc || !grads_out) return rc;  // grads_out == null: partials stay in the workspace (cast_reduce_partials_batch)
   const long count = 2L * H + 2L * ((long)H * H + H);
   return launch_reduce_partials(static_cast<float*>(workspace), grid, count, grads_out, count, (float*)nullptr,
                                 (cudaStream_t)stream);
@@ -688,8 +693,7 @@ extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, c
                             const float* qn, const float* mean, const float* rstd, const float* gamma, const float* Wq,
                             const float* Wk, const float* Wv, long N, int H, float* dx, float* grads_out,
                             void* workspace, size_t workspace_bytes, void* stream) {
-  if (!dQ || !dK || !dV || !dres || !x || !qn || !mean || !rstd || !gamma || !Wq || !Wk || !Wv || !dx || !grads_out ||
-      N <= 0)
+  if (!dQ || !dK || !dV || !dres || !x || !qn || !mean || !rstd || !gamma || !Wq || !Wk || !Wv || !dx || N <= 0)
     return set_error(CAST_ERR_BAD_ARG, "qkv_bwd");
   if (!cast_fused_supported(H)) return set_error(CAST_ERR_UNSUPPORTED, "qkv_bwd: H > 64");
   if (!workspace || workspace_bytes < cast_block_bwd_workspace_bytes(N, H))
@@ -709,7 +713,7 @@ extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, c
     CAST_LAUNCH(qkv_bwd_kernel, dim3(grid), dim3(FT), smem, (cudaStream_t)stream, a, d);
   }
   int rc = check_launch("qkv_bwd");
-  if (rc) return rc;
+  if (rc || !grads_out) return rc;
   const long count = 2L * H + 3L * ((long)H * H + H);
   return launch_reduce_partials(static_cast<float*>(workspace), grid, count, grads_out, count, (float*)nullptr,
                                 (cudaStream_t)stream);

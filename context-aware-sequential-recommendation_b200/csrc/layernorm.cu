@@ -161,6 +161,49 @@ reduce_partials_kernel(const float* __restrict__ partial, int nparts, long count
   }
 }
 
+// several independent reductions in one launch (blockIdx.y = job): the per-CTA gradient partials of every fused
+// backward kernel of a step are folded once, after the last of them, instead of by one small launch each
+constexpr int RP_MAX_JOBS = 16;
+struct ReduceJobs {
+  const float* partial[RP_MAX_JOBS];
+  float* out[RP_MAX_JOBS];
+  long count[RP_MAX_JOBS];
+  int nparts[RP_MAX_JOBS];
+};
+__global__ void __launch_bounds__(RP_COLS * RP_GROUPS) reduce_partials_batch_kernel(ReduceJobs jobs) {
+  __shared__ float red[RP_GROUPS][RP_COLS];
+  const int job = blockIdx.y;
+  const float* __restrict__ partial = jobs.partial[job];
+  float* __restrict__ out = jobs.out[job];
+  const long count = jobs.count[job];
+  const int nparts = jobs.nparts[job];
+  const int cl = threadIdx.x % RP_COLS, g = threadIdx.x / RP_COLS;
+  for (long c0 = (long)blockIdx.x * RP_COLS; c0 < count; c0 += (long)gridDim.x * RP_COLS) {
+    const long c = c0 + cl;
+    float acc[RP_ILP];
+#pragma unroll
+    for (int u = 0; u < RP_ILP; ++u) acc[u] = 0.f;
+    if (c < count) {
+      for (int p0 = g; p0 < nparts; p0 += RP_GROUPS * RP_ILP) {
+#pragma unroll
+        for (int u = 0; u < RP_ILP; ++u) {
+          const int p = p0 + u * RP_GROUPS;
+          if (p < nparts) acc[u] += partial[(long)p * count + c];
+        }
+      }
+    }
+    red[g][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (g == 0 && c < count) {
+      float s = red[0][cl];
+#pragma unroll
+      for (int k = 1; k < RP_GROUPS; ++k) s += red[k][cl];
+      out[c] = s;
+    }
+    __syncthreads();
+  }
+}
+
 int launch_reduce_partials(const float* partial, int nparts, long count, float* out0, long split, float* out1,
                            cudaStream_t stream) {
   long g = cdiv(count, RP_COLS);
@@ -173,6 +216,31 @@ int launch_reduce_partials(const float* partial, int nparts, long count, float* 
 }  // namespace cast
 
 using namespace cast;
+
+extern "C" int cast_reduce_partials_batch(int njobs, const float* const* partials, const int* nparts,
+                                          const long* counts, float* const* outs, void* stream) {
+  if (njobs < 0 || (njobs > 0 && (!partials || !nparts || !counts || !outs)))
+    return set_error(CAST_ERR_BAD_ARG, "reduce_partials_batch");
+  for (int j0 = 0; j0 < njobs; j0 += RP_MAX_JOBS) {
+    ReduceJobs jobs{};
+    const int n = njobs - j0 < RP_MAX_JOBS ? njobs - j0 : RP_MAX_JOBS;
+    long maxc = 1;
+    for (int j = 0; j < n; ++j) {
+      if (!partials[j0 + j] || !outs[j0 + j] || nparts[j0 + j] <= 0 || counts[j0 + j] <= 0)
+        return set_error(CAST_ERR_BAD_ARG, "reduce_partials_batch: job");
+      jobs.partial[j] = partials[j0 + j];
+      jobs.out[j] = outs[j0 + j];
+      jobs.count[j] = counts[j0 + j];
+      jobs.nparts[j] = nparts[j0 + j];
+      if (counts[j0 + j] > maxc) maxc = counts[j0 + j];
+    }
+    long g = cdiv(maxc, RP_COLS);
+    if (g > 2368) g = 2368;
+    CAST_LAUNCH(reduce_partials_batch_kernel, dim3((unsigned)g, (unsigned)n), dim3(RP_COLS * RP_GROUPS), 0,
+                (cudaStream_t)stream, jobs);
+  }
+  return check_launch("reduce_partials_batch");
+}
 
 extern "C" int cast_layernorm_fwd(const float* x, const float* gamma, const float* beta, long N, int H, float eps,
                                   float* y, float* mean, float* rstd, float* xnz, float* ynz, void* stream) {

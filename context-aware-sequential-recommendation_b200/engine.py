@@ -245,6 +245,11 @@ class Engine:
                     setattr(b, nm, f(N))
                 for nm in ("rmax", "rlinv", "rowD"):
                     setattr(b, nm, f(B * h * T))
+                if self.use_fused and bool(self.lib.cast_fused_supported(H)):
+                    # own partial buffers per block: the fixed-order reduction of all blocks is one launch at the end
+                    # of backward (cast_reduce_partials_batch) instead of one small launch per fused backward kernel
+                    nws = self.lib.cast_block_bwd_workspace_bytes(N, H) // 4 + 16
+                    b.ws_ffn, b.ws_qkv = f(nws), f(nws)
                 blocks.append(b)
             c.tw[tower] = SimpleNamespace(blocks=blocks, out=f(N, H), muf=f(N), rsf=f(N), dx_in=f(N, H), x_in=None)
         c.x0 = f(N, H)
@@ -419,8 +424,10 @@ class Engine:
                 self._call(self.lib.cast_ffn_bwd, dx.data_ptr(), ids.data_ptr(), b.zn.data_ptr(), b.h1d.data_ptr(),
                            b.y.data_ptr(), b.mu2.data_ptr(), b.rs2.data_ptr(), P[pre + "ln2.gamma"].data_ptr(),
                            P[pre + "ffn1.w"].data_ptr(), P[pre + "ffn2.w"].data_ptr(), rate, self.seed, self.step_ptr,
-                           block_site(tower, i, 3), c.N, H, dy.data_ptr(), self.G[pre + "ln2.beta"].data_ptr(),
-                           c.ws.data_ptr(), c.ws_bytes, self._stream())
+                           block_site(tower, i, 3), c.N, H, dy.data_ptr(), None,
+                           b.ws_ffn.data_ptr(), b.ws_ffn.numel() * 4, self._stream())
+                c.reduce_jobs.append((b.ws_ffn, self.lib.cast_block_bwd_parts(c.N, 0), 2 * H + 2 * (H * H + H),
+                                      self.G[pre + "ln2.beta"]))
                 dQ, dK, dV = t[1], t[2], t[3]
                 self._call(self.lib.cast_attn_bwd, b.Q.data_ptr(), H, b.K.data_ptr(), H, b.V.data_ptr(), H,
                            dy.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), b.rmax.data_ptr(),
@@ -432,8 +439,10 @@ class Engine:
                 self._call(self.lib.cast_qkv_bwd, dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), dy.data_ptr(),
                            x_i.data_ptr(), b.qn.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
                            P[pre + "ln1.gamma"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "k.w"].data_ptr(),
-                           P[pre + "v.w"].data_ptr(), c.N, H, dst.data_ptr(), self.G[pre + "ln1.beta"].data_ptr(),
-                           c.ws.data_ptr(), c.ws_bytes, self._stream())
+                           P[pre + "v.w"].data_ptr(), c.N, H, dst.data_ptr(), None,
+                           b.ws_qkv.data_ptr(), b.ws_qkv.numel() * 4, self._stream())
+                c.reduce_jobs.append((b.ws_qkv, self.lib.cast_block_bwd_parts(c.N, 1), 2 * H + 3 * (H * H + H),
+                                      self.G[pre + "ln1.beta"]))
                 dx = dst
                 continue
             # x_out = (dropout(h1d W2 + b2) + zn) * mask                      modules.py:304-311, sasrec.py:83
@@ -541,6 +550,7 @@ class Engine:
         plan = self.plan
         ids = c.keys3[0]
         d = c.dseq
+        c.reduce_jobs = []
         dstreams: Dict[str, torch.Tensor] = {}
         if plan.merge and plan.merge[3] == "post":
             ds = self.merge_bwd(c, d)
@@ -572,6 +582,21 @@ class Engine:
             if key in plan.towers:
                 dk = self.tower_bwd(c, key, dk, ids)
             self.scatter(c, c.cids[j], 1, [dk], [None], [sq], tname)
+        self.flush_reduce_jobs(c)
+
+    def flush_reduce_jobs(self, c):
+        """One fixed-order reduction launch for the per-CTA gradient partials of every fused backward kernel."""
+        jobs = c.reduce_jobs
+        if not jobs:
+            return
+        import ctypes as C
+        n = len(jobs)
+        parts = (C.c_void_p * n)(*[j[0].data_ptr() for j in jobs])
+        nparts = (C.c_int * n)(*[int(j[1]) for j in jobs])
+        counts = (C.c_long * n)(*[int(j[2]) for j in jobs])
+        outs = (C.c_void_p * n)(*[j[3].data_ptr() for j in jobs])
+        self._call(self.lib.cast_reduce_partials_batch, n, parts, nparts, counts, outs, self._stream())
+        c.reduce_jobs = []
 
     def adam(self, c):
         # gradients are divided by sums[2] = sum(istarget) (global under data parallelism) inside the kernel

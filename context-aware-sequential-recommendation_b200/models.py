@@ -29,6 +29,7 @@ class _Model:
         self.attention_weights = None
         self.launches_per_step = None
         self._pinned = {}
+        self._sums_host = None
 
     # ------------------------------------------------------------------ helpers
     def _stage(self, c, seq, pos, neg, time_seq, hours, days):
@@ -73,11 +74,17 @@ class _Model:
         s = torch.cuda.Stream(device=eng.device)
         s.wait_stream(torch.cuda.current_stream(eng.device))
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        single = eng.grad_allreduce is None and eng.after_adam is None  # one process: the whole step is one graph
         with torch.cuda.stream(s):
             with torch.cuda.graph(g1, stream=s):
                 eng.launch_fwd_bwd(c)
-            with torch.cuda.graph(g2, stream=s):
-                eng.adam(c)
+                if single:
+                    eng.adam(c)
+            if not single:
+                with torch.cuda.graph(g2, stream=s):
+                    eng.adam(c)
+            else:
+                g2 = None
         torch.cuda.current_stream(eng.device).wait_stream(s)
         eng.w.copy_(saved[0]); eng.m.copy_(saved[1]); eng.v.copy_(saved[2]); eng.adam_state.copy_(saved[3])
         c.graph = (g1, g2)
@@ -89,11 +96,12 @@ class _Model:
             if c.graph is None:
                 self._capture(c)
             c.graph[0].replay()
-            if eng.grad_allreduce is not None:
-                eng.grad_allreduce(c)
-            c.graph[1].replay()
-            if eng.after_adam is not None:
-                eng.after_adam()
+            if c.graph[1] is not None:
+                if eng.grad_allreduce is not None:
+                    eng.grad_allreduce(c)
+                c.graph[1].replay()
+                if eng.after_adam is not None:
+                    eng.after_adam()
         else:
             eng.launch_train_step(c)
 
@@ -111,7 +119,14 @@ class _Model:
     def train_step(self, u, seq, pos, neg, time_seq=None, hours=None, days=None):
         """== sess.run([model.auc, model.loss, model.train_op], feed) of reference main.py:212-219."""
         s = self.train_step_async(u, seq, pos, neg, time_seq, hours, days)
-        loss_sum, auc_sum, cnt = s[:3].tolist()
+        if s.device.type == "cuda":  # 12-byte read-back into pinned memory, one stream synchronisation
+            if self._sums_host is None:
+                self._sums_host = torch.zeros(4, dtype=torch.float32, pin_memory=True)
+            self._sums_host.copy_(s[:4], non_blocking=True)
+            torch.cuda.current_stream(s.device).synchronize()
+            loss_sum, auc_sum, cnt = self._sums_host[:3].tolist()
+        else:
+            loss_sum, auc_sum, cnt = s[:3].tolist()
         return auc_sum / cnt, loss_sum / cnt
 
     def forward_eval(self, seq, time_seq=None, hours=None, days=None, want_attn=False):

@@ -125,6 +125,14 @@ int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* beta, const
  * kernels; default 3; 0 = FP32 FFMA kernels. */
 int cast_fused_set_backend(int backend);
 size_t cast_block_bwd_workspace_bytes(long N, int H);
+/* cast_ffn_bwd / cast_qkv_bwd sum their per-CTA gradient partials (workspace layout [parts][count], count =
+ * 2H + 2(H*H+H) resp. 2H + 3(H*H+H)) into grads_out with a fixed-order reduction launch.  With grads_out == NULL the
+ * partials are left in the workspace: the caller folds the partials of all blocks of a step in one launch with
+ * cast_reduce_partials_batch (same fixed order, same bits).  cast_block_bwd_parts = number of partial blocks
+ * (which: 0 = ffn_bwd, 1 = qkv_bwd). */
+int cast_block_bwd_parts(long N, int which);
+int cast_reduce_partials_batch(int njobs, const float* const* partials, const int* nparts, const long* counts,
+                               float* const* outs, void* stream);
 int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, const float* h1d, const float* y, const float* mean,
                  const float* rstd, const float* gamma, const float* W1, const float* W2, float drop_rate,
                  unsigned long long seed, const unsigned long long* step, int site_out, long N, int H, float* dy,
