@@ -168,6 +168,7 @@ struct ReduceJobs {
   const float* partial[RP_MAX_JOBS];
   float* out[RP_MAX_JOBS];
   long count[RP_MAX_JOBS];
+  long pitch[RP_MAX_JOBS];  // distance between consecutive partial blocks (>= count)
   int nparts[RP_MAX_JOBS];
 };
 __global__ void __launch_bounds__(RP_COLS * RP_GROUPS) reduce_partials_batch_kernel(ReduceJobs jobs) {
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(RP_COLS * RP_GROUPS) reduce_partials_batch_ker
   const int job = blockIdx.y;
   const float* __restrict__ partial = jobs.partial[job];
   float* __restrict__ out = jobs.out[job];
-  const long count = jobs.count[job];
+  const long count = jobs.count[job], pitch = jobs.pitch[job];
   const int nparts = jobs.nparts[job];
   const int cl = threadIdx.x % RP_COLS, g = threadIdx.x / RP_COLS;
   for (long c0 = (long)blockIdx.x * RP_COLS; c0 < count; c0 += (long)gridDim.x * RP_COLS) {
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(RP_COLS * RP_GROUPS) reduce_partials_batch_ker
 #pragma unroll
         for (int u = 0; u < RP_ILP; ++u) {
           const int p = p0 + u * RP_GROUPS;
-          if (p < nparts) acc[u] += partial[(long)p * count + c];
+          if (p < nparts) acc[u] += partial[(long)p * pitch + c];
         }
       }
     }
@@ -218,7 +219,8 @@ int launch_reduce_partials(const float* partial, int nparts, long count, float* 
 using namespace cast;
 
 extern "C" int cast_reduce_partials_batch(int njobs, const float* const* partials, const int* nparts,
-                                          const long* counts, float* const* outs, void* stream) {
+                                          const long* counts, const long* pitches, float* const* outs,
+                                          void* stream) {
   if (njobs < 0 || (njobs > 0 && (!partials || !nparts || !counts || !outs)))
     return set_error(CAST_ERR_BAD_ARG, "reduce_partials_batch");
   for (int j0 = 0; j0 < njobs; j0 += RP_MAX_JOBS) {
@@ -231,6 +233,8 @@ extern "C" int cast_reduce_partials_batch(int njobs, const float* const* partial
       jobs.partial[j] = partials[j0 + j];
       jobs.out[j] = outs[j0 + j];
       jobs.count[j] = counts[j0 + j];
+      jobs.pitch[j] = pitches ? pitches[j0 + j] : counts[j0 + j];
+      if (jobs.pitch[j] < jobs.count[j]) return set_error(CAST_ERR_BAD_ARG, "reduce_partials_batch: pitch");
       jobs.nparts[j] = nparts[j0 + j];
       if (counts[j0 + j] > maxc) maxc = counts[j0 + j];
     }
@@ -259,6 +263,8 @@ extern "C" int cast_layernorm_fwd(const float* x, const float* gamma, const floa
   return check_launch("layernorm_fwd");
 }
 
+extern "C" int cast_layernorm_bwd_parts(long N) { return (int)cdiv(N, LN_ROWS_PER_CTA); }
+
 extern "C" size_t cast_layernorm_bwd_workspace_bytes(long N, int H) {
   return (size_t)cdiv(N, LN_ROWS_PER_CTA) * 2 * H * sizeof(float);
 }
@@ -266,7 +272,7 @@ extern "C" size_t cast_layernorm_bwd_workspace_bytes(long N, int H) {
 extern "C" int cast_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                   const float* gamma, long N, int H, const float* dx_add, float* dx, float* dgamma,
                                   float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || H <= 0 || H > 32 * LN_MAXV || N <= 0)
+  if (!dy || !x || !mean || !rstd || !gamma || !dx || (!dgamma != !dbeta) || H <= 0 || H > 32 * LN_MAXV || N <= 0)
     return set_error(CAST_ERR_BAD_ARG, "layernorm_bwd");
   if (!workspace || workspace_bytes < cast_layernorm_bwd_workspace_bytes(N, H))
     return set_error(CAST_ERR_WORKSPACE, "layernorm_bwd: workspace too small");
@@ -287,6 +293,6 @@ extern "C" int cast_layernorm_bwd(const float* dy, const float* x, const float* 
   else CAST_LN_BWD(32)
 #undef CAST_LN_BWD
   int rc = check_launch("layernorm_bwd");
-  if (rc) return rc;
+  if (rc || !dgamma) return rc;  // dgamma == dbeta == null: partials [parts][gamma H | beta H] stay in the workspace
   return launch_reduce_partials(partial, ncta, 2L * H, dgamma, H, dbeta, (cudaStream_t)stream);
 }

@@ -413,7 +413,18 @@ class Engine:
         x_last = tb.blocks[-1].xout if nb else tb.x_in
         fused = self.use_fused and bool(self.lib.cast_fused_supported(H))
         dx = t[0]
-        self.ln_bwd(c, d_out, x_last, tb.muf, tb.rsf, tower + ".lnf", dx)
+        if fused:  # gamma/beta partials of the tower's final LayerNorm join the step's single reduction launch
+            if getattr(tb, "ws_lnf", None) is None:
+                nb_ = self.lib.cast_layernorm_bwd_workspace_bytes(c.N, H)
+                tb.ws_lnf = torch.empty(nb_ // 4 + 16, dtype=torch.float32, device=self.device)
+            self._call(self.lib.cast_layernorm_bwd, d_out.data_ptr(), x_last.data_ptr(), tb.muf.data_ptr(),
+                       tb.rsf.data_ptr(), self.P[tower + ".lnf.gamma"].data_ptr(), c.N, H, None, dx.data_ptr(), None,
+                       None, tb.ws_lnf.data_ptr(), tb.ws_lnf.numel() * 4, self._stream())
+            parts = self.lib.cast_layernorm_bwd_parts(c.N)
+            c.reduce_jobs.append((tb.ws_lnf.data_ptr(), parts, H, self.G[tower + ".lnf.gamma"], 2 * H))
+            c.reduce_jobs.append((tb.ws_lnf.data_ptr() + 4 * H, parts, H, self.G[tower + ".lnf.beta"], 2 * H))
+        else:
+            self.ln_bwd(c, d_out, x_last, tb.muf, tb.rsf, tower + ".lnf", dx)
         for i in reversed(range(nb)):
             b = tb.blocks[i]
             pre = f"{tower}.{i}."
@@ -426,8 +437,9 @@ class Engine:
                            P[pre + "ffn1.w"].data_ptr(), P[pre + "ffn2.w"].data_ptr(), rate, self.seed, self.step_ptr,
                            block_site(tower, i, 3), c.N, H, dy.data_ptr(), None,
                            b.ws_ffn.data_ptr(), b.ws_ffn.numel() * 4, self._stream())
-                c.reduce_jobs.append((b.ws_ffn, self.lib.cast_block_bwd_parts(c.N, 0), 2 * H + 2 * (H * H + H),
-                                      self.G[pre + "ln2.beta"]))
+                cnt = 2 * H + 2 * (H * H + H)
+                c.reduce_jobs.append((b.ws_ffn.data_ptr(), self.lib.cast_block_bwd_parts(c.N, 0), cnt,
+                                      self.G[pre + "ln2.beta"], cnt))
                 dQ, dK, dV = t[1], t[2], t[3]
                 self._call(self.lib.cast_attn_bwd, b.Q.data_ptr(), H, b.K.data_ptr(), H, b.V.data_ptr(), H,
                            dy.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), b.rmax.data_ptr(),
@@ -441,8 +453,9 @@ class Engine:
                            P[pre + "ln1.gamma"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "k.w"].data_ptr(),
                            P[pre + "v.w"].data_ptr(), c.N, H, dst.data_ptr(), None,
                            b.ws_qkv.data_ptr(), b.ws_qkv.numel() * 4, self._stream())
-                c.reduce_jobs.append((b.ws_qkv, self.lib.cast_block_bwd_parts(c.N, 1), 2 * H + 3 * (H * H + H),
-                                      self.G[pre + "ln1.beta"]))
+                cnt = 2 * H + 3 * (H * H + H)
+                c.reduce_jobs.append((b.ws_qkv.data_ptr(), self.lib.cast_block_bwd_parts(c.N, 1), cnt,
+                                      self.G[pre + "ln1.beta"], cnt))
                 dx = dst
                 continue
             # x_out = (dropout(h1d W2 + b2) + zn) * mask                      modules.py:304-311, sasrec.py:83
@@ -571,8 +584,13 @@ class Engine:
         if add_time:
             dstreams["time"] = g0
         if plan.learned_pos:
-            self._call(self.lib.cast_colsum, g0.data_ptr(), c.B, self.T * self.H, self.T * self.H,
-                       self.G["pos_emb"].data_ptr(), c.ws.data_ptr(), c.ws_bytes, self._stream())
+            th = self.T * self.H
+            if self.use_fused and bool(self.lib.cast_fused_supported(self.H)):
+                # d(pos_emb) = sum over the batch of g0 [B, T*H]: another job of the step's reduction launch
+                c.reduce_jobs.append((g0.data_ptr(), c.B, th, self.G["pos_emb"], th))
+            else:
+                self._call(self.lib.cast_colsum, g0.data_ptr(), c.B, th, th, self.G["pos_emb"].data_ptr(),
+                           c.ws.data_ptr(), c.ws_bytes, self._stream())
         sq = float(self.H ** 0.5)
         self.scatter(c, c.keys3, 3, [g0, c.seq_emb, c.seq_emb], [None, c.gpos, c.gneg], [sq, 1.0, 1.0], "item_emb")
         for j, (tname, key) in enumerate((("time_emb", "time"), ("hours_emb", "hours"), ("days_emb", "days"))):
@@ -591,11 +609,12 @@ class Engine:
             return
         import ctypes as C
         n = len(jobs)
-        parts = (C.c_void_p * n)(*[j[0].data_ptr() for j in jobs])
+        parts = (C.c_void_p * n)(*[int(j[0]) for j in jobs])
         nparts = (C.c_int * n)(*[int(j[1]) for j in jobs])
         counts = (C.c_long * n)(*[int(j[2]) for j in jobs])
+        pitches = (C.c_long * n)(*[int(j[4]) for j in jobs])
         outs = (C.c_void_p * n)(*[j[3].data_ptr() for j in jobs])
-        self._call(self.lib.cast_reduce_partials_batch, n, parts, nparts, counts, outs, self._stream())
+        self._call(self.lib.cast_reduce_partials_batch, n, parts, nparts, counts, pitches, outs, self._stream())
         c.reduce_jobs = []
 
     def adam(self, c):

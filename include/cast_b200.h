@@ -131,8 +131,11 @@ size_t cast_block_bwd_workspace_bytes(long N, int H);
  * cast_reduce_partials_batch (same fixed order, same bits).  cast_block_bwd_parts = number of partial blocks
  * (which: 0 = ffn_bwd, 1 = qkv_bwd). */
 int cast_block_bwd_parts(long N, int which);
+ /* out_j[c] = sum_{p < nparts_j} partials_j[p * pitch_j + c], c < count_j (pitches == NULL: pitch = count). */
 int cast_reduce_partials_batch(int njobs, const float* const* partials, const int* nparts, const long* counts,
-                               float* const* outs, void* stream);
+                               const long* pitches, float* const* outs, void* stream);
+/* cast_layernorm_bwd with dgamma == dbeta == NULL leaves its partials [parts][gamma H | beta H] in the workspace. */
+int cast_layernorm_bwd_parts(long N);
 int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, const float* h1d, const float* y, const float* mean,
                  const float* rstd, const float* gamma, const float* W1, const float* W2, float drop_rate,
                  unsigned long long seed, const unsigned long long* step, int site_out, long N, int H, float* dy,
