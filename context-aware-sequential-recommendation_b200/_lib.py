@@ -45,6 +45,7 @@ SIGNATURES = {
     "cast_block_bwd_parts": (I, [L, I]),
     "cast_reduce_partials_batch": (I, [I, P, P, P, P, P, P]),
     "cast_layernorm_bwd_parts": (I, [L]),
+    "cast_logits_loss_parts": (I, [L]),
     "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P, P]),
     "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P, P, P]),
     "cast_logits_loss_workspace_bytes": (SZ, [L]),

@@ -86,6 +86,8 @@ __global__ void loss_final_kernel(const float* __restrict__ partial, int nparts,
 
 using namespace cast;
 
+extern "C" int cast_logits_loss_parts(long N) { return (int)cdiv(N, LOSS_ROWS_PER_CTA); }
+
 extern "C" size_t cast_logits_loss_workspace_bytes(long N) {
   return (size_t)cdiv(N, LOSS_ROWS_PER_CTA) * 3 * sizeof(float);
 }
@@ -93,7 +95,7 @@ extern "C" size_t cast_logits_loss_workspace_bytes(long N) {
 extern "C" int cast_logits_loss(const float* seq_emb, const float* table, int V, int H, long N, const int* pos,
                                 const int* neg, float* pos_logits, float* neg_logits, float* sums, float* dseq,
                                 float* gpos, float* gneg, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!seq_emb || !table || !pos || !neg || !sums || V <= 0 || H <= 0 || N <= 0)
+  if (!seq_emb || !table || !pos || !neg || V <= 0 || H <= 0 || N <= 0)
     return set_error(CAST_ERR_BAD_ARG, "logits_loss");
   if (!workspace || workspace_bytes < cast_logits_loss_workspace_bytes(N))
     return set_error(CAST_ERR_WORKSPACE, "logits_loss: workspace too small");
@@ -102,7 +104,7 @@ extern "C" int cast_logits_loss(const float* seq_emb, const float* table, int V,
   CAST_LAUNCH(logits_loss_kernel, dim3(ncta), dim3(32 * LOSS_WARPS), 0, (cudaStream_t)stream, seq_emb, table, V, H, N,
               pos, neg, pos_logits, neg_logits, dseq, gpos, gneg, partial);
   int rc = check_launch("logits_loss");
-  if (rc) return rc;
+  if (rc || !sums) return rc;  // sums == null: the [parts][3] partials stay in the workspace (cast_reduce_partials_batch)
   CAST_LAUNCH(loss_final_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, partial, ncta, sums);
   return check_launch("loss_final");
 }

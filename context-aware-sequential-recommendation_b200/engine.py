@@ -550,12 +550,19 @@ class Engine:
         c.seq_emb = x
         return x
 
-    def loss_fwd_bwd(self, c, with_grad=True):
+    def loss_fwd_bwd(self, c, with_grad=True, defer_sums=False):
+        ws, ws_bytes, sums = c.ws, c.ws_bytes, c.sums
+        if defer_sums:  # the three loss sums join the step's single reduction launch (end of backward)
+            if getattr(c, "ws_loss", None) is None:
+                c.ws_loss = torch.empty(self.lib.cast_logits_loss_workspace_bytes(c.N) // 4 + 16, dtype=torch.float32,
+                                        device=self.device)
+            ws, ws_bytes, sums = c.ws_loss, c.ws_loss.numel() * 4, None
+            c.reduce_jobs.append((c.ws_loss.data_ptr(), self.lib.cast_logits_loss_parts(c.N), 3, c.sums, 3))
         self._call(self.lib.cast_logits_loss, c.seq_emb.data_ptr(), self.P["item_emb"].data_ptr(),
                    self.P["item_emb"].shape[0], self.H, c.N, c.keys3[1].data_ptr(), c.keys3[2].data_ptr(),
-                   c.pos_logits.data_ptr(), c.neg_logits.data_ptr(), c.sums.data_ptr(),
+                   c.pos_logits.data_ptr(), c.neg_logits.data_ptr(), self._p(sums),
                    c.dseq.data_ptr() if with_grad else None, c.gpos.data_ptr() if with_grad else None,
-                   c.gneg.data_ptr() if with_grad else None, c.ws.data_ptr(), c.ws_bytes, self._stream())
+                   c.gneg.data_ptr() if with_grad else None, ws.data_ptr(), ws_bytes, self._stream())
 
     def backward(self, c):
         """Un-normalised gradients of sum(loss terms) into self.g (the 1/sum(istarget) factor — global under data
@@ -563,7 +570,8 @@ class Engine:
         plan = self.plan
         ids = c.keys3[0]
         d = c.dseq
-        c.reduce_jobs = []
+        if getattr(c, "reduce_jobs", None) is None:
+            c.reduce_jobs = []
         dstreams: Dict[str, torch.Tensor] = {}
         if plan.merge and plan.merge[3] == "post":
             ds = self.merge_bwd(c, d)
@@ -657,8 +665,9 @@ class Engine:
                 self._call(self.lib.cast_scatter_sort, c.keys3.data_ptr(), 3, c.N, V, c.sws.data_ptr(), c.sws_bytes,
                            c.side.cuda_stream)
             c.presorted = True
+        c.reduce_jobs = []
         self.forward(c, train=True)
-        self.loss_fwd_bwd(c, with_grad=True)
+        self.loss_fwd_bwd(c, with_grad=True, defer_sums=True)
         self.backward(c)
 
     def launch_train_step(self, c):

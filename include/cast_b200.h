@@ -180,6 +180,8 @@ size_t cast_logits_loss_workspace_bytes(long N);
 int cast_logits_loss(const float* seq_emb, const float* table, int V, int H, long N, const int* pos, const int* neg,
                      float* pos_logits, float* neg_logits, float* sums, float* dseq, float* gpos, float* gneg,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* sums == NULL leaves the per-CTA partials [parts][3] in the workspace (folded later by cast_reduce_partials_batch). */
+int cast_logits_loss_parts(long N);
 
 /* Deterministic sparse embedding gradient (TF autodiff of the gathers: unsorted_segment_sum):
  * dtable[r,:] = sum over entries e (in ascending e) with keys[e] == r of rows_s[n,:] * rowscale_s[n] * scale_s,
