@@ -47,7 +47,9 @@ SIGNATURES = {
     "cast_layernorm_bwd_parts": (I, [L]),
     "cast_logits_loss_parts": (I, [L]),
     "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P, P]),
-    "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P, P, P]),
+    "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P, P, P, SZ,
+                      P]),
+    "cast_attn_bwd_workspace_bytes": (SZ, [I, I, I]),
     "cast_logits_loss_workspace_bytes": (SZ, [L]),
     "cast_logits_loss": (I, [P, P, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),
     "cast_scatter_workspace_bytes": (SZ, [L, I, I]),

@@ -26,7 +26,7 @@ extern template int dispatch_att<256>(int, const AttnFwdArgs*, const AttnBwdArgs
 
 bool attn_mma_supported(const AttnDims& dm);
 int dispatch_att_mma(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, const float* out, const float* resid,
-                     const AttnDims& dm, cudaStream_t stream);
+                     float* pbuf, float* dbuf, const AttnDims& dm, cudaStream_t stream);
 
 int attn_mma_set_chunk(int nt);
 
@@ -47,6 +47,10 @@ static int dispatch_by_width(int which, const AttnFwdArgs* fa, const AttnBwdArgs
 
 using namespace cast;
 
+extern "C" size_t cast_attn_bwd_workspace_bytes(int B, int T, int h) {
+  return 2 * (size_t)B * h * T * T * sizeof(float);
+}
+
 extern "C" int cast_attn_set_chunk(int columns) { return attn_mma_set_chunk(columns / 8); }
 
 extern "C" int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv,
@@ -62,7 +66,7 @@ extern "C" int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk,
                    drop_rate, seed, step, site};
   // tensor-core path (attention_mma.cu) unless the [h*B,T,T] weights are wanted or the head is wider than 64
   int rc = (!attn_weights && attn_mma_supported(dm))
-               ? dispatch_att_mma(0, &args, nullptr, nullptr, nullptr, dm, (cudaStream_t)stream)
+               ? dispatch_att_mma(0, &args, nullptr, nullptr, nullptr, nullptr, nullptr, dm, (cudaStream_t)stream)
                : dispatch_by_width(0, &args, nullptr, dm, (cudaStream_t)stream);
   if (rc) return rc;
   return check_launch("attn_fwd");
@@ -74,7 +78,7 @@ extern "C" int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk,
                              float drop_rate, unsigned long long seed, const unsigned long long* step, int site,
                              float* dQ, long lddq,
                              float* dK, long lddk, float* dV, long lddv, const float* out, const float* queries,
-                             void* stream) {
+                             void* workspace, size_t workspace_bytes, void* stream) {
   if (!Q || !K || !V || !dO || !kmask || !qmask || !row_max || !row_linv || !rowD || !dQ || !dK || !dV || B <= 0 ||
       T <= 0 || H <= 0 || h <= 0 || H % h)
     return set_error(CAST_ERR_BAD_ARG, "attn_bwd");
@@ -83,11 +87,15 @@ extern "C" int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk,
                    lddv,
                    drop_rate, seed, step, site};
   const bool mma = out && queries && attn_mma_supported(dm);
-  int rc = mma ? dispatch_att_mma(1, nullptr, &args, out, queries, dm, (cudaStream_t)stream)
+  // with a [2][h*B,T,T] workspace the dQ kernel stores P~ and dS and the dK/dV kernel does not recompute them
+  const size_t half = (size_t)B * h * T * T * sizeof(float);
+  float* pbuf = (mma && workspace && workspace_bytes >= 2 * half) ? static_cast<float*>(workspace) : nullptr;
+  float* dbuf = pbuf ? pbuf + (size_t)B * h * T * T : nullptr;
+  int rc = mma ? dispatch_att_mma(1, nullptr, &args, out, queries, pbuf, dbuf, dm, (cudaStream_t)stream)
                : dispatch_by_width(1, nullptr, &args, dm, (cudaStream_t)stream);
   if (rc) return rc;
   if ((rc = check_launch("attn_bwd_dq"))) return rc;
-  rc = mma ? dispatch_att_mma(2, nullptr, &args, out, queries, dm, (cudaStream_t)stream)
+  rc = mma ? dispatch_att_mma(2, nullptr, &args, out, queries, pbuf, dbuf, dm, (cudaStream_t)stream)
            : dispatch_by_width(2, nullptr, &args, dm, (cudaStream_t)stream);
   if (rc) return rc;
   return check_launch("attn_bwd_dkv");

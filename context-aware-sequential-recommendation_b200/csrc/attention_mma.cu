@@ -380,9 +380,13 @@ struct AttnBwdMmaArgs {
   AttnBwdArgs b;
   const float* out;    // forward output (P~ V + queries) [B*T, H]
   const float* resid;  // queries = LN(x) [B*T, H]
+  float* pbuf;         // optional [h*B, T, T]: P~ (dropped, query-masked probabilities) written by the dQ kernel
+  float* dbuf;         // optional [h*B, T, T]: dS, so that the dK/dV kernel is two products and no recomputation
 };
 
-template <int KS, int NT, int KG>
+// ST: also store P~ and dS of every computed score to aa.pbuf / aa.dbuf (then fully-masked "uniform" rows, whose P~
+// reaches all T keys, are walked over the whole key range like in the forward pass)
+template <int KS, int NT, int KG, bool ST>
 __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 2) ? 2 : 1) attn_bwd_dq_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
@@ -413,14 +417,17 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
     return;
   }
   // only kept keys (first_key <= j <= i) carry dS; fully-masked (uniform) rows have dS == 0
-  const int kend = q0 + AM_T;
-  const int kbeg = (first_key / TC) * TC;
+  const int qlo = q0 > qstart ? q0 : qstart;
+  const bool uni = ST && qlo < first_key;
+  const int kend = uni ? T : q0 + AM_T;
+  const int kbeg = uni ? 0 : (first_key / TC) * TC;
   const int nch = kend > kbeg ? (kend - kbeg + TC - 1) / TC : 0;
   const int r0 = q0 + warp * 16;
   const int iA = r0 + g, iB = iA + 8;
   const int rlive = qstart > first_key ? qstart : first_key;  // rows below have zero dQ
-  const bool wact = r0 + 16 > rlive;
-  const int wkend = r0 + 16;
+  const bool wuni = ST && (r0 > qstart ? r0 : qstart) < first_key;
+  const bool wact = ST ? (r0 + 16 > qstart) : (r0 + 16 > rlive);
+  const int wkend = wuni ? T : r0 + 16;
 
   const float* Kg = a.K + rowbase * a.ldk + hh * d;
   const float* Vg = a.V + rowbase * a.ldv + hh * d;
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   const Drop dr = make_drop(a.rate, a.seed, a.step, a.site);
   const unsigned long long ibA = ((unsigned long long)((long)hh * dm.B + b) * T + (unsigned long long)(long)iA) * T;
   const unsigned long long ibB = ibA + 8ull * T;
-  const bool okA = iA >= rlive, okB = iB >= rlive;  // (rlive >= 0)
+  const bool okA = iA >= (ST ? qstart : rlive), okB = iB >= (ST ? qstart : rlive);  // (qstart, rlive >= 0)
   const float mxA = okA ? a.row_max[sbase + iA] : 0.f, mxB = okB ? a.row_max[sbase + iB] : 0.f;
   const float liA = okA ? a.row_linv[sbase + iA] : 0.f, liB = okB ? a.row_linv[sbase + iB] : 0.f;
   const float qmA = okA ? a.qmask[rowbase + iA] : 0.f, qmB = okB ? a.qmask[rowbase + iB] : 0.f;
@@ -500,9 +507,37 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
             const bool keep = ((c & 1) ? km.y : km.x) != 0.f && j <= i && i >= rlive;
             const float mx = (c < 2) ? mxA : mxB, li = (c < 2) ? liA : liB, qm = (c < 2) ? qmA : qmB;
             const float D = (c < 2) ? DA : DB;
-            const float p = __expf(s[nt][c] * dm.inv_sqrt_d - mx) * li;
-            const float dpt = dp[nt][c] * qm * dm0[c];
-            s[nt][c] = keep ? p * (dpt - D) * dm.inv_sqrt_d : 0.f;
+            const float mul = qm * dm0[c];
+            const float dpt = dp[nt][c] * mul;
+            if (ST) {
+              const bool okr = (c < 2) ? okA : okB;
+              const float sv = keep ? s[nt][c] * dm.inv_sqrt_d : CAST_NEG_FILL;
+              const float p = okr ? __expf(sv - mx) * li : 0.f;  // uniform rows: exp(fill - fill) / T
+              dp[nt][c] = p * mul;                                  // P~
+              s[nt][c] = keep ? p * (dpt - D) * dm.inv_sqrt_d : 0.f;
+            } else {
+              const float p = __expf(s[nt][c] * dm.inv_sqrt_d - mx) * li;
+              s[nt][c] = keep ? p * (dpt - D) * dm.inv_sqrt_d : 0.f;
+            }
+          }
+          if (ST) {
+            const int j = j0 + jl;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              if (!(hf ? okB : okA) || j >= T) continue;
+              const unsigned long long e = (hf ? ibB : ibA) + (unsigned long long)j;
+              if (((T | j) & 1) == 0) {
+                *reinterpret_cast<float2*>(aa.pbuf + e) = make_float2(dp[nt][2 * hf], dp[nt][2 * hf + 1]);
+                *reinterpret_cast<float2*>(aa.dbuf + e) = make_float2(s[nt][2 * hf], s[nt][2 * hf + 1]);
+              } else {
+                aa.pbuf[e] = dp[nt][2 * hf];
+                aa.dbuf[e] = s[nt][2 * hf];
+                if (j + 1 < T) {
+                  aa.pbuf[e + 1] = dp[nt][2 * hf + 1];
+                  aa.dbuf[e + 1] = s[nt][2 * hf + 1];
+                }
+              }
+            }
           }
         }
       }
@@ -722,6 +757,207 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward: dK, dV from
+// the P~ / dS the dQ kernel stored: dV += P~^T dO, dK += dS^T Q, nothing recomputed.  CTA = 64 keys, 8 warps: warp
+// (w & 3) owns 16 keys, (w >> 2) one 16-query half of each staged 32-query chunk; A^T fragments come straight from
+// the row-major [query][key] tiles (a0 = P~[q0+tig][k0+g]), masked to the entries the dQ kernel actually wrote.
+constexpr int AW_TQ = 32, AW_PS = 72, AW_THREADS = 256;
+
+template <int KS>
+__global__ void __launch_bounds__(AW_THREADS, 2) attn_bwd_dkv_ws_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  constexpr int DP = 8 * KS, NTO = KS, TQ = AW_TQ, PS = AW_PS, NW = AW_THREADS / 32;
+  const AttnBwdArgs& a = aa.b;
+  CAST_DYN_SMEM(float, sm);
+  __shared__ int s_first[2];
+  float* Pst = sm;                     // [2][TQ][PS]  P~ rows of the chunk's queries, columns = this tile's keys
+  float* Dst = Pst + 2 * TQ * PS;      // [2][TQ][PS]  dS
+  float* Qst = Dst + 2 * TQ * PS;      // [2][TQ][PS]  Q  (row stride PS: conflict-free [k][n] fragment loads)
+  float* dOst = Qst + 2 * TQ * PS;     // [2][TQ][PS]  dO
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, warp = wid & 3, qg = wid >> 2, g = lane >> 2, tig = lane & 3;
+  const int T = dm.T, d = dm.d;
+  int b, hh, ntile, tile;
+  am_block(dm, b, hh, ntile, tile);
+  const int k0 = am_row0(T, ntile, tile, AM_T);
+  const long rowbase = (long)b * T;
+  int first_key, qstart;
+  am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
+  const bool has_uniform = qstart < first_key;
+  if (k0 + AM_T <= first_key && !has_uniform) {
+    for (int idx = t; idx < AM_T * d; idx += AW_THREADS) {
+      const int j = k0 + idx / d, c = idx % d;
+      if (j >= 0) {
+        a.dK[(rowbase + j) * a.lddk + hh * d + c] = 0.f;
+        a.dV[(rowbase + j) * a.lddv + hh * d + c] = 0.f;
+      }
+    }
+    return;
+  }
+  const int nchunk = (T + TQ - 1) / TQ;
+  auto needed = [&](int cc) {
+    const int c0 = am_row0(T, nchunk, cc, TQ);
+    if (c0 + TQ <= qstart) return false;
+    const bool cuni = has_uniform && c0 < first_key;
+    return cuni || c0 + TQ > k0;
+  };
+  auto next_needed = [&](int cc) {
+    while (cc < nchunk && !needed(cc)) ++cc;
+    return cc;
+  };
+  const float* Qg = a.Q + rowbase * a.ldq + hh * d;
+  const float* dOg = a.dO + rowbase * dm.H + hh * d;
+  const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vo = am_vec2_ok(a.dO, dm.H, d, hh);
+  const unsigned long long hb = (unsigned long long)((long)hh * dm.B + b) * T;
+  const bool vp = ((T | k0) & 1) == 0 && (reinterpret_cast<uintptr_t>(aa.pbuf) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(aa.dbuf) & 7) == 0;
+  auto issue = [&](int cc, int st) {
+    const int c0 = am_row0(T, nchunk, cc, TQ);
+    am_load_rows_async<TQ, PS, NW>(Qst + st * TQ * PS, Qg, a.ldq, c0, T, d, vq);
+    am_load_rows_async<TQ, PS, NW>(dOst + st * TQ * PS, dOg, dm.H, c0, T, d, vo);
+    for (int r = wid; r < TQ; r += NW) {
+      const int i = c0 + r;
+      const bool okr = i >= 0;  // (i < T by construction)
+      const unsigned long long e = (hb + (unsigned long long)(okr ? i : 0)) * T;
+      float* pd = Pst + (st * TQ + r) * PS;
+      float* dd = Dst + (st * TQ + r) * PS;
+      if (vp) {
+        const int j = k0 + 2 * lane;
+        const bool ok = okr && j >= 0 && j < T;
+        const unsigned long long ej = e + (unsigned long long)(ok ? j : 0);
+        cp_async<8>(pd + 2 * lane, aa.pbuf + ej, ok);
+        cp_async<8>(dd + 2 * lane, aa.dbuf + ej, ok);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = k0 + lane + 32 * u;
+          const bool ok = okr && j >= 0 && j < T;
+          const unsigned long long ej = e + (unsigned long long)(ok ? j : 0);
+          cp_async<4>(pd + lane + 32 * u, aa.pbuf + ej, ok);
+          cp_async<4>(dd + lane + 32 * u, aa.dbuf + ej, ok);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  int cc = next_needed(0);
+  if (cc < nchunk) issue(cc, 0); else cp_async_commit();
+  am_zero_pad<DP, PS>(Qst, 4 * TQ, d);
+
+  const int r0 = k0 + warp * 16;
+  const int jA = r0 + g, jB = jA + 8;
+  const int qs0 = qstart > 0 ? qstart : 0;
+  float gk[NTO][4], gv[NTO][4];
+#pragma unroll
+  for (int no = 0; no < NTO; ++no)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) gk[no][c] = gv[no][c] = 0.f;
+  // entry (i, j) was written by the dQ kernel iff row i is computed and either uniform (all keys) or j is a kept-range key
+  auto valid = [&](int i, int j) { return i >= qs0 && j >= 0 && (i < first_key || (j <= i && j >= first_key)); };
+
+  for (int it = 0; cc < nchunk; ++it) {
+    const int st = it & 1;
+    const int c0 = am_row0(T, nchunk, cc, TQ);
+    const bool cuni = has_uniform && c0 < first_key;
+    const int cn = next_needed(cc + 1);
+    if (cn < nchunk) {
+      issue(cn, st ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int ql0 = qg * 16;  // this warp's 16 queries of the chunk
+    if (r0 + 16 > 0 && (cuni || c0 + ql0 + 16 > r0)) {
+      const float* Pc = Pst + st * TQ * PS + warp * 16 + g;
+      const float* Dc = Dst + st * TQ * PS + warp * 16 + g;
+      const float* Qc = Qst + st * TQ * PS + g;
+      const float* dOc = dOst + st * TQ * PS + g;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int ql = ql0 + ks * 8 + tig;
+        const int i0 = c0 + ql, i1 = i0 + 4;
+        const bool v00 = valid(i0, jA), v01 = valid(i0, jB), v10 = valid(i1, jA), v11 = valid(i1, jB);
+        unsigned ph[4], pl[4], dh[4], dl[4];
+        tf32_split(v00 ? Pc[ql * PS] : 0.f, ph[0], pl[0]);
+        tf32_split(v01 ? Pc[ql * PS + 8] : 0.f, ph[1], pl[1]);
+        tf32_split(v10 ? Pc[(ql + 4) * PS] : 0.f, ph[2], pl[2]);
+        tf32_split(v11 ? Pc[(ql + 4) * PS + 8] : 0.f, ph[3], pl[3]);
+        tf32_split(v00 ? Dc[ql * PS] : 0.f, dh[0], dl[0]);
+        tf32_split(v01 ? Dc[ql * PS + 8] : 0.f, dh[1], dl[1]);
+        tf32_split(v10 ? Dc[(ql + 4) * PS] : 0.f, dh[2], dl[2]);
+        tf32_split(v11 ? Dc[(ql + 4) * PS + 8] : 0.f, dh[3], dl[3]);
+        {
+          unsigned bh[NTO][2], bl[NTO][2];
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) {
+            tf32_split(dOc[ql * PS + no * 8], bh[no][0], bl[no][0]);
+            tf32_split(dOc[(ql + 4) * PS + no * 8], bh[no][1], bl[no][1]);
+          }
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) mma_tf32(gv[no], pl, bh[no][0], bh[no][1]);
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) mma_tf32(gv[no], ph, bl[no][0], bl[no][1]);
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) mma_tf32(gv[no], ph, bh[no][0], bh[no][1]);
+        }
+        {
+          unsigned bh[NTO][2], bl[NTO][2];
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) {
+            tf32_split(Qc[ql * PS + no * 8], bh[no][0], bl[no][0]);
+            tf32_split(Qc[(ql + 4) * PS + no * 8], bh[no][1], bl[no][1]);
+          }
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) mma_tf32(gk[no], dl, bh[no][0], bh[no][1]);
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) mma_tf32(gk[no], dh, bl[no][0], bl[no][1]);
+#pragma unroll
+          for (int no = 0; no < NTO; ++no) mma_tf32(gk[no], dh, bh[no][0], bh[no][1]);
+        }
+      }
+    }
+    __syncthreads();
+    cc = cn;
+  }
+  cp_async_wait<0>();
+  {  // dK, dV = sums of the two query halves
+    __syncthreads();
+    float* mk = Pst;  // [128 threads][4 * NTO]
+    float* mv = Dst;
+    const int slot = warp * 32 + lane;
+    if (qg == 1) {
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) {
+        *reinterpret_cast<float4*>(mk + (slot * NTO + no) * 4) = make_float4(gk[no][0], gk[no][1], gk[no][2], gk[no][3]);
+        *reinterpret_cast<float4*>(mv + (slot * NTO + no) * 4) = make_float4(gv[no][0], gv[no][1], gv[no][2], gv[no][3]);
+      }
+    }
+    __syncthreads();
+    if (qg == 1) return;
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) {
+      const float4 k1 = *reinterpret_cast<const float4*>(mk + (slot * NTO + no) * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(mv + (slot * NTO + no) * 4);
+      gk[no][0] += k1.x; gk[no][1] += k1.y; gk[no][2] += k1.z; gk[no][3] += k1.w;
+      gv[no][0] += v1.x; gv[no][1] += v1.y; gv[no][2] += v1.z; gv[no][3] += v1.w;
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int j = half ? jB : jA;
+    if (j < 0) continue;
+#pragma unroll
+    for (int no = 0; no < NTO; ++no)
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int c = no * 8 + 2 * tig + c2;
+        if (c < d) {
+          a.dK[(rowbase + j) * a.lddk + hh * d + c] = gk[no][half * 2 + c2];
+          a.dV[(rowbase + j) * a.lddv + hh * d + c] = gv[no][half * 2 + c2];
+        }
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ dispatch
 template <int KS, int NT>
 static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba, const AttnDims& dm,
@@ -745,13 +981,34 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
     constexpr int KGB = (NT == 4) ? 2 : 1;
     constexpr int TCB = TC * KGB;
     const size_t smem = (2 * AM_T + 4 * TCB) * row + sizeof(float) * (2 * TCB + AM_T);
-    auto kf = attn_bwd_dq_mma_kernel<KS, NT, KGB>;
+    if (ba->pbuf) {
+      static size_t cfgs = 48 * 1024;
+      auto kf = attn_bwd_dq_mma_kernel<KS, NT, KGB, true>;
+      if (smem > cfgs) {
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cfgs = smem;
+      }
+      CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
+      return CAST_OK;
+    }
+    auto kf = attn_bwd_dq_mma_kernel<KS, NT, KGB, false>;
     if (smem > cfg[1]) {
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg[1] = smem;
     }
     CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
   } else {
+    if (ba->pbuf) {
+      static size_t cfgw = 48 * 1024;
+      const size_t smemw = sizeof(float) * 8 * AW_TQ * AW_PS;
+      auto kw = attn_bwd_dkv_ws_kernel<KS>;
+      if (smemw > cfgw) {
+        cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
+        cfgw = smemw;
+      }
+      CAST_LAUNCH(kw, grid, dim3(AW_THREADS), smemw, stream, *ba, dm);
+      return CAST_OK;
+    }
     constexpr int KGB = (NT == 4) ? 2 : 1;
     constexpr int TCB = TC * KGB;
     const size_t smem = (2 * AM_T + 4 * TCB) * row + sizeof(float) * 8 * TCB;
@@ -776,9 +1033,9 @@ int attn_mma_set_chunk(int nt) {
 
 // which: 0 = forward (fa), 1 = backward dQ, 2 = backward dK/dV (ba + out/resid)
 int dispatch_att_mma(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, const float* out, const float* resid,
-                     const AttnDims& dm, cudaStream_t stream) {
+                     float* pbuf, float* dbuf, const AttnDims& dm, cudaStream_t stream) {
   AttnBwdMmaArgs bm{};
-  if (ba) { bm.b = *ba; bm.out = out; bm.resid = resid; }
+  if (ba) { bm.b = *ba; bm.out = out; bm.resid = resid; bm.pbuf = pbuf; bm.dbuf = dbuf; }
   const int ks = (dm.d + 7) / 8;
   if (g_chunk_tiles == 8) {
     switch (ks) {

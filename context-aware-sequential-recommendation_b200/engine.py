@@ -252,6 +252,10 @@ class Engine:
                     b.ws_ffn, b.ws_qkv = f(nws), f(nws)
                 blocks.append(b)
             c.tw[tower] = SimpleNamespace(blocks=blocks, out=f(N, H), muf=f(N), rsf=f(N), dx_in=f(N, H), x_in=None)
+        # attention backward scratch: P~ and dS of one block ([2][h*B,T,T]), shared by all blocks (d <= 64 only)
+        c.attn_ws = None
+        if H // h <= 64 and 2 * B * h * T * T * 4 <= (2 << 30):
+            c.attn_ws = torch.empty(self.lib.cast_attn_bwd_workspace_bytes(B, T, h) // 4, dtype=torch.float32, device=dev)
         c.x0 = f(N, H)
         c.emb = {t: f(N, H) for t in self.plan.tables if t != "item_emb"}
         c.demb = {t: f(N, H) for t in self.plan.tables if t != "item_emb"}
@@ -446,7 +450,8 @@ class Engine:
                            b.rlinv.data_ptr(), ids.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed,
                            self.step_ptr,
                            block_site(tower, i, 1), dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H,
-                           b.y.data_ptr(), b.qn.data_ptr(), self._stream())
+                           b.y.data_ptr(), b.qn.data_ptr(), self._p(c.attn_ws),
+                           c.attn_ws.numel() * 4 if c.attn_ws is not None else 0, self._stream())
                 dst = tb.dx_in if i == 0 else t[0]
                 self._call(self.lib.cast_qkv_bwd, dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), dy.data_ptr(),
                            x_i.data_ptr(), b.qn.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
@@ -472,7 +477,7 @@ class Engine:
                        ids.data_ptr(), b.rowD.data_ptr(), B, T, H, h, rate, self.seed, self.step_ptr,
                        block_site(tower, i, 1),
                        dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H, b.y.data_ptr(), b.qn.data_ptr(),
-                       self._stream())
+                       self._p(c.attn_ws), c.attn_ws.numel() * 4 if c.attn_ws is not None else 0, self._stream())
             self.linear_wgrad(c, b.qn, dQ, self.G[pre + "q.w"], self.G[pre + "q.b"])
             self.linear_wgrad(c, x_i, dK, self.G[pre + "k.w"], self.G[pre + "k.b"])
             self.linear_wgrad(c, x_i, dV, self.G[pre + "v.w"], self.G[pre + "v.b"])

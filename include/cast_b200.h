@@ -165,12 +165,16 @@ int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const floa
 int cast_attn_set_chunk(int columns);
 /* Gradient of the attention output (without the residual branch) w.r.t. Q, K, V.  rowD: scratch [B,h,T].
  * out / queries (optional, both or neither): the forward call's `out` and `queries`; with them (and d = H/h <= 64)
- * the tensor-core kernels run and D_i = sum_j P_ij dP_ij is taken as dO_i . (out_i - queries_i). */
+ * the tensor-core kernels run and D_i = sum_j P_ij dP_ij is taken as dO_i . (out_i - queries_i).
+ * workspace (optional, cast_attn_bwd_workspace_bytes = 2 * B*h*T*T floats): the dQ kernel stores P~ and dS there and
+ * the dK/dV kernel reads them back instead of recomputing the scores. */
+size_t cast_attn_bwd_workspace_bytes(int B, int T, int h);
 int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv, const float* dO,
                   const float* kmask, const float* qmask, const float* row_max, const float* row_linv,
                   const int* skip_ids, float* rowD, int B, int T, int H, int h, float drop_rate,
                   unsigned long long seed, const unsigned long long* step, int site, float* dQ, long lddq, float* dK,
-                  long lddk, float* dV, long lddv, const float* out, const float* queries, void* stream);
+                  long lddk, float* dV, long lddv, const float* out, const float* queries, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* models/sasrec.py:87-115: pos/neg row gathers from the zero-padded table, row dots, literal BCE
  * (-log(sigmoid+1e-24)), istarget mask, AUC.  sums[0..2] = {sum loss terms, sum auc terms, sum istarget}

@@ -98,11 +98,15 @@ def run_case(kind, B, T, H, h, rate, use_ids, path, seed=0):
                                None, rmax.data_ptr(), rlinv.data_ptr(), stream)
         assert rc == 0
     dQ, dK, dV = (torch.full((B, T, H), 9.0, dtype=torch.float32, device=dev) for _ in range(3))
-    mma = path == "mma"
+    mma = path in ("mma", "mma_ws")
+    ws = None
+    if path == "mma_ws":  # the dQ kernel stores P~ / dS, the dK/dV kernel reads them back (poisoned: NaNs must not leak)
+        ws = torch.full((lib.cast_attn_bwd_workspace_bytes(B, T, h) // 4,), float("nan"), dtype=torch.float32, device=dev)
     rc = lib.cast_attn_bwd(tQ.data_ptr(), H, tK.data_ptr(), H, tV.data_ptr(), H, tdO.data_ptr(), tkm.data_ptr(),
                            tqm.data_ptr(), rmax.data_ptr(), rlinv.data_ptr(), idp, rowD.data_ptr(), B, T, H, h, rate, sd,
                            step.data_ptr(), site, dQ.data_ptr(), H, dK.data_ptr(), H, dV.data_ptr(), H,
-                           out.data_ptr() if mma else None, tres.data_ptr() if mma else None, stream)
+                           out.data_ptr() if mma else None, tres.data_ptr() if mma else None,
+                           None if ws is None else ws.data_ptr(), 0 if ws is None else ws.numel() * 4, stream)
     assert rc == 0, lib.cast_last_error_string()
     ref = ref_attention(Q, K, V, resid, kmask, qmask, ids if use_ids else None,
                         keep.cpu().numpy().reshape(h * B, T, T), rate, h, dO)
@@ -113,8 +117,8 @@ def run_case(kind, B, T, H, h, rate, use_ids, path, seed=0):
         assert err <= TOL, (name, err)
 
 
-EMU = [(3, 9, 16, 2, 0.25, True, "mma"), (3, 9, 16, 2, 0.25, False, "mma"), (2, 70, 12, 1, 0.0, True, "mma"),
-       (3, 67, 6, 1, 0.3, False, "mma"), (3, 9, 16, 2, 0.25, False, "ffma")]
+EMU = [(3, 9, 16, 2, 0.25, True, "mma"), (3, 9, 16, 2, 0.25, False, "mma_ws"), (2, 70, 12, 1, 0.0, True, "mma_ws"),
+       (3, 67, 6, 1, 0.3, False, "mma_ws"), (3, 67, 6, 1, 0.3, False, "mma"), (3, 9, 16, 2, 0.25, False, "ffma")]
 
 
 @pytest.mark.emu
@@ -126,7 +130,11 @@ def test_attention_emulated(B, T, H, h, rate, use_ids, path):
 GPU = [(8, 200, 50, 1, 0.2, True, "mma"), (8, 200, 50, 1, 0.2, False, "mma"), (5, 200, 50, 2, 0.2, True, "mma"),
        (4, 50, 128, 4, 0.2, True, "mma"), (4, 50, 64, 1, 0.0, False, "mma"), (3, 37, 50, 2, 0.5, True, "mma"),
        (3, 129, 24, 3, 0.1, False, "mma"), (4, 64, 8, 1, 0.0, True, "mma"), (3, 300, 40, 1, 0.2, False, "mma"),
-       (8, 200, 50, 1, 0.2, True, "ffma"), (4, 200, 50, 2, 0.2, False, "ffma"), (3, 50, 256, 1, 0.2, True, "mma")]
+       (8, 200, 50, 1, 0.2, True, "ffma"), (4, 200, 50, 2, 0.2, False, "ffma"), (3, 50, 256, 1, 0.2, True, "mma"),
+       (8, 200, 50, 1, 0.2, True, "mma_ws"), (8, 200, 50, 1, 0.2, False, "mma_ws"), (5, 200, 50, 2, 0.2, True, "mma_ws"),
+       (4, 50, 128, 4, 0.2, True, "mma_ws"), (4, 50, 64, 1, 0.0, False, "mma_ws"), (3, 37, 50, 2, 0.5, True, "mma_ws"),
+       (3, 129, 24, 3, 0.1, False, "mma_ws"), (4, 64, 8, 1, 0.0, True, "mma_ws"), (3, 300, 40, 1, 0.2, False, "mma_ws"),
+       (3, 53, 25, 1, 0.2, False, "mma_ws"), (3, 50, 256, 1, 0.2, True, "mma_ws")]
 
 
 @pytest.mark.gpu
