@@ -56,7 +56,7 @@ SIGNATURES = {
     "cast_scatter_partial_bytes": (SZ, [L, I, I]),
     "cast_scatter_rows": (I, [P, I, L, P, P, P, I, I, P, P, SZ, P, SZ, P]),
     "cast_scatter_sort": (I, [P, I, L, I, P, SZ, P]),
-    "cast_scatter_apply": (I, [I, L, P, P, P, I, I, P, P, SZ, P, SZ, P]),
+    "cast_scatter_apply": (I, [I, L, P, P, P, I, I, P, P, SZ, P, SZ, I, P]),
     "cast_adam_init_state": (I, [P, F, F, P]),
     "cast_adam_tf_step": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, P]),
     "cast_adam_tf_range": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, I, P]),

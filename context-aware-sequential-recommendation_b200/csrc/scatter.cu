@@ -118,7 +118,7 @@ constexpr int SEG_CHUNK = 64;  // sorted entries walked by one warp (two per lan
 template <int NV>
 __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay,
                                        long total, long N, ScatterSrc src, int V, int H, float* __restrict__ dtable,
-                                       float* __restrict__ part, int* __restrict__ pkey) {
+                                       float* __restrict__ part, int* __restrict__ pkey, int accumulate) {
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long beg = w * SEG_CHUNK;
@@ -191,7 +191,7 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
-            if (c < H) dtable[(long)cur * H + c] = acc[i];
+            if (c < H) dtable[(long)cur * H + c] = accumulate ? dtable[(long)cur * H + c] + acc[i] : acc[i];
           }
         }
 #pragma unroll
@@ -222,7 +222,7 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
-      if (c < H) dtable[(long)cur * H + c] = acc[i];
+      if (c < H) dtable[(long)cur * H + c] = accumulate ? dtable[(long)cur * H + c] + acc[i] : acc[i];
     }
   }
   if (lane == 0) {
@@ -236,7 +236,7 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
 // chunk order) folded in a fixed order at the end => still a fixed summation tree, with ST_U loads in flight.
 template <int NV>
 __global__ void segment_stitch_kernel(const float* __restrict__ part, const int* __restrict__ pkey, long nchunks,
-                                      int V, int H, float* __restrict__ dtable) {
+                                      int V, int H, float* __restrict__ dtable, int accumulate) {
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nchunks) return;
@@ -278,7 +278,7 @@ __global__ void segment_stitch_kernel(const float* __restrict__ part, const int*
       float s = part[(w * 2 + 1) * H + c];
 #pragma unroll
       for (int u = 0; u < ST_U; ++u) s += acc[u][i];
-      dtable[(long)key * H + c] = s;
+      dtable[(long)key * H + c] = accumulate ? dtable[(long)key * H + c] + s : s;
     }
   }
 }
@@ -348,7 +348,8 @@ extern "C" int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void*
 // Reduce half: fixed-order segment sums of the rows over the arrays cast_scatter_sort left in the workspace.
 extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, const float* const* rowscale,
                                   const float* scale, int V, int H, float* dtable, void* workspace,
-                                  size_t workspace_bytes, void* partial, size_t partial_bytes, void* stream) {
+                                  size_t workspace_bytes, void* partial, size_t partial_bytes, int accumulate,
+                                  void* stream) {
   if (!rows || !scale || !dtable || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0 || H <= 0 || H > 1024)
     return set_error(CAST_ERR_BAD_ARG, "scatter_apply");
   const long total = N * nsrc;
@@ -373,7 +374,9 @@ extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, co
     src.scale[s] = s < nsrc ? scale[s] : 0.f;
   }
   // rows nobody touches (and row 0) must read as zero: dense-gradient semantics of the reference
-  cudaMemsetAsync(dtable, 0, (size_t)V * H * sizeof(float), st);
+  // (accumulate: dtable already holds the sum of an earlier call over other sources; every row is written at most
+  // once per call, so adding to it is race-free and keeps a fixed summation order)
+  if (!accumulate) cudaMemsetAsync(dtable, 0, (size_t)V * H * sizeof(float), st);
   const long nseg = cdiv(total, SEG_CHUNK);
   int* pkey = reinterpret_cast<int*>(hist + 256L * nchunks);
   float* part = static_cast<float*>(partial);
@@ -382,10 +385,10 @@ extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, co
 #define CAST_SEG(NV)                                                                                            \
   {                                                                                                             \
     CAST_LAUNCH(segment_partial_kernel<NV>, grid, block, 0, st, kin, pin, total, N, src, V, H, dtable, part,    \
-                pkey);                                                                                          \
+                pkey, accumulate);                                                                              \
     if ((rc = check_launch("segment_partial"))) return rc;                                                      \
     CAST_LAUNCH(segment_stitch_kernel<NV>, grid, block, 0, st, (const float*)part, (const int*)pkey, nseg, V, H, \
-                dtable);                                                                                        \
+                dtable, accumulate);                                                                            \
   }
   if (H <= 64) CAST_SEG(2)
   else if (H <= 128) CAST_SEG(4)
@@ -403,5 +406,5 @@ extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float*
   int rc = cast_scatter_sort(keys, nsrc, N, V, workspace, workspace_bytes, stream);
   if (rc) return rc;
   return cast_scatter_apply(nsrc, N, rows, rowscale, scale, V, H, dtable, workspace, workspace_bytes, partial,
-                            partial_bytes, stream);
+                            partial_bytes, 0, stream);
 }

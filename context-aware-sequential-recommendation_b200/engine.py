@@ -349,7 +349,7 @@ class Engine:
             c.presorted = False
             self._call(self.lib.cast_scatter_apply, nsrc, N, rows_a, rs_a, sc_a, V, self.H,
                        self.G[table_name].data_ptr(), c.sws.data_ptr(), c.sws_bytes, c.spart.data_ptr(),
-                       c.spart_bytes, self._stream())
+                       c.spart_bytes, 0, self._stream())
             return
         self._call(self.lib.cast_scatter_rows, keys.data_ptr(), nsrc, N, rows_a, rs_a, sc_a, V, self.H,
                    self.G[table_name].data_ptr(), c.sws.data_ptr(), c.sws_bytes, c.spart.data_ptr(), c.spart_bytes,

@@ -200,7 +200,11 @@ size_t cast_scatter_partial_bytes(long N, int nsrc, int H);       /* float scrat
 int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void* workspace, size_t workspace_bytes, void* stream);
 int cast_scatter_apply(int nsrc, long N, const float* const* rows, const float* const* rowscale, const float* scale,
                        int V, int H, float* dtable, void* workspace, size_t workspace_bytes, void* partial,
-                       size_t partial_bytes, void* stream);
+                       size_t partial_bytes, int accumulate, void* stream);
+/* accumulate != 0: dtable is not cleared and every touched row is added to (the sum over other sources left there by an
+ * earlier cast_scatter_apply).  Measured at C2: running the pos/neg part on a side stream during backward and only the
+ * input-embedding part at the end was slower (0.698 vs 0.666 ms/step: the side kernels take SMs from the persistent
+ * backward kernels), so the engine keeps one apply over all three sources. */
 int cast_scatter_rows(const int* keys /* [nsrc*N] */, int nsrc, long N, const float* const* rows,
                       const float* const* rowscale, const float* scale, int V, int H, float* dtable,
                       void* workspace, size_t workspace_bytes, void* partial, size_t partial_bytes, void* stream);
