@@ -46,6 +46,9 @@ SIGNATURES = {
     "cast_reduce_partials_batch": (I, [I, P, P, P, P, P, P]),
     "cast_layernorm_bwd_parts": (I, [L]),
     "cast_logits_loss_parts": (I, [L]),
+    "cast_lnf_loss_parts": (I, [L]),
+    "cast_lnf_loss_workspace_bytes": (SZ, [L, I]),
+    "cast_lnf_loss": (I, [P, P, P, F, P, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),
     "cast_attn_fwd": (I, [P, L, P, L, P, L, P, P, P, I, I, I, I, F, U64, P, I, P, P, P, P, P, P]),
     "cast_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, P, P, P, P, I, I, I, I, F, U64, P, I, P, L, P, L, P, L, P, P, P, SZ,
                       P]),

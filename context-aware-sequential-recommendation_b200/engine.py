@@ -403,6 +403,9 @@ class Engine:
                 self.linear_fwd(c, b.h1d, self.P[pre + "ffn2.w"], self.P[pre + "ffn2.b"], b.xout, rate=rate,
                                 site=block_site(tower, i, 3), resid=b.zn, ldr=H, row_ids=ids)
             x = b.xout
+        if tower == "main" and train and getattr(c, "fuse_tail", False):
+            tb.x_last = x       # cast_lnf_loss normalises it (and writes tb.out) together with the loss
+            return tb.out
         self.ln_fwd(x, tower + ".lnf", tb.out, tb.muf, tb.rsf)
         return tb.out
 
@@ -417,7 +420,9 @@ class Engine:
         x_last = tb.blocks[-1].xout if nb else tb.x_in
         fused = self.use_fused and bool(self.lib.cast_fused_supported(H))
         dx = t[0]
-        if fused:  # gamma/beta partials of the tower's final LayerNorm join the step's single reduction launch
+        if tower == "main" and getattr(c, "fuse_tail", False):
+            pass                # dx (= t[0]) and the gamma/beta partials were produced by cast_lnf_loss
+        elif fused:  # gamma/beta partials of the tower's final LayerNorm join the step's single reduction launch
             if getattr(tb, "ws_lnf", None) is None:
                 nb_ = self.lib.cast_layernorm_bwd_workspace_bytes(c.N, H)
                 tb.ws_lnf = torch.empty(nb_ // 4 + 16, dtype=torch.float32, device=self.device)
@@ -555,6 +560,29 @@ class Engine:
         c.seq_emb = x
         return x
 
+    def tail_fusable(self):
+        """final LayerNorm + loss + LayerNorm backward in one launch: the main tower's output must be seq_emb itself"""
+        plan = self.plan
+        return (self.use_fused and bool(self.lib.cast_fused_supported(self.H))
+                and not (plan.merge and plan.merge[3] == "post"))
+
+    def loss_tail_fused(self, c):
+        tb = c.tw["main"]
+        H, N = self.H, c.N
+        if getattr(c, "ws_tail", None) is None:
+            c.ws_tail = torch.empty(self.lib.cast_lnf_loss_workspace_bytes(N, H) // 4 + 16, dtype=torch.float32,
+                                    device=self.device)
+        parts = self.lib.cast_lnf_loss_parts(N)
+        self._call(self.lib.cast_lnf_loss, tb.x_last.data_ptr(), self.P["main.lnf.gamma"].data_ptr(),
+                   self.P["main.lnf.beta"].data_ptr(), 1e-8, self.P["item_emb"].data_ptr(),
+                   self.P["item_emb"].shape[0], H, N, c.keys3[1].data_ptr(), c.keys3[2].data_ptr(), tb.out.data_ptr(),
+                   c.pos_logits.data_ptr(), c.neg_logits.data_ptr(), c.gpos.data_ptr(), c.gneg.data_ptr(),
+                   c.t[0].data_ptr(), c.ws_tail.data_ptr(), c.ws_tail.numel() * 4, self._stream())
+        base = c.ws_tail.data_ptr()
+        c.reduce_jobs.append((base, parts, 3, c.sums, 3))
+        c.reduce_jobs.append((base + 4 * 3 * parts, parts, H, self.G["main.lnf.gamma"], 2 * H))
+        c.reduce_jobs.append((base + 4 * (3 * parts + H), parts, H, self.G["main.lnf.beta"], 2 * H))
+
     def loss_fwd_bwd(self, c, with_grad=True, defer_sums=False):
         ws, ws_bytes, sums = c.ws, c.ws_bytes, c.sums
         if defer_sums:  # the three loss sums join the step's single reduction launch (end of backward)
@@ -671,9 +699,14 @@ class Engine:
                            c.side.cuda_stream)
             c.presorted = True
         c.reduce_jobs = []
+        c.fuse_tail = self.tail_fusable()
         self.forward(c, train=True)
-        self.loss_fwd_bwd(c, with_grad=True, defer_sums=True)
+        if c.fuse_tail:
+            self.loss_tail_fused(c)
+        else:
+            self.loss_fwd_bwd(c, with_grad=True, defer_sums=True)
         self.backward(c)
+        c.fuse_tail = False
 
     def launch_train_step(self, c):
         """Enqueue one full training step (forward, loss, backward, [all-reduce], Adam) on the current stream."""

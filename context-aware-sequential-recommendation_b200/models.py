@@ -43,12 +43,16 @@ class _Model:
             st = (torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin),
                   torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin))
             self._pinned[key] = st
-        k3, c3 = st
+        k3, c3 = st[0], st[1]
+        if len(st) == 2:  # numpy views of the pinned staging buffers: np.copyto has far less overhead than Tensor.copy_
+            st = (k3, c3, k3.numpy(), c3.numpy())
+            self._pinned[key] = st
+        k3n, c3n = st[2], st[3]
         for j, a in enumerate((seq, pos, neg)):
             if a is not None:
-                k3[j].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.int32).reshape(-1)))
+                np.copyto(k3n[j], np.asarray(a).reshape(-1), casting="unsafe")
             else:
-                k3[j].zero_()
+                k3n[j].fill(0)
         c.keys3.copy_(k3, non_blocking=True)
         tables = eng.plan.tables
         need = [("time_emb", time_seq), ("hours_emb", hours), ("days_emb", days)]
@@ -57,7 +61,7 @@ class _Model:
                 if t in tables:
                     if a is None:
                         raise ValueError(f"model {self.registry_name} needs the {t[:-4]} sequence")
-                    c3[j].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.int32).reshape(-1)))
+                    np.copyto(c3n[j], np.asarray(a).reshape(-1), casting="unsafe")
             c.cids.copy_(c3, non_blocking=True)
 
     def _capture(self, c):

@@ -40,6 +40,8 @@ def _work(name, a, B, T, H, h):
         return 12.0 * a[4], 28.0 * a[4]
     if name == "cast_logits_loss":
         return 6.0 * a[4] * a[3], 4.0 * 4 * a[4] * a[3]
+    if name == "cast_lnf_loss":     # LN + 2 gathers + dots + LN backward: x, 2 table rows in; seq_emb, dx out (a[6]=H, a[7]=N)
+        return 30.0 * a[7] * a[6], 4.0 * 5 * a[7] * a[6]
     if name == "cast_scatter_rows":
         n, nsrc, Hh, V = a[2], a[1], a[7], a[6]
         return 2.0 * n * nsrc * Hh, 4.0 * (n * nsrc * Hh + V * Hh) + 16.0 * n * nsrc

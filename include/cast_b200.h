@@ -186,6 +186,15 @@ int cast_logits_loss(const float* seq_emb, const float* table, int V, int H, lon
                      void* workspace, size_t workspace_bytes, void* stream);
 /* sums == NULL leaves the per-CTA partials [parts][3] in the workspace (folded later by cast_reduce_partials_batch). */
 int cast_logits_loss_parts(long N);
+/* Training tail in one launch (H <= 64): seq_emb = LayerNorm(x) (modules.py:53-80, the main tower's final normalize),
+ * the logits / loss / AUC terms of cast_logits_loss on it, and dx = d(sum loss)/dx through that LayerNorm.
+ * Workspace: [parts][3] loss partials followed by [parts][gamma H | beta H] LayerNorm-parameter partials, both left
+ * for cast_reduce_partials_batch. */
+int cast_lnf_loss_parts(long N);
+size_t cast_lnf_loss_workspace_bytes(long N, int H);
+int cast_lnf_loss(const float* x, const float* gamma, const float* beta, float eps, const float* table, int V, int H,
+                  long N, const int* pos, const int* neg, float* seq_emb, float* pos_logits, float* neg_logits,
+                  float* gpos, float* gneg, float* dx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Deterministic sparse embedding gradient (TF autodiff of the gathers: unsorted_segment_sum):
  * dtable[r,:] = sum over entries e (in ascending e) with keys[e] == r of rows_s[n,:] * rowscale_s[n] * scale_s,
