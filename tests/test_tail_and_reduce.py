@@ -1,0 +1,129 @@
+"""ABI-level checks of the two step-level fusions:
+
+* `cast_reduce_partials_batch` -- several fixed-order partial reductions in one launch (per-CTA gradient partials of
+  the fused backward kernels, LayerNorm gamma/beta partials with a pitch, batch column sums) against numpy float64;
+* `cast_lnf_loss` -- final LayerNorm (modules.py:53-80) + logits / BCE / AUC (models/sasrec.py:87-115) + LayerNorm
+  backward in one launch against the separate `cast_layernorm_fwd` -> `cast_logits_loss` -> `cast_layernorm_bwd` calls
+  it replaces (same library, same inputs) and against the oracle's loss.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, backend
+
+
+def _stream(kind, dev):
+    return torch.cuda.current_stream(dev).cuda_stream if kind == "gpu" else None
+
+
+def run_reduce(kind):
+    lib, dev = backend(kind)
+    rng = np.random.RandomState(0)
+    jobs = [(37, 1000, 1000), (148, 7700, 7700), (5, 3, 3), (64, 50, 100), (128, 10000, 10000)]  # parts, count, pitch
+    bufs, outs, refs = [], [], []
+    for parts, count, pitch in jobs:
+        a = rng.randn(parts, pitch).astype(np.float32)
+        bufs.append(torch.from_numpy(a).to(dev))
+        outs.append(torch.full((count,), 7.0, dtype=torch.float32, device=dev))
+        refs.append(a[:, :count].astype(np.float64).sum(0))
+    n = len(jobs)
+    rc = lib.cast_reduce_partials_batch(
+        n, (C.c_void_p * n)(*[b.data_ptr() for b in bufs]), (C.c_int * n)(*[j[0] for j in jobs]),
+        (C.c_long * n)(*[j[1] for j in jobs]), (C.c_long * n)(*[j[2] for j in jobs]),
+        (C.c_void_p * n)(*[o.data_ptr() for o in outs]), _stream(kind, dev))
+    assert rc == 0, lib.cast_last_error_string()
+    for o, r in zip(outs, refs):
+        got = o.cpu().numpy().astype(np.float64)
+        assert np.abs(got - r).max() <= 2e-5 * max(np.abs(r).max(), 1.0)
+    # run-to-run bit stability (fixed summation order)
+    first = [o.clone() for o in outs]
+    rc = lib.cast_reduce_partials_batch(
+        n, (C.c_void_p * n)(*[b.data_ptr() for b in bufs]), (C.c_int * n)(*[j[0] for j in jobs]),
+        (C.c_long * n)(*[j[1] for j in jobs]), (C.c_long * n)(*[j[2] for j in jobs]),
+        (C.c_void_p * n)(*[o.data_ptr() for o in outs]), _stream(kind, dev))
+    assert rc == 0
+    assert all(torch.equal(a, b) for a, b in zip(first, outs))
+
+
+def run_tail(kind, N, H, V):
+    lib, dev = backend(kind)
+    st = _stream(kind, dev)
+    rng = np.random.RandomState(N + H)
+    x = torch.from_numpy(rng.randn(N, H).astype(np.float32)).to(dev)
+    gamma = torch.from_numpy((1 + 0.1 * rng.randn(H)).astype(np.float32)).to(dev)
+    beta = torch.from_numpy((0.1 * rng.randn(H)).astype(np.float32)).to(dev)
+    table = torch.from_numpy((0.3 * rng.randn(V, H)).astype(np.float32)).to(dev)
+    table[0] = 0
+    pos_np = rng.randint(0, V, N).astype(np.int32)
+    pos_np[:: 7] = 0                                   # padding positions: not targets
+    neg_np = np.where(pos_np > 0, rng.randint(1, V, N), 0).astype(np.int32)
+    pos, neg = torch.from_numpy(pos_np).to(dev), torch.from_numpy(neg_np).to(dev)
+    f = lambda *s: torch.full(s, 3.0, dtype=torch.float32, device=dev)  # noqa: E731
+    # ---- separate kernels
+    y, mu, rs = f(N, H), f(N), f(N)
+    assert lib.cast_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, H, 1e-8, y.data_ptr(),
+                                  mu.data_ptr(), rs.data_ptr(), None, None, st) == 0
+    ws = torch.empty(max(lib.cast_logits_loss_workspace_bytes(N), lib.cast_layernorm_bwd_workspace_bytes(N, H)) // 4 + 16,
+                     dtype=torch.float32, device=dev)
+    pl, nl, sums, dseq, gp, gn = f(N), f(N), f(4), f(N, H), f(N), f(N)
+    assert lib.cast_logits_loss(y.data_ptr(), table.data_ptr(), V, H, N, pos.data_ptr(), neg.data_ptr(), pl.data_ptr(),
+                                nl.data_ptr(), sums.data_ptr(), dseq.data_ptr(), gp.data_ptr(), gn.data_ptr(),
+                                ws.data_ptr(), ws.numel() * 4, st) == 0
+    dx, dgam, dbet = f(N, H), f(H), f(H)
+    assert lib.cast_layernorm_bwd(dseq.data_ptr(), x.data_ptr(), mu.data_ptr(), rs.data_ptr(), gamma.data_ptr(), N, H,
+                                  None, dx.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                  st) == 0
+    # ---- fused tail
+    y2, pl2, nl2, gp2, gn2, dx2 = f(N, H), f(N), f(N), f(N), f(N), f(N, H)
+    wt = torch.empty(lib.cast_lnf_loss_workspace_bytes(N, H) // 4 + 16, dtype=torch.float32, device=dev)
+    rc = lib.cast_lnf_loss(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-8, table.data_ptr(), V, H, N,
+                           pos.data_ptr(), neg.data_ptr(), y2.data_ptr(), pl2.data_ptr(), nl2.data_ptr(), gp2.data_ptr(),
+                           gn2.data_ptr(), dx2.data_ptr(), wt.data_ptr(), wt.numel() * 4, st)
+    assert rc == 0, lib.cast_last_error_string()
+    parts = lib.cast_lnf_loss_parts(N)
+    sums2, dgam2, dbet2 = f(3), f(H), f(H)
+    base = wt.data_ptr()
+    rc = lib.cast_reduce_partials_batch(
+        3, (C.c_void_p * 3)(base, base + 4 * 3 * parts, base + 4 * (3 * parts + H)), (C.c_int * 3)(parts, parts, parts),
+        (C.c_long * 3)(3, H, H), (C.c_long * 3)(3, 2 * H, 2 * H),
+        (C.c_void_p * 3)(sums2.data_ptr(), dgam2.data_ptr(), dbet2.data_ptr()), st)
+    assert rc == 0, lib.cast_last_error_string()
+
+    def close(a, b, tol=2e-5):
+        a, b = a.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)
+        return np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-30)
+    assert close(y2, y) and close(pl2, pl) and close(nl2, nl) and close(gp2, gp) and close(gn2, gn)
+    assert close(dx2, dx) and close(dgam2, dgam) and close(dbet2, dbet)
+    assert close(sums2, sums[:3], 1e-5)
+    # the oracle's loss on the same normalised rows (models/sasrec.py:99-108)
+    yt, tt = y.cpu(), table.cpu()
+    pe, ne = tt[torch.from_numpy(pos_np).long()], tt[torch.from_numpy(neg_np).long()]
+    plo, nlo = (pe * yt).sum(-1), (ne * yt).sum(-1)
+    ist = torch.from_numpy((pos_np != 0).astype(np.float32))
+    loss_o = ((-torch.log(torch.sigmoid(plo) + 1e-24) - torch.log(1 - torch.sigmoid(nlo) + 1e-24)) * ist).sum()
+    s = sums2.cpu().numpy()
+    assert abs(s[0] - float(loss_o)) <= 1e-4 * abs(float(loss_o)) and s[2] == float(ist.sum())
+
+
+@pytest.mark.emu
+def test_reduce_partials_batch_emulated():
+    run_reduce("emu")
+
+
+@pytest.mark.emu
+def test_fused_tail_emulated():
+    run_tail("emu", 150, 20, 40)
+
+
+@pytest.mark.gpu
+def test_reduce_partials_batch_gpu():
+    run_reduce("gpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,V", [(25600, 50, 3417), (999, 64, 57), (130, 33, 500)])
+def test_fused_tail_gpu(N, H, V):
+    run_tail("gpu", N, H, V)
