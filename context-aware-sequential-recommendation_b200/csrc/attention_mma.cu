@@ -362,16 +362,20 @@ attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
       if (a.row_max) a.row_max[sbase + i] = live ? m : 0.f;
       if (a.row_linv) a.row_linv[sbase + i] = linv;
     }
+    const long obase = (rowbase + i) * dm.H + hh * d;
+    const bool pair_ok = ((dm.H | d) & 1) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0;
 #pragma unroll
-    for (int no = 0; no < NTO; ++no)
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = no * 8 + 2 * tig + cc;
-        if (c < d) {
-          const long off = (rowbase + i) * dm.H + hh * d + c;
-          a.out[off] = o[no][half * 2 + cc] * f + rrow[c];
-        }
+    for (int no = 0; no < NTO; ++no) {
+      const int c = no * 8 + 2 * tig;
+      if (c >= d) continue;
+      const float v0 = o[no][half * 2] * f + rrow[c];
+      if (pair_ok) {  // d even => c + 1 < d
+        *reinterpret_cast<float2*>(a.out + obase + c) = make_float2(v0, o[no][half * 2 + 1] * f + rrow[c + 1]);
+      } else {
+        a.out[obase + c] = v0;
+        if (c + 1 < d) a.out[obase + c + 1] = o[no][half * 2 + 1] * f + rrow[c + 1];
       }
+    }
   }
 }
 
@@ -568,13 +572,20 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
     const int i = half ? iB : iA;
     if (i < 0) continue;
     const bool live = wact && i >= rlive;
+    const long obase = (rowbase + i) * a.lddq + hh * d;
+    const bool pair_ok = (((int)(a.lddq & 1) | d) & 1) == 0 && (reinterpret_cast<uintptr_t>(a.dQ) & 7) == 0;
 #pragma unroll
-    for (int no = 0; no < NTO; ++no)
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = no * 8 + 2 * tig + cc;
-        if (c < d) a.dQ[(rowbase + i) * a.lddq + hh * d + c] = live ? o[no][half * 2 + cc] : 0.f;
+    for (int no = 0; no < NTO; ++no) {
+      const int c = no * 8 + 2 * tig;
+      if (c >= d) continue;
+      const float v0 = live ? o[no][half * 2] : 0.f, v1 = live ? o[no][half * 2 + 1] : 0.f;
+      if (pair_ok) {
+        *reinterpret_cast<float2*>(a.dQ + obase + c) = make_float2(v0, v1);
+      } else {
+        a.dQ[obase + c] = v0;
+        if (c + 1 < d) a.dQ[obase + c + 1] = v1;
       }
+    }
   }
 }
 
@@ -744,16 +755,25 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   for (int half = 0; half < 2; ++half) {
     const int j = half ? jB : jA;
     if (j < 0) continue;
+    const long kb = (rowbase + j) * a.lddk + hh * d, vb = (rowbase + j) * a.lddv + hh * d;
+    const bool pair_ok = (((int)((a.lddk | a.lddv) & 1) | d) & 1) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(a.dK) | reinterpret_cast<uintptr_t>(a.dV)) & 7) == 0;
 #pragma unroll
-    for (int no = 0; no < NTO; ++no)
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int c = no * 8 + 2 * tig + c2;
-        if (c < d) {
-          a.dK[(rowbase + j) * a.lddk + hh * d + c] = gk[no][half * 2 + c2];
-          a.dV[(rowbase + j) * a.lddv + hh * d + c] = gv[no][half * 2 + c2];
+    for (int no = 0; no < NTO; ++no) {
+      const int c = no * 8 + 2 * tig;
+      if (c >= d) continue;
+      if (pair_ok) {
+        *reinterpret_cast<float2*>(a.dK + kb + c) = make_float2(gk[no][half * 2], gk[no][half * 2 + 1]);
+        *reinterpret_cast<float2*>(a.dV + vb + c) = make_float2(gv[no][half * 2], gv[no][half * 2 + 1]);
+      } else {
+        a.dK[kb + c] = gk[no][half * 2];
+        a.dV[vb + c] = gv[no][half * 2];
+        if (c + 1 < d) {
+          a.dK[kb + c + 1] = gk[no][half * 2 + 1];
+          a.dV[vb + c + 1] = gv[no][half * 2 + 1];
         }
       }
+    }
   }
 }
 
@@ -945,16 +965,25 @@ __global__ void __launch_bounds__(AW_THREADS, 2) attn_bwd_dkv_ws_kernel(AttnBwdM
   for (int half = 0; half < 2; ++half) {
     const int j = half ? jB : jA;
     if (j < 0) continue;
+    const long kb = (rowbase + j) * a.lddk + hh * d, vb = (rowbase + j) * a.lddv + hh * d;
+    const bool pair_ok = (((int)((a.lddk | a.lddv) & 1) | d) & 1) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(a.dK) | reinterpret_cast<uintptr_t>(a.dV)) & 7) == 0;
 #pragma unroll
-    for (int no = 0; no < NTO; ++no)
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int c = no * 8 + 2 * tig + c2;
-        if (c < d) {
-          a.dK[(rowbase + j) * a.lddk + hh * d + c] = gk[no][half * 2 + c2];
-          a.dV[(rowbase + j) * a.lddv + hh * d + c] = gv[no][half * 2 + c2];
+    for (int no = 0; no < NTO; ++no) {
+      const int c = no * 8 + 2 * tig;
+      if (c >= d) continue;
+      if (pair_ok) {
+        *reinterpret_cast<float2*>(a.dK + kb + c) = make_float2(gk[no][half * 2], gk[no][half * 2 + 1]);
+        *reinterpret_cast<float2*>(a.dV + vb + c) = make_float2(gv[no][half * 2], gv[no][half * 2 + 1]);
+      } else {
+        a.dK[kb + c] = gk[no][half * 2];
+        a.dV[vb + c] = gv[no][half * 2];
+        if (c + 1 < d) {
+          a.dK[kb + c + 1] = gk[no][half * 2 + 1];
+          a.dV[vb + c + 1] = gv[no][half * 2 + 1];
         }
       }
+    }
   }
 }
 

@@ -512,14 +512,24 @@ __global__ void __launch_bounds__(FT, 3) ln_qkv_fwd_mma_kernel(LnQkvArgs a, FDim
     rm_mm_bt_tight<KS, S>(acc, (m == 0 ? Ns : Xs) + m0 * S, Wsm + m * WT + n0 * S, nact, lane);
     const float* bias = a.b[m];
     float* out = a.out[m];
+    const bool pair_ok = (H & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       if (nt >= nact) continue;
+      const int c = n0 + nt * 8 + 2 * tig;  // this thread's column pair (c, c+1) of the fragment
+      if (c >= H) continue;
+      const float bc0 = bias[c], bc1 = c + 1 < H ? bias[c + 1] : 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const long row = row0 + m0 + g + (e >> 1) * 8;
-        const int c = n0 + nt * 8 + 2 * tig + (e & 1);
-        if (c < H && row < d.N) out[row * H + c] = acc[nt][e] + bias[c];
+      for (int hf = 0; hf < 2; ++hf) {
+        const long row = row0 + m0 + g + hf * 8;
+        if (row >= d.N) continue;
+        const float v0 = acc[nt][2 * hf] + bc0, v1 = acc[nt][2 * hf + 1] + bc1;
+        if (pair_ok && c + 1 < H) {
+          *reinterpret_cast<float2*>(out + row * H + c) = make_float2(v0, v1);
+        } else {
+          out[row * H + c] = v0;
+          if (c + 1 < H) out[row * H + c + 1] = v1;
+        }
       }
     }
   }
@@ -546,6 +556,7 @@ __global__ void __launch_bounds__(FT, 3) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDim
   rm_load_w_t<HP8, S>(Wsm + WT, a.W2, H);
   const Drop dh = make_drop(a.rate, a.seed, a.step, a.site_h);
   const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
+  const bool pair_ok = (H & 1) == 0 && ((reinterpret_cast<uintptr_t>(a.h1d) | reinterpret_cast<uintptr_t>(a.xout)) & 7) == 0;
   cp_async_wait<0>();
   __syncthreads();
   f_layernorm_rows(Ys, Ns, a.gamma, a.beta, a.eps, row0, d, a.zn, a.mean, a.rstd, nullptr, nullptr);
@@ -560,17 +571,21 @@ __global__ void __launch_bounds__(FT, 3) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDim
     for (int hf = 0; hf < 2; ++hf) {
       const int r = m0 + g + hf * 8, c0 = n0 + nt * 8 + 2 * tig;
       const long row = row0 + r;
-      float dm2[2];
+      float dm2[2], hv[2];
       drop_mul2(dh, (unsigned long long)(row * H + c0), dm2[0], dm2[1]);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = c0 + cc;
-        float h = 0.f;
-        if (c < H && row < d.N) {
-          h = fmaxf(acc[nt][hf * 2 + cc] + a.b1[c], 0.f) * dm2[cc];
-          a.h1d[row * H + c] = h;
+        hv[cc] = (c < H && row < d.N) ? fmaxf(acc[nt][hf * 2 + cc] + a.b1[c], 0.f) * dm2[cc] : 0.f;
+        Ys[r * S + c] = hv[cc];
+      }
+      if (row < d.N && c0 < H) {
+        if (pair_ok && c0 + 1 < H) {
+          *reinterpret_cast<float2*>(a.h1d + row * H + c0) = make_float2(hv[0], hv[1]);
+        } else {
+          a.h1d[row * H + c0] = hv[0];
+          if (c0 + 1 < H) a.h1d[row * H + c0 + 1] = hv[1];
         }
-        Ys[r * S + c] = h;
       }
     }
   }
@@ -586,15 +601,19 @@ __global__ void __launch_bounds__(FT, 3) ln_ffn_fwd_mma_kernel(LnFfnArgs a, FDim
       const long row = row0 + r;
       if (row >= d.N) continue;
       const float m = a.ids ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;
-      float dm2[2];
+      float dm2[2], ov[2];
       drop_mul2(dout, (unsigned long long)(row * H + c0), dm2[0], dm2[1]);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = c0 + cc;
-        if (c < H) {
-          float o = (acc[nt][hf * 2 + cc] + a.b2[c]) * dm2[cc];
-          o += Ns[r * S + c];
-          a.xout[row * H + c] = o * m;
+        ov[cc] = c < H ? ((acc[nt][hf * 2 + cc] + a.b2[c]) * dm2[cc] + Ns[r * S + c]) * m : 0.f;
+      }
+      if (c0 < H) {
+        if (pair_ok && c0 + 1 < H) {
+          *reinterpret_cast<float2*>(a.xout + row * H + c0) = make_float2(ov[0], ov[1]);
+        } else {
+          a.xout[row * H + c0] = ov[0];
+          if (c0 + 1 < H) a.xout[row * H + c0 + 1] = ov[1];
         }
       }
     }
