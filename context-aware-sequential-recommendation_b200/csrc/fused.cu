@@ -242,7 +242,7 @@ struct LnBwdOut {
   float dgamma, dbeta;  // column owned by thread (tid % 64) for tid < 128: tid/64 == 0 -> dgamma, == 1 -> dbeta
 };
 
-template <int NWARP = FT / 32>
+template <int NWARP = FT / 32, bool COLS = true>
 __device__ __forceinline__ void f_ln_bwd_rows(const float* __restrict__ Gs, const float* __restrict__ Xr, int sxr,
                                               int sxc, const float* __restrict__ Add,
                                               const float* __restrict__ gamma,
@@ -288,7 +288,8 @@ __device__ __forceinline__ void f_ln_bwd_rows(const float* __restrict__ Gs, cons
   }
   __syncthreads();
   // (b) column sums for dgamma / dbeta: threads 0..63 -> dgamma[c], 64..127 -> dbeta[c]
-  if (t < 128) {
+  // (COLS == false: the caller spreads them over all its threads, fused_mma.cuh)
+  if (COLS && t < 128) {
     const int c = t & 63;
     if (c < d.H) {
       float s = 0.f;

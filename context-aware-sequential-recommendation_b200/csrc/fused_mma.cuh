@@ -159,6 +159,50 @@ __device__ __forceinline__ void rm_wgrad(float (&acc)[NB][NTW][4], const float* 
   }
 }
 
+// Column sums spread over the whole CTA: thread t owns column t & 63 of the row slice t >> 6 (64 / SL rows); partial
+// sums stay in the thread's registers across all tiles and are folded over the SL slices, in slice order, once at the
+// end of the kernel (rm_fold_cols) -- instead of 64 threads walking all 64 rows of every tile.
+template <int SL, int S>
+__device__ __forceinline__ float rm_colsum_slice(const float* __restrict__ Ts) {
+  const int c = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  constexpr int R = FR / SL;
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) s += Ts[(sl * R + r) * S + c];
+  return s;
+}
+// dgamma / dbeta slice sums of the LayerNorm backward: sum_r G[r][c] * xhat[r][c] and sum_r G[r][c]
+template <int SL, int S>
+__device__ __forceinline__ void rm_ln_cols_slice(const float* __restrict__ Gs, const float* __restrict__ Xr,
+                                                 const float* __restrict__ rowstat, float& dgam, float& dbet) {
+  const int c = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  constexpr int R = FR / SL;
+  float sg = 0.f, sb = 0.f;
+#pragma unroll
+  for (int r0 = 0; r0 < R; ++r0) {
+    const int r = sl * R + r0;
+    const float gv = Gs[r * S + c];
+    sg += gv * ((Xr[r * S + c] - rowstat[r * 4]) * rowstat[r * 4 + 1]);
+    sb += gv;
+  }
+  dgam += sg;
+  dbet += sb;
+}
+// out[c] = sum over the SL slices (fixed order) of the per-thread partials; scratch: [SL][64] floats
+template <int SL>
+__device__ __forceinline__ void rm_fold_cols(float v, float* __restrict__ scratch, float* __restrict__ out, int H) {
+  const int c = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  __syncthreads();
+  scratch[sl * 64 + c] = v;
+  __syncthreads();
+  if (sl == 0 && c < H) {
+    float s = scratch[c];
+#pragma unroll
+    for (int k = 1; k < SL; ++k) s += scratch[k * 64 + c];
+    out[c] = s;
+  }
+}
+
 template <int NTW>
 __device__ __forceinline__ void rm_zero(float (&acc)[NTW][4]) {
 #pragma unroll
@@ -218,7 +262,8 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
   rm_zero(gWq[0]);
   rm_zero(gWkv[0]);
   rm_zero(gWkv[1]);
-  float vb = 0.f;  // group 0 -> dbq, 1 -> dbk, 2 -> dbv
+  constexpr int SL = BT / 64;  // row slices of the column sums
+  float vbq = 0.f, vbk = 0.f, vbv = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
   if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
   int it = 0;
@@ -260,9 +305,9 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
     rm_mm_bt<KS, S, NTW>(accq, Gq + m0 * S, Wsm + n0 * S, nact, lane);             // dqn (without the residual)
     rm_mm_bt<KS, S, NTW>(acck, Gk + m0 * S, Wsm + TILE + n0 * S, nact, lane);      // dx through K ...
     rm_mm_bt<KS, S, NTW>(acck, Gv + m0 * S, Wsm + 2 * TILE + n0 * S, nact, lane);  // ... and V
-    f_colsum(Gq, 0, d, vb);
-    f_colsum(Gk, 1, d, vb);
-    f_colsum(Gv, 2, d, vb);
+    vbq += rm_colsum_slice<SL, S>(Gq);
+    vbk += rm_colsum_slice<SL, S>(Gk);
+    vbv += rm_colsum_slice<SL, S>(Gv);
     __syncthreads();
 #pragma unroll
     for (int nt = 0; nt < NTW; ++nt) {
@@ -276,16 +321,18 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
       }
     }
     __syncthreads();
-    f_ln_bwd_rows<NW>(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet);
+    f_ln_bwd_rows<NW, false>(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet);
+    rm_ln_cols_slice<SL, S>(Gq, X, rowstat, dgam, dbet);
   }
   float* P = a.partial + (long)blockIdx.x * (2L * H + 3L * (H * H + H));
-  if (t < 64 && t < H) P[H + t] = dgam;
-  if (t >= 64 && t < 128 && (t & 63) < H) P[t & 63] = dbet;
+  rm_fold_cols<SL>(dgam, sm, P + H, H);
+  rm_fold_cols<SL>(dbet, sm, P, H);
+  rm_fold_cols<SL>(vbq, sm, P + 2 * H + H * H, H);
+  rm_fold_cols<SL>(vbk, sm, P + 2 * H + (H * H + H) + H * H, H);
+  rm_fold_cols<SL>(vbv, sm, P + 2 * H + 2 * (H * H + H) + H * H, H);
   rm_store_wpartial(P + 2 * H, gWq[0], m0, n0, nact, H, lane);
   rm_store_wpartial(P + 2 * H + (H * H + H), gWkv[0], m0, n0, nact, H, lane);
   rm_store_wpartial(P + 2 * H + 2 * (H * H + H), gWkv[1], m0, n0, nact, H, lane);
-  const int grp = t >> 6;
-  if (grp < 3 && (t & 63) < H) P[2 * H + grp * (H * H + H) + H * H + (t & 63)] = vb;
 }
 
 // ------------------------------------------------------------------------------------------------ ffn backward
@@ -323,7 +370,8 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
   float gW1[1][NTW][4], gW2[1][NTW][4];
   rm_zero(gW1[0]);
   rm_zero(gW2[0]);
-  float vb = 0.f;  // thread-owned vector gradient: group 0 -> db2, 1 -> db1 (tid/64), column tid%64
+  constexpr int SL = BT / 64;  // row slices of the column sums
+  float vb1 = 0.f, vb2 = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
   if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
   int it = 0;
@@ -378,7 +426,7 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
         }
       }
     }
-    f_colsum(Gd, 0, d, vb);
+    vb2 += rm_colsum_slice<SL, S>(Gd);
     __syncthreads();
     // dW1 += zn^T Dh ; db1 += colsum(Dh) ; dzn = Dh W1^T + Gm  (stored over Gd)
     {
@@ -397,17 +445,18 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
         }
       }
     }
-    f_colsum(Dh, 1, d, vb);
+    vb1 += rm_colsum_slice<SL, S>(Dh);
     __syncthreads();
-    f_ln_bwd_rows<NW>(Gd, Yr, S, 1, nullptr, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dy, dgam, dbet);
+    f_ln_bwd_rows<NW, false>(Gd, Yr, S, 1, nullptr, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dy, dgam, dbet);
+    rm_ln_cols_slice<SL, S>(Gd, Yr, rowstat, dgam, dbet);
   }
   float* P = a.partial + (long)blockIdx.x * (2L * H + 2L * (H * H + H));
-  if (t < 64 && t < H) P[H + t] = dgam;
-  if (t >= 64 && t < 128 && (t & 63) < H) P[t & 63] = dbet;
+  rm_fold_cols<SL>(dgam, sm, P + H, H);
+  rm_fold_cols<SL>(dbet, sm, P, H);
+  rm_fold_cols<SL>(vb1, sm, P + 2 * H + H * H, H);
+  rm_fold_cols<SL>(vb2, sm, P + 2 * H + H * H + H + H * H, H);
   rm_store_wpartial(P + 2 * H, gW1[0], m0, n0, nact, H, lane);
   rm_store_wpartial(P + 2 * H + H * H + H, gW2[0], m0, n0, nact, H, lane);
-  if ((t >> 6) == 1 && (t & 63) < H) P[2 * H + H * H + (t & 63)] = vb;              // db1
-  if ((t >> 6) == 0 && (t & 63) < H) P[2 * H + H * H + H + H * H + (t & 63)] = vb;  // db2
 }
 
 // ------------------------------------------------------------------------------------------------ forward kernels
