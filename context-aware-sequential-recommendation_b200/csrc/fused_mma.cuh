@@ -48,6 +48,13 @@ __device__ __forceinline__ bool rm_vec2_ok(const void* p, int H) {
   return (H & 1) == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0;
 }
 
+// zero the padding columns H..HP8-1 of `rows` tile rows
+template <int HP8, int S>
+__device__ __forceinline__ void rm_zero_pad(float* __restrict__ buf, int rows, int H) {
+  for (int r = threadIdx.x; r < rows; r += (int)blockDim.x)
+    for (int c = H; c < HP8; ++c) buf[r * S + c] = 0.f;
+}
+
 // W[H][H] row-major (global) -> Ws[k][n] stride S; the caller zeroed the buffer (64 rows) beforehand
 template <int S>
 __device__ __forceinline__ void rm_load_w(float* __restrict__ Ws, const float* __restrict__ W, int H) {
@@ -241,7 +248,8 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
   int nact = KS - NTW * nh;
   nact = nact < 0 ? 0 : (nact > NTW ? NTW : nact);
   const int m0 = mt * 16, n0 = nh * NTW * 8;
-  for (int i = t; i < 2 * STAGE + 3 * TILE; i += BT) sm[i] = 0.f;
+  for (int i = t; i < 3 * TILE; i += BT) Wsm[i] = 0.f;      // weights: zero padded to [64][S]
+  rm_zero_pad<8 * KS, S>(sm, 10 * FR, H);                   // K-padding columns of the ten stage tiles
   __syncthreads();
   rm_load_w<S>(Wsm, a.Wq, H);
   rm_load_w<S>(Wsm + TILE, a.Wk, H);
@@ -353,7 +361,8 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
   const int m0 = mt * 16, n0 = nh * NTW * 8;
   const float scale = a.rate > 0.f ? 1.0f / (1.0f - a.rate) : 1.0f;
   const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
-  for (int i = t; i < 2 * STAGE + 4 * TILE; i += BT) sm[i] = 0.f;
+  for (int i = t; i < 4 * TILE; i += BT) Gd[i] = 0.f;       // Gd, Dh and the two weight tiles
+  rm_zero_pad<8 * KS, S>(sm, 8 * FR, H);                    // K-padding columns of the eight stage tiles
   __syncthreads();
   rm_load_w<S>(W1s, a.W1, H);
   rm_load_w<S>(W2s, a.W2, H);
@@ -487,13 +496,6 @@ __device__ __forceinline__ void rm_load_w_t(float* __restrict__ Wt, const float*
       if (n < HP8) Wt[n * S + k] = v[i][j];
     }
   }
-}
-
-// zero the padding columns H..HP8-1 of `rows` tile rows
-template <int HP8, int S>
-__device__ __forceinline__ void rm_zero_pad(float* __restrict__ buf, int rows, int H) {
-  for (int r = threadIdx.x; r < rows; r += FT)
-    for (int c = H; c < HP8; ++c) buf[r * S + c] = 0.f;
 }
 
 // rm_mm_bt for a Bt buffer that ends after the last real n-tile: when nact is odd the ldmatrix rows of the missing

@@ -123,6 +123,7 @@ def roofline_of_dominant(kernels, B, T, H, args, root):
         fp32_peak = 2 * 128 * 148 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         # fp32-grade results need the 3xTF32 split: 3 tensor passes per algorithmic product, at half the bf16 rate
         eff_peak = peak / 2.0 / 3.0
+        mma_peak = 1024 * 148 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         narrow = H <= 64 and top["name"] != "cast_gemm"
         pipe = ("tensor cores, mma.sync m16n8k8 TF32 x3 (hi/lo split keeps fp32 parity 1e-4); head width "
                 f"{H} < one UMMA tile, so warp-level MMA with register-resident softmax"
@@ -134,6 +135,9 @@ def roofline_of_dominant(kernels, B, T, H, args, root):
                 "algorithmic_flops_per_step": top["flops_per_step"],
                 "pipe_used": pipe,
                 "peak_3xtf32_tflops": eff_peak, "frac_of_3xtf32_peak": top["tflops"] / eff_peak,
+                # warp-level path: HMMA.1688.F32.TF32 holds the SMSP tensor pipe 8 cycles (measured, ncu:
+                # pipe_tensor_cycles_active / HMMA count, profiles/r02_mma_sync_rate.txt) => 1024 flop/clk/SM
+                "mma_sync_tf32_peak_tflops": mma_peak, "frac_of_mma_sync_3xtf32": top["tflops"] / (mma_peak / 3.0),
                 "fp32_pipe_peak_tflops": fp32_peak, "frac_of_fp32_pipe": top["tflops"] / fp32_peak}
     peak = pk["hbm_gbs"]
     return {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
