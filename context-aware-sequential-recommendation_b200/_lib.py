@@ -46,6 +46,7 @@ SIGNATURES = {
     "cast_reduce_partials_batch": (I, [I, P, P, P, P, P, P]),
     "cast_layernorm_bwd_parts": (I, [L]),
     "cast_logits_loss_parts": (I, [L]),
+    "cast_time_features": (I, [P, P, P, I, I, P, I, P, P, P, P]),
     "cast_lnf_loss_parts": (I, [L]),
     "cast_lnf_loss_workspace_bytes": (SZ, [L, I]),
     "cast_lnf_loss": (I, [P, P, P, F, P, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),

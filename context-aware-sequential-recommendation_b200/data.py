@@ -131,6 +131,32 @@ def timedelta_bins(deltas: np.ndarray, bin_in_hours=48, max_bins=200, log_scale=
     return np.minimum(b, max_bins).astype(np.int32)
 
 
+def time_bin_edges(bin_in_hours=48, max_bins=200, log_scale=False, min_ts=None, max_ts=None) -> np.ndarray:
+    """edges[k] = smallest integer time delta (seconds) whose `get_timedelta_bin` exceeds k, k = 0..max_bins-1, found
+    with the reference's own scalar rule (so float64 `log` rounding is inherited, not re-derived): the bin of a delta
+    is the number of edges <= delta.  Input table of the device ETL (`cast_time_features`)."""
+    f = lambda d: get_timedelta_bin(d, bin_in_hours, max_bins, log_scale, min_ts, max_ts)  # noqa: E731
+    if not log_scale:
+        return (np.arange(1, max_bins + 1, dtype=np.int64) * int(bin_in_hours) * 3600)
+    edges = np.empty(max_bins, dtype=np.int64)
+    cap = 1 << 62
+    for k in range(max_bins):
+        lo, hi = 0, 1
+        while hi < cap and f(hi) <= k:        # gallop to a delta whose bin exceeds k
+            lo, hi = hi, hi * 2
+        if f(hi) <= k:                        # never exceeded (bin saturates below k+1)
+            edges[k] = np.iinfo(np.int64).max
+            continue
+        while lo + 1 < hi:                    # invariant: f(lo) <= k < f(hi)
+            mid = (lo + hi) // 2
+            if f(mid) <= k:
+                lo = mid
+            else:
+                hi = mid
+        edges[k] = hi if f(0) <= k else 0
+    return edges
+
+
 def add_time_bin(users, log_scale, bin_in_hours=48, max_bins=200):
     """util.py:185-201 — annotate every record with the bin of its distance to the user's last event."""
     lo = hi = None

@@ -176,6 +176,14 @@ int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk, const floa
                   long lddk, float* dV, long lddv, const float* out, const float* queries, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Time-context ids from raw timestamps on the device (reference util.py:24-43 hour / weekday, util.py:73-120
+ * get_timedelta_bin, applied per position by sampler.py:61-72 and util.py:276-289).  ts [B,T] int64 seconds, ids [B,T]
+ * (0 = padding => all three outputs 0), ref [B] reference time per row or NULL (= ts[b,T-1], the newest event of the
+ * left-padded row), edges[k] = smallest delta (seconds) whose bin exceeds k, tabulated on the host with the reference's
+ * scalar rule (data.time_bin_edges): bin = #{k : edges[k] <= ref - ts}.  Outputs int32 [B,T]. */
+int cast_time_features(const long long* ts, const long long* ref, const int* ids, int B, int T, const long long* edges,
+                       int n_edges, int* bins, int* hours, int* days, void* stream);
+
 /* models/sasrec.py:87-115: pos/neg row gathers from the zero-padded table, row dots, literal BCE
  * (-log(sigmoid+1e-24)), istarget mask, AUC.  sums[0..2] = {sum loss terms, sum auc terms, sum istarget}
  * (un-normalised: the caller divides, or all-reduces first under data parallelism, sasrec.py:105-108).
