@@ -447,17 +447,30 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   if (nch > 0) issue(kbeg, 0); else cp_async_commit();
   am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
   // D_i = dO_i . (out_i - queries_i) over this head's columns: one warp per row
-  for (int r = wid; r < AM_T; r += NW) {
-    const int i = q0 + r;
-    float acc = 0.f;
-    if (i >= qstart && i >= 0) {
-      const long off = (rowbase + i) * dm.H + hh * d;
-      for (int c = lane; c < d; c += 32) acc += a.dO[off + c] * (aa.out[off + c] - aa.resid[off + c]);
+  {  // all of a warp's rows at once: the (up to) 6 loads per row are independent and stay in flight together
+    constexpr int RW = AM_T / NW;
+    float acc[RW];
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+      const int i = q0 + wid + k * NW;
+      acc[k] = 0.f;
+      if (i >= qstart && i >= 0) {
+        const long off = (rowbase + i) * dm.H + hh * d;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = lane + 32 * u;
+          if (c < d) acc[k] = fmaf(a.dO[off + c], aa.out[off + c] - aa.resid[off + c], acc[k]);
+        }
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      Dsm[r] = acc;
-      if (i >= 0) a.rowD[sbase + i] = acc;
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+      const int r = wid + k * NW, i = q0 + r;
+      const float v = warp_sum(acc[k]);
+      if (lane == 0) {
+        Dsm[r] = v;
+        if (i >= 0) a.rowD[sbase + i] = v;
+      }
     }
   }
   const Drop dr = make_drop(a.rate, a.seed, a.step, a.site);

@@ -399,12 +399,15 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
       cp_async_wait<0>();
     }
     __syncthreads();
-    // masked / dropped upstream gradient
-    for (int r = warp; r < FR; r += NW) {
-      const long row = row0 + r;
-      const bool ok = row < d.N;
-      const float m = (ok && (!a.ids || a.ids[row] != 0)) ? 1.f : 0.f;
-      for (int c = 2 * lane; c < H; c += 64) {  // a lane owns a column pair: one dropout hash word
+    // masked / dropped upstream gradient: one (row, column pair) task per thread and pass, one dropout hash word each
+    {
+      const int PW = (H + 1) >> 1;
+#pragma unroll 4
+      for (int p = t; p < FR * PW; p += BT) {
+        const int r = p / PW, c = 2 * (p - r * PW);
+        const long row = row0 + r;
+        const bool ok = row < d.N;
+        const float m = (ok && (!a.ids || a.ids[row] != 0)) ? 1.f : 0.f;
         float dm2[2];
         drop_mul2(dout, (unsigned long long)(row * H + c), dm2[0], dm2[1]);
         const float g0 = Gm[r * S + c] * m;
