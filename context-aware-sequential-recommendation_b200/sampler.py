@@ -117,6 +117,74 @@ class SampleStream:
         return tuple(out)
 
 
+class FastSampleStream:
+    """Same stream as `SampleStream`, produced by the C++ restatement of numpy's legacy RandomState in the library
+    (`cast_sampler_*`, csrc/sampler_host.cu): ~20x the Python stream's rate, so the host keeps up with the GPU step.
+    Bit-identical batches for a given seed (tests/test_fast_sampler.py compares it with `SampleStream`, itself pinned
+    to batches captured from the reference's `sample_function`)."""
+
+    def __init__(self, user_train: Dict[int, Sequence], usernum: int, itemnum: int, batch_size: int, maxlen: int,
+                 bin_in_hours: int, max_bins: int, log_scale: bool, min_timedelta, max_timedelta, seed: int, lib=None):
+        import ctypes as C
+        from . import _lib
+        from .data import time_bin_edges
+        self.lib = lib if lib is not None else _lib.load_library()
+        self.B, self.T = batch_size, maxlen
+        log_scale = bool(log_scale)
+        bih, mb = (48, 200) if log_scale else (bin_in_hours, max_bins)   # sampler.py:66
+        counts = np.zeros(usernum + 2, dtype=np.int64)
+        for u, seq in user_train.items():
+            counts[u + 1] = len(seq)
+        uptr = np.cumsum(counts)
+        n = int(uptr[-1])
+        items = np.zeros(n, np.int32)
+        ratings = np.zeros(n, np.int32)
+        hours = np.zeros(n, np.int32)
+        days = np.zeros(n, np.int32)
+        ts = np.zeros(n, np.int64)
+        for u, seq in user_train.items():
+            if not len(seq):
+                continue
+            a = _UserArrays(seq)
+            lo = int(uptr[u])
+            items[lo:lo + len(seq)] = a.item
+            ratings[lo:lo + len(seq)] = a.rating
+            hours[lo:lo + len(seq)] = a.hour
+            days[lo:lo + len(seq)] = a.day
+            ts[lo:lo + len(seq)] = a.t
+        edges = np.ascontiguousarray(time_bin_edges(bih, mb, log_scale, min_timedelta if log_scale else None,
+                                                    max_timedelta if log_scale else None))
+        self._keep = (uptr, items, ratings, hours, days, ts, edges)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        self.h = self.lib.cast_sampler_create(usernum, itemnum, p(uptr), p(items), p(ratings), p(hours), p(days), p(ts),
+                                              maxlen, int(seed) & 0xFFFFFFFF, p(edges), int(edges.size))
+        if not self.h:
+            raise RuntimeError("cast_sampler_create failed")
+        self._C = C
+
+    def next_batch(self):
+        B, T, C = self.B, self.T, self._C
+        user = np.empty(B, np.int32)
+        out = [np.empty((B, T), np.int32) for _ in range(7)]  # seq pos neg timeseq ratings hours days
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.cast_sampler_next(self.h, B, p(user), *[p(a) for a in out])
+        if rc != 0:
+            raise RuntimeError(f"cast_sampler_next failed ({rc})")
+        seq, pos, neg, timeseq, ratings, hours, days = out
+        return user, seq, pos, neg, timeseq, ratings, hours, days, [None] * B
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cast_sampler_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class WarpSampler:
     """reference sampler.py:83-136 interface: `WarpSampler(args, User, usernum, itemnum, batch_size=, maxlen=,
     n_workers=1).next_batch()` / `.close()`.  One background thread keeps a few batches ahead (the reference uses one
@@ -128,8 +196,16 @@ class WarpSampler:
             raise ValueError("the reference stream is defined for n_workers=1 (main.py:148)")
         lo, hi = get_delta_range(User)
         seed = args.seed if getattr(args, "seed", None) else int(np.random.randint(2e9))
-        self.stream = SampleStream(User, usernum, itemnum, batch_size, maxlen, args.bin_in_hours, args.max_bins,
-                                   args.log_scale, lo, hi, seed, with_objects=with_objects)
+        self.stream = None
+        if not with_objects and getattr(args, "fast_sampler", True):
+            try:  # C++ stream (same batches, ~20x faster); the Python stream remains the fallback and the oracle
+                self.stream = FastSampleStream(User, usernum, itemnum, batch_size, maxlen, args.bin_in_hours,
+                                               args.max_bins, args.log_scale, lo, hi, seed)
+            except Exception:
+                self.stream = None
+        if self.stream is None:
+            self.stream = SampleStream(User, usernum, itemnum, batch_size, maxlen, args.bin_in_hours, args.max_bins,
+                                       args.log_scale, lo, hi, seed, with_objects=with_objects)
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, prefetch))
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)

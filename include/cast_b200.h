@@ -176,6 +176,19 @@ int cast_attn_bwd(const float* Q, long ldq, const float* K, long ldk, const floa
                   long lddk, float* dV, long lddv, const float* out, const float* queries, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Host-side training-batch sampler, stream-identical to the reference's sample_function (sampler.py:16-81) for a given
+ * --seed: numpy's legacy RandomState (MT19937 + masked-rejection randint) restated in C++, consumed in the same order
+ * (user draws until one with > 1 training events; negatives newest position first, rejecting the user's items).
+ * user_ptr [usernum+2] is a CSR over user ids 0..usernum (user 0 empty) into items / ratings / hours / days / ts (the
+ * latter four optional); edges / n_edges as in cast_time_features (optional).  cast_sampler_next fills [B,T] int32
+ * arrays left-padded with zeros (timeseq / ratings / hours / days may be NULL).  The object owns host memory only. */
+void* cast_sampler_create(int usernum, int itemnum, const long* user_ptr, const int* items, const int* ratings,
+                          const int* hours, const int* days, const long long* ts, int maxlen, unsigned seed,
+                          const long long* edges, int n_edges);
+int cast_sampler_next(void* sampler, int B, int* user, int* seq, int* pos, int* neg, int* timeseq, int* ratings,
+                      int* hours, int* days);
+void cast_sampler_destroy(void* sampler);
+
 /* Time-context ids from raw timestamps on the device (reference util.py:24-43 hour / weekday, util.py:73-120
  * get_timedelta_bin, applied per position by sampler.py:61-72 and util.py:276-289).  ts [B,T] int64 seconds, ids [B,T]
  * (0 = padding => all three outputs 0), ref [B] reference time per row or NULL (= ts[b,T-1], the newest event of the
