@@ -188,6 +188,10 @@ def run(args, device=None, lib=None, logger=None):
         sampler.close()
         if log:
             log.close()
+    if world > 1:
+        import torch.distributed as tdist
+        if tdist.is_initialized():
+            tdist.destroy_process_group()
     if rc == 0:
         print("Done")
     return rc
