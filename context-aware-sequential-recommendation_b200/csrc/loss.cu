@@ -118,7 +118,8 @@ lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
     const float d0 = h0 ? v0 - mean : 0.f, d1 = h1 ? v1 - mean : 0.f;
     const float var = warp_sum(d0 * d0 + d1 * d1) / (float)H;
     const float stdv = sqrtf(var + eps);
-    const float xh0 = d0 / stdv, xh1 = d1 / stdv;
+    const float rs = 1.0f / stdv;
+    const float xh0 = d0 * rs, xh1 = d1 * rs;
     const float y0 = h0 ? g0 * xh0 + b0 : 0.f, y1 = h1 ? g1 * xh1 + b1 : 0.f;
     if (h0) seq[n * H + c0] = y0;
     if (h1) seq[n * H + c1] = y1;
@@ -147,7 +148,6 @@ lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
     const float a0 = e0 * g0, a1 = e1 * g1;
     const float s1 = warp_sum(a0 + a1) / (float)H;
     const float s2 = warp_sum(a0 * xh0 + a1 * xh1) / (float)H;
-    const float rs = 1.0f / stdv;
     if (h0) dx[n * H + c0] = rs * (a0 - s1 - xh0 * s2);
     if (h1) dx[n * H + c1] = rs * (a1 - s1 - xh1 * s2);
     dg0 = fmaf(e0, xh0, dg0);
