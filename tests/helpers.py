@@ -81,3 +81,34 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def synth_batch(B, T, itemnum, seed, mean_len=None, max_bins=200):
+    """Seeded synthetic batch in the sampler's layout (left-padded seq/pos/neg + time bins, hours, days) for parity
+    runs at BASELINE.json shapes the golden fixtures (T=50, B=16) do not reach: ragged lengths (some shorter than
+    T, some full), Zipf item popularity (duplicate ids stress the sparse scatter), the newest event in bin 0."""
+    rng = np.random.RandomState(seed)
+    mean_len = mean_len or 0.8 * T
+    prob = np.arange(1, itemnum + 1, dtype=np.float64) ** -1.0
+    cdf = np.cumsum(prob / prob.sum())
+    cdf[-1] = 1.0
+    seq = np.zeros((B, T), np.int32)
+    pos = np.zeros((B, T), np.int32)
+    neg = np.zeros((B, T), np.int32)
+    lens = np.clip(rng.lognormal(np.log(mean_len) - 0.32, 0.8, B), 2, T + 1).astype(np.int64)
+    lens[0] = T + 1      # one full row
+    lens[-1] = 2         # one almost empty row
+    for b in range(B):
+        n = int(lens[b])
+        items = np.searchsorted(cdf, rng.rand(n)) + 1
+        k = n - 1
+        seq[b, T - k:] = items[:-1]
+        pos[b, T - k:] = items[1:]
+        neg[b, T - k:] = rng.randint(1, itemnum + 1, k)
+    live = seq > 0
+    ts = np.where(live, np.minimum(max_bins, rng.geometric(0.05, (B, T)) - 1), 0).astype(np.int32)
+    ts[:, -1] = 0
+    hrs = np.where(live, rng.randint(1, 25, (B, T)), 0).astype(np.int32)
+    dys = np.where(live, rng.randint(1, 8, (B, T)), 0).astype(np.int32)
+    return {"u": np.arange(1, B + 1, dtype=np.int32), "seq": seq, "pos": pos, "neg": neg, "timeseq": ts,
+            "hours": hrs, "days": dys}

@@ -17,11 +17,13 @@ from cast_b200.engine import Engine
 TOL = 1e-4
 
 
-def run_step(kind, model, B, T, H, heads, rate, seed=7, randomize=True, blocks=2, tag="lin", l2=0.0):
+def run_step(kind, model, B, T, H, heads, rate, seed=7, randomize=True, blocks=2, tag="lin", l2=0.0, gb=None,
+             itemnum=300):
     lib, dev = backend(kind)
     args = make_args(hidden_units=H, maxlen=T, num_heads=heads, num_blocks=blocks, dropout_rate=rate, l2_emb=l2)
-    gb = golden_batch(tag=tag, B=B, T=T)
-    eng = Engine(model, 80, 300, args, device=dev, lib=lib, seed=seed)
+    if gb is None:
+        gb = golden_batch(tag=tag, B=B, T=T)
+    eng = Engine(model, 80, itemnum, args, device=dev, lib=lib, seed=seed)
     p = {k: v.detach().cpu().clone() for k, v in eng.P.items()}
     if randomize:  # non-trivial beta/gamma/biases so that query masks, residual LN paths etc. are exercised
         g = torch.Generator().manual_seed(3)

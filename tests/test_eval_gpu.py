@@ -77,3 +77,33 @@ def test_full_catalog_evaluation_counts_are_exact():
     np.random.seed(3)
     ndcg, hr = cev.evaluate(m, dataset, args, None, batch_users=U, mode="full")
     assert (ndcg, hr) == cev.metrics_from_ranks(gt_o)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_name", ["sasrec", "cast_3"])
+def test_candidate_logits_and_ranks_bit_exact_vs_canonical_order(model_name):
+    """SURVEY A-12 contract: the 101-candidate logits are the canonical fp32 dot (k ascending, product and sum rounded
+    separately) of the device's own last-position vector with the zero-padded table rows — so logits compare BIT FOR
+    BIT with `oracle.canonical_logits`, and count_greater / count_equal / the literal argsort rank (util.py:318-321)
+    are equal by construction, not by margin."""
+    dataset, args, m, p = _setup(model_name)
+    random.seed(11)
+    np.random.seed(11)
+    cand = cev.build_candidates(dataset, args, "test")
+    U = len(cand["u"])
+    item_idx = np.asarray(cand["item_idx"], np.int32).copy()
+    item_idx[0, 5] = item_idx[0, 0]          # an exact tie with the target
+    item_idx[1, 7] = 0                       # the pad id scores exactly 0
+    logits, cgt, ceq = m.score_candidates(cand["seq"], item_idx, cand["timeseq"], cand["hours"], cand["days"])
+    c = m.engine.ctx(U)
+    last = c.seq_emb.view(U, args.maxlen, 50)[:, -1, :].cpu().numpy()
+    table = m.engine.P["item_emb"].cpu().numpy().copy()
+    table[0] = 0
+    for u in range(U):
+        lo = O.canonical_logits(last[u:u + 1], table[item_idx[u]])[0]
+        assert np.array_equal(logits[u].view(np.uint32), lo.view(np.uint32)), u
+        gt, eq = O.rank_counts(lo)
+        assert (int(cgt[u]), int(ceq[u])) == (gt, eq)
+        rank_dev = int(cgt[u]) if ceq[u] == 0 else O.rank_of_target(logits[u])
+        assert rank_dev == O.rank_of_target(lo)
+    assert ceq[0] >= 1
