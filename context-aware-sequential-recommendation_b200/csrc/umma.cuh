@@ -11,6 +11,11 @@
 #pragma once
 #include <stdint.h>
 
+#ifdef CAST_EMU
+// host emulation of this API (tests/emu, test infrastructure): same names and semantics, see the header
+#include "umma_emu.h"
+#else
+
 namespace cast {
 namespace umma {
 
@@ -194,3 +199,5 @@ __device__ __forceinline__ void stage_split_strided(unsigned char* __restrict__ 
 
 }  // namespace umma
 }  // namespace cast
+
+#endif  // !CAST_EMU

@@ -174,6 +174,16 @@ class Engine:
         self.init_parameters(self.seed or 42)
         self._call(self.lib.cast_adam_init_state, self.adam_state.data_ptr(), self.beta1, self.beta2, self._stream())
         self._ctx: Dict[int, SimpleNamespace] = {}
+        # tcgen05 row kernels (csrc/row_umma.cu): per-block weight operand images, rebuilt once per forward pass
+        self.use_rowk = bool(self.lib.cast_rowk_supported(self.H))
+        self.rowk_block: Dict[str, int] = {}
+        if self.use_rowk:
+            names = [f"{tower}.{i}." for tower, nb in self.plan.towers.items() for i in range(nb)]
+            self.rowk_block = {n: j for j, n in enumerate(names)}
+            self.rowk_img_bytes = int(self.lib.cast_rowk_image_bytes(self.H))
+            self.rowk_img = torch.zeros(max(1, len(names)) * self.rowk_img_bytes, dtype=torch.uint8, device=self.device)
+            ptrs = [self.P[n + w].data_ptr() for n in names for w in ("q.w", "k.w", "v.w", "ffn1.w", "ffn2.w")]
+            self.rowk_wptrs = (C.c_void_p * len(ptrs))(*ptrs)
         self.world_size = 1
         self.grad_allreduce = None  # set by dist.attach(); called between backward and Adam
         self.shard = None           # set by dist.attach(shard_item_table=True): row-sharded item-table update
@@ -365,10 +375,17 @@ class Engine:
         x = x_in
         nb = len(tb.blocks)
         fused = self.use_fused and bool(self.lib.cast_fused_supported(H))
+        rowk = self.rowk_active()
         P = self.P
         for i, b in enumerate(tb.blocks):
             pre = f"{tower}.{i}."
-            if fused:
+            if rowk:
+                self._call(self.lib.cast_rowk_ln_qkv_fwd, x.data_ptr(), P[pre + "ln1.gamma"].data_ptr(),
+                           P[pre + "ln1.beta"].data_ptr(), P[pre + "q.b"].data_ptr(), P[pre + "k.b"].data_ptr(),
+                           P[pre + "v.b"].data_ptr(), self.rowk_image(pre), c.N, H, 1e-8, b.qn.data_ptr(),
+                           b.Q.data_ptr(), b.K.data_ptr(), b.V.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
+                           b.kmask.data_ptr(), b.qmask.data_ptr(), self._stream())
+            elif fused:
                 self._call(self.lib.cast_ln_qkv_fwd, x.data_ptr(), P[pre + "ln1.gamma"].data_ptr(),
                            P[pre + "ln1.beta"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "q.b"].data_ptr(),
                            P[pre + "k.w"].data_ptr(), P[pre + "k.b"].data_ptr(), P[pre + "v.w"].data_ptr(),
@@ -389,7 +406,13 @@ class Engine:
                        b.qn.data_ptr(), b.kmask.data_ptr(), b.qmask.data_ptr(), B, T, H, h, rate, self.seed,
                        self.step_ptr, block_site(tower, i, 1), ids.data_ptr(), b.y.data_ptr(), self._p(attn),
                        b.rmax.data_ptr(), b.rlinv.data_ptr(), self._stream())
-            if fused:
+            if rowk:
+                self._call(self.lib.cast_rowk_ln_ffn_fwd, b.y.data_ptr(), P[pre + "ln2.gamma"].data_ptr(),
+                           P[pre + "ln2.beta"].data_ptr(), P[pre + "ffn1.b"].data_ptr(), P[pre + "ffn2.b"].data_ptr(),
+                           self.rowk_image(pre), ids.data_ptr(), rate, self.seed, self.step_ptr,
+                           block_site(tower, i, 2), block_site(tower, i, 3), c.N, H, 1e-8, b.zn.data_ptr(),
+                           b.h1d.data_ptr(), b.xout.data_ptr(), b.mu2.data_ptr(), b.rs2.data_ptr(), self._stream())
+            elif fused:
                 self._call(self.lib.cast_ln_ffn_fwd, b.y.data_ptr(), P[pre + "ln2.gamma"].data_ptr(),
                            P[pre + "ln2.beta"].data_ptr(), P[pre + "ffn1.w"].data_ptr(), P[pre + "ffn1.b"].data_ptr(),
                            P[pre + "ffn2.w"].data_ptr(), P[pre + "ffn2.b"].data_ptr(), ids.data_ptr(), rate,
@@ -535,10 +558,19 @@ class Engine:
         return c.dsrc
 
     # ------------------------------------------------------------------ whole model
+    def rowk_active(self):
+        return self.use_rowk and self.use_fused and bool(self.rowk_block)
+
+    def rowk_image(self, pre: str) -> int:
+        return self.rowk_img.data_ptr() + self.rowk_block[pre] * self.rowk_img_bytes
+
     def forward(self, c, train: bool, want_attn: bool = False):
         """Builds seq_emb [N,H] from the ids already resident in c.keys3 / c.cids; returns the buffer."""
         plan = self.plan
         ids = c.keys3[0]
+        if self.rowk_active():  # weights moved since the last step: refresh the tf32 hi/lo operand images
+            self._call(self.lib.cast_rowk_presplit, self.rowk_wptrs, len(self.rowk_block), self.H,
+                       self.rowk_img.data_ptr(), self.rowk_img.numel(), self._stream())
         streams: Dict[str, torch.Tensor] = {}
         for j, (tname, key) in enumerate((("time_emb", "time"), ("hours_emb", "hours"), ("days_emb", "days"))):
             if tname in plan.tables:

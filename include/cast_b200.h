@@ -121,6 +121,26 @@ int cast_ln_ffn_fwd(const float* y, const float* gamma, const float* beta, const
                     const float* W2, const float* b2, const int* ids, float drop_rate, unsigned long long seed,
                     const unsigned long long* step, int site_hidden, int site_out, long N, int H, float eps, float* zn,
                     float* h1d, float* xout, float* mean, float* rstd, void* stream);
+/* ---- the same forward row kernels on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulators) -----
+ * cast_rowk_supported(H): hidden_units the tcgen05 row kernels accept (their shared-memory plan must fit 227 KB).
+ * cast_rowk_presplit: once per step (weights change with every Adam update), splits the five [H,H] matrices of each
+ *   block {Wq, Wk, Wv, W1, W2} (`weights` = HOST array of nblocks*5 device pointers) into tf32 hi/lo operand images
+ *   (K-major UMMA layout; transposed and plain forms) at images + b * cast_rowk_image_bytes(H).
+ * cast_rowk_ln_qkv_fwd / cast_rowk_ln_ffn_fwd: same contract as cast_ln_qkv_fwd / cast_ln_ffn_fwd, weights taken from
+ *   the block's images.  cast_rowk_status reports (and clears) the kernels' barrier watchdog; it synchronises. */
+int cast_rowk_supported(int H);
+size_t cast_rowk_image_bytes(int H);
+int cast_rowk_presplit(const float* const* weights, int nblocks, int H, void* images, size_t image_bytes, void* stream);
+int cast_rowk_ln_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* bq, const float* bk,
+                         const float* bv, const void* images, long N, int H, float eps, float* qn, float* Q, float* K,
+                         float* V, float* mean, float* rstd, float* kmask, float* qmask, void* stream);
+int cast_rowk_ln_ffn_fwd(const float* y, const float* gamma, const float* beta, const float* b1, const float* b2,
+                         const void* images, const int* ids, float drop_rate, unsigned long long seed,
+                         const unsigned long long* step, int site_hidden, int site_out, long N, int H, float eps,
+                         float* zn, float* h1d, float* xout, float* mean, float* rstd, void* stream);
+int cast_rowk_status(int* timed_out);
+/* test / tuning hook: cap the persistent grid (default and maximum: one CTA per SM) */
+int cast_rowk_set_grid(int max_ctas);
 /* Row-kernel backend (A/B testing): bit 0 = backward kernels on the tensor cores (mma.sync 3xTF32), bit 1 = forward
  * kernels; default 3; 0 = FP32 FFMA kernels. */
 int cast_fused_set_backend(int backend);

@@ -54,6 +54,21 @@ def no_drop(site, x):
     return x
 
 
+# ReLU sites: the FFN hidden activation of a block carries its dropout site id (block_site(.., 2)); the two dense
+# layers of the CAST merge MLP are SITE_MLP0 / SITE_MLP1.  RELU_HOOK(site, pre) -> bool tensor (where the unit is
+# treated as active) lets a parity test resolve the derivative AT the kink: a pre-activation within fp32 noise of 0
+# (|pre| ~ 1e-6 for 50-term dot products) has an implementation-defined sign, and one flipped unit moves an
+# un-normalised weight gradient by O(1e-3) relative at BASELINE batch sizes.  Default (None): plain torch.relu.
+SITE_MLP0, SITE_MLP1 = 9100, 9101
+RELU_HOOK = None
+
+
+def _relu(site, pre):
+    if RELU_HOOK is None:
+        return torch.relu(pre)
+    return pre * RELU_HOOK(site, pre.detach()).to(pre.dtype)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # modules.py
 # ----------------------------------------------------------------------------------------------------------
@@ -119,7 +134,7 @@ def multihead_attention(queries, keys, wq, bq, wk, bk, wv, bv, num_heads, drop, 
 
 def feedforward(inputs, w1, b1, w2, b2, drop, site_hidden, site_out):
     """modules.py:280-318 — conv1d(k=1) == dense; ReLU; dropout; dense; dropout; += inputs."""
-    outputs = torch.relu(inputs @ w1 + b1)                          # :298-300
+    outputs = _relu(site_hidden, inputs @ w1 + b1)                  # :298-300
     outputs = drop(site_hidden, outputs)                            # :301
     outputs = outputs @ w2 + b2                                     # :304-306
     outputs = drop(site_out, outputs)                               # :307
@@ -129,8 +144,8 @@ def feedforward(inputs, w1, b1, w2, b2, drop, site_hidden, site_out):
 
 def mlp(inputs, w0, b0, w1, b1):
     """modules.py:321-335 — both dense layers carry ReLU."""
-    h = torch.relu(inputs @ w0 + b0)
-    h = torch.relu(h @ w1 + b1)
+    h = _relu(SITE_MLP0, inputs @ w0 + b0)
+    h = _relu(SITE_MLP1, h @ w1 + b1)
     return h
 
 

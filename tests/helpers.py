@@ -112,3 +112,56 @@ def synth_batch(B, T, itemnum, seed, mean_len=None, max_bins=200):
     dys = np.where(live, rng.randint(1, 8, (B, T)), 0).astype(np.int32)
     return {"u": np.arange(1, B + 1, dtype=np.int32), "seq": seq, "pos": pos, "neg": neg, "timeseq": ts,
             "hours": hrs, "days": dys}
+
+
+KINK_TAU = 2e-5
+
+
+class relu_kink_hook:
+    """Context manager: while active, the oracle takes the ReLU derivative of units whose pre-activation lies within
+    KINK_TAU of zero (fp32 noise of the H-term dot products; a handful of units per block at BASELINE sizes) from the
+    device buffers of the step that has just run — everywhere else the oracle's own sign stands.  `self.ambiguous`
+    counts the overridden units, `self.total` all units seen, so tests can assert the override stays negligible."""
+
+    def __init__(self, eng, c, rate):
+        self.eng, self.c, self.rate = eng, c, rate
+        self.ambiguous = self.total = 0
+
+    def device_active(self, site):
+        c = self.c
+        if site == O.SITE_MLP0:
+            return (c.mlp_h > 0).cpu(), None
+        if site == O.SITE_MLP1:   # cast_9 masks the MLP output afterwards: padded rows read 0 there, which is their
+            return (c.mlp_out > 0).cpu(), None   # derivative as well (the mask multiplies the gradient)
+        tower = {v: k for k, v in O.TOWER_ID.items()}[site // 1000]
+        blk = c.tw[tower].blocks[(site % 1000) // 10]
+        act = (blk.h1d > 0).cpu()            # active AND kept by the hidden dropout
+        keep = None
+        if self.rate > 0:
+            eng = self.eng
+            n = act.numel()
+            k = torch.empty(n, dtype=torch.uint8, device=eng.device)
+            rc = eng.lib.cast_dropout_keep(self.rate, eng.seed, eng.step_ptr, site, n, k.data_ptr(), eng._stream())
+            assert rc == 0
+            keep = k.cpu().bool().reshape(act.shape)
+        return act, keep
+
+    def __call__(self, site, pre):
+        mask = pre > 0
+        amb = pre.abs() < KINK_TAU
+        self.total += pre.numel()
+        if bool(amb.any()):
+            act, keep = self.device_active(site)
+            act = act.reshape(pre.shape)
+            sel = amb if keep is None else amb & keep.reshape(pre.shape)   # a dropped unit has no gradient anyway
+            self.ambiguous += int(sel.sum())
+            mask = torch.where(sel, act, mask)
+        return mask
+
+    def __enter__(self):
+        O.RELU_HOOK = self
+        return self
+
+    def __exit__(self, *exc):
+        O.RELU_HOOK = None
+        return False
