@@ -42,6 +42,7 @@ SIGNATURES = {
     "cast_rowk_ln_ffn_fwd": (I, [P, P, P, P, P, P, P, F, U64, P, I, I, L, I, F, P, P, P, P, P, P]),
     "cast_rowk_status": (I, [P]),
     "cast_rowk_set_grid": (I, [I]),
+    "cast_rowk_set_trace": (I, [P]),
     "cast_block_bwd_workspace_bytes": (SZ, [L, I]),
     "cast_ffn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, F, U64, P, I, L, I, P, P, P, SZ, P]),
     "cast_qkv_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, L, I, P, P, P, SZ, P]),

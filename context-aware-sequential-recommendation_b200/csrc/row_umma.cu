@@ -7,8 +7,8 @@
 // with the same arithmetic as the mma.sync kernels of fused_mma.cuh (3xTF32 operand split: x = hi + lo,
 // A*B ~= lo*hi + hi*lo + hi*hi, fp32 accumulation) and the same saved tensors for backward.
 //
-// Structure (persistent CTAs, one per SM, 256 threads, 128-row tiles; thread t owns row t & 127 = TMEM lane, column half
-// t >> 7: columns [0,32) or [32,H)):
+// Structure (persistent CTAs, one per SM; 16 "row" warps + 1 MMA warp; every CTA owns a contiguous, balanced range of
+// rows walked in 128-row tiles; row thread t owns row t & 127 = TMEM lane and the 16 columns of quarter t >> 7):
 //   * the row tile [128, H] is ONE contiguous block of global memory: it is brought into a dense shared-memory tile with
 //     16-byte cp.async (next tile prefetched while the current one is processed) and every output tile leaves through a
 //     dense tile + coalesced 16-byte stores, so global traffic is fully coalesced although threads own rows;
@@ -16,8 +16,11 @@
 //   * the operand is split into tf32 hi / lo once per element and stored in the K-major no-swizzle UMMA layout of
 //     umma.cuh (16-byte stores, conflict free); weights come pre-split as images made once per step by
 //     cast_rowk_presplit and are bulk-copied (cp.async.bulk + mbarrier transaction bytes) once per CTA;
-//   * one thread issues 3 x ceil(H/8) tcgen05.mma per product (M = 128, N = 64 or 128) and commits to an mbarrier;
-//     the epilogue reads the accumulator with tcgen05.ld (thread <-> row) and applies bias / ReLU / dropout / residual /
+//   * a dedicated warp issues 3 x ceil(H/8) tcgen05.mma per product (M = 128, N = 64 or 128) as soon as the row warps
+//     have arrived on the operand's mbarrier, and commits to a second mbarrier; the row warps never wait for the issue
+//     loop, only for the product they need next.  In ln_qkv_fwd the K|V product (operand = raw x) is issued first and
+//     runs under the LayerNorm; the Q product runs under the K and V epilogues;
+//   * the epilogue reads the accumulator with tcgen05.ld (thread <-> row) and applies bias / ReLU / dropout / residual /
 //     padding mask in registers.
 #include "cast_rt.cuh"
 #include "mma_tf32.cuh"
@@ -26,7 +29,8 @@
 namespace cast {
 
 constexpr int RU_ROWS = 128;
-constexpr int RU_THREADS = 256;
+constexpr int RU_ROW_THREADS = 512;          // 16 warps: 4 lane quarters x 4 column quarters
+constexpr int RU_THREADS = RU_ROW_THREADS + 32;  // + the MMA warp
 constexpr int RU_PA = RU_ROWS * 16 + 16;  // slab pitch of a 128-row operand tile (bytes)
 constexpr int RU_NIMG = 9;                // weight images per block, see ru_img_offset
 constexpr size_t RU_SMEM_MAX = 232448;    // 227 KB opt-in dynamic shared memory per CTA
@@ -64,39 +68,42 @@ struct RuPresplitArgs {
   const float* w[16][5];  // per block: Wq, Wk, Wv, W1, W2   ([H, H] row-major, [in, out])
 };
 
+// one thread per (image, row n, column k); grid = (ceil(2*NP*KP / 256), RU_NIMG, nblocks)
 __global__ void __launch_bounds__(256) ru_presplit_kernel(RuPresplitArgs a, int H, unsigned char* __restrict__ images) {
   const RuShape s = ru_shape(H);
-  const int blk = blockIdx.x / RU_NIMG, which = blockIdx.x % RU_NIMG;
+  const int blk = blockIdx.z, which = blockIdx.y;
   unsigned char* img = images + (size_t)blk * ru_img_block_bytes(s) + ru_img_offset(s, which);
   const int rows = (which == 1) ? 2 * s.NP : s.NP;
   const int pitch = rows * 16 + 16;
   const int half = s.SL * pitch;
   const int KP = 4 * s.SL;
   const bool transposed = which < 4;
-  for (int idx = threadIdx.x; idx < rows * KP; idx += (int)blockDim.x) {
-    const int n = idx / KP, k = idx - n * KP;
-    const float* W;
-    int nn = n;
-    switch (which) {
-      case 0: case 4: W = a.w[blk][0]; break;
-      case 1: W = a.w[blk][n < s.NP ? 1 : 2]; nn = n < s.NP ? n : n - s.NP; break;
-      case 2: case 7: W = a.w[blk][3]; break;
-      case 3: case 8: W = a.w[blk][4]; break;
-      case 5: W = a.w[blk][1]; break;
-      default: W = a.w[blk][2]; break;
-    }
-    float v = 0.f;
-    if (nn < H && k < H) v = transposed ? W[k * H + nn] : W[nn * H + k];
-    unsigned hi, lo;
-    tf32_split(v, hi, lo);
-    const int off = (k >> 2) * pitch + n * 16 + (k & 3) * 4;
-    *reinterpret_cast<unsigned*>(img + off) = hi;
-    *reinterpret_cast<unsigned*>(img + half + off) = lo;
+  const int idx = blockIdx.x * (int)blockDim.x + threadIdx.x;
+  if (idx >= rows * KP) return;
+  int n, k;  // the fast index follows the unit stride of the source so that the global reads coalesce
+  if (transposed) { k = idx / rows; n = idx - k * rows; } else { n = idx / KP; k = idx - n * KP; }
+  const float* W;
+  int nn = n;
+  switch (which) {
+    case 0: case 4: W = a.w[blk][0]; break;
+    case 1: W = a.w[blk][n < s.NP ? 1 : 2]; nn = n < s.NP ? n : n - s.NP; break;
+    case 2: case 7: W = a.w[blk][3]; break;
+    case 3: case 8: W = a.w[blk][4]; break;
+    case 5: W = a.w[blk][1]; break;
+    default: W = a.w[blk][2]; break;
   }
+  float v = 0.f;
+  if (nn < H && k < H) v = transposed ? W[k * H + nn] : W[nn * H + k];
+  unsigned hi, lo;
+  tf32_split(v, hi, lo);
+  const int off = (k >> 2) * pitch + n * 16 + (k & 3) * 4;
+  *reinterpret_cast<unsigned*>(img + off) = hi;
+  *reinterpret_cast<unsigned*>(img + half + off) = lo;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// device helpers.  Thread t: row r = t & 127, half ch = t >> 7, columns c0 + i (i < 32, c0 = 32 ch), slabs 8 ch + i (i < 8).
+// device helpers.  Row thread t: row r = t & 127, column quarter qd = t >> 7, columns c0 + i (i < 16, c0 = 16 qd),
+// slabs 4 qd + i (i < 4).
 
 #ifndef CAST_EMU
 __device__ __forceinline__ void ru_cp_async16(float* dst, const float* src, int bytes) {  // bytes in [0,16]: rest zero
@@ -109,18 +116,20 @@ inline void ru_cp_async16(float* dst, const float* src, int bytes) {
 }
 #endif
 
+__device__ __forceinline__ void ru_row_sync() { umma::named_sync(1, RU_ROW_THREADS); }
+
 // dense tile <- nvalid floats starting at src (a contiguous row block of a [N, H] tensor), zero up to ntotal floats
 __device__ __forceinline__ void ru_tile_load_async(float* __restrict__ tile, const float* __restrict__ src, long nvalid,
                                                    int ntotal) {
   const int t = threadIdx.x;
   if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    for (int i = 4 * t; i < ntotal; i += 4 * RU_THREADS) {
+    for (int i = 4 * t; i < ntotal; i += 4 * RU_ROW_THREADS) {
       long left = (nvalid - i) * 4;
       const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
       ru_cp_async16(tile + i, bytes > 0 ? src + i : src, bytes);
     }
   } else {  // unaligned base pointer: plain loads (never the case for the engine's buffers)
-    for (int i = t; i < ntotal; i += RU_THREADS) tile[i] = i < nvalid ? src[i] : 0.f;
+    for (int i = t; i < ntotal; i += RU_ROW_THREADS) tile[i] = i < nvalid ? src[i] : 0.f;
   }
   cp_async_commit();
 }
@@ -130,20 +139,20 @@ __device__ __forceinline__ void ru_tile_store(float* __restrict__ dst, const flo
   const int t = threadIdx.x;
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const int n4 = (int)(nvalid >> 2);
-    for (int i = t; i < n4; i += RU_THREADS)
+    for (int i = t; i < n4; i += RU_ROW_THREADS)
       reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(tile)[i];
-    for (int i = 4 * n4 + t; i < nvalid; i += RU_THREADS) dst[i] = tile[i];
+    for (int i = 4 * n4 + t; i < nvalid; i += RU_ROW_THREADS) dst[i] = tile[i];
   } else {
-    for (int i = t; i < nvalid; i += RU_THREADS) dst[i] = tile[i];
+    for (int i = t; i < nvalid; i += RU_ROW_THREADS) dst[i] = tile[i];
   }
 }
 
-// this thread's 32 columns of its row: x[i] = tile[r][c0 + i] (0 for columns >= H)
-__device__ __forceinline__ void ru_row_load(const float* __restrict__ tile, int r, int c0, int H, float (&x)[32]) {
+// this thread's 16 columns of its row: x[i] = tile[r][c0 + i] (0 for columns >= H)
+__device__ __forceinline__ void ru_row_load(const float* __restrict__ tile, int r, int c0, int H, float (&x)[16]) {
   const float* p = tile + r * H + c0;
   if ((H & 1) == 0) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < 16; i += 2) {
       if (c0 + i < H) {
         const float2 v = *reinterpret_cast<const float2*>(p + i);
         x[i] = v.x;
@@ -154,29 +163,29 @@ __device__ __forceinline__ void ru_row_load(const float* __restrict__ tile, int 
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = (c0 + i < H) ? p[i] : 0.f;
+    for (int i = 0; i < 16; ++i) x[i] = (c0 + i < H) ? p[i] : 0.f;
   }
 }
 
-__device__ __forceinline__ void ru_row_store(float* __restrict__ tile, int r, int c0, int H, const float (&x)[32]) {
+__device__ __forceinline__ void ru_row_store(float* __restrict__ tile, int r, int c0, int H, const float (&x)[16]) {
   float* p = tile + r * H + c0;
   if ((H & 1) == 0) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2)
+    for (int i = 0; i < 16; i += 2)
       if (c0 + i < H) *reinterpret_cast<float2*>(p + i) = make_float2(x[i], x[i + 1]);
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < 16; ++i)
       if (c0 + i < H) p[i] = x[i];
   }
 }
 
 // split this thread's columns into tf32 hi / lo and store them as its slabs of the operand tile (x is 0 beyond H)
-__device__ __forceinline__ void ru_stage(unsigned char* __restrict__ hi, unsigned char* __restrict__ lo, int r, int ch,
-                                         int SL, const float (&x)[32]) {
+__device__ __forceinline__ void ru_stage(unsigned char* __restrict__ hi, unsigned char* __restrict__ lo, int r, int qd,
+                                         int SL, const float (&x)[16]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int s = 8 * ch + i;
+  for (int i = 0; i < 4; ++i) {
+    const int s = 4 * qd + i;
     if (s < SL) {
       uint4 h, l;
       tf32_split(x[4 * i + 0], h.x, l.x);
@@ -187,6 +196,15 @@ __device__ __forceinline__ void ru_stage(unsigned char* __restrict__ hi, unsigne
       *reinterpret_cast<uint4*>(lo + s * RU_PA + r * 16) = l;
     }
   }
+}
+
+// the row warps' "operand tile is staged" signal: every writer makes its generic-proxy stores visible to the async
+// proxy, the warp converges, one lane arrives (barrier count = 16 warps)
+__device__ __forceinline__ void ru_operand_ready(uint64_t* bar) {
+  umma::fence_smem_to_async();
+  umma::fence_before_sync();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
 }
 
 // D[128 x N] (tensor memory, columns from tmem_d) = A[128 x 8KS] * B[N x 8KS]^T with the 3xTF32 split; ONE thread.
@@ -206,49 +224,84 @@ __device__ __forceinline__ void ru_issue(uint32_t tmem_d, uint32_t a_hi, uint32_
   }
 }
 
+// optional phase trace (tuning): row thread 0 of every CTA stamps clock64() at phase boundaries, [cta][tile slot < 4][16]
+__device__ long long* g_rowk_trace = nullptr;
+#ifndef CAST_EMU
+#define RU_STAMP(slot, k)                                                                      \
+  if (trace && threadIdx.x == 0 && (slot) < 4) trace[((long)blockIdx.x * 4 + (slot)) * 16 + (k)] = clock64()
+#else
+#define RU_STAMP(slot, k)
+#endif
+
 // a watchdog instead of a hang: a barrier phase that never completes is reported through cast_rowk_status
 __device__ int g_rowk_timeout = 0;
 __device__ __forceinline__ void ru_wait(uint64_t* bar, uint32_t parity) {
   if (!umma::mbar_wait(bar, parity, 1u << 22)) g_rowk_timeout = 1;
 }
 
-// LayerNorm of the row held as two column halves by threads t and t ^ 128 (modules.py:74-78: biased variance, eps inside
-// the sqrt).  y = gamma * ((x - mean) * rstd) + beta for columns < H, 0 beyond.  red: [3][128][2] floats.
-// Returns the row sums of x and y (for the zero-sum flags of modules.py:222,248); has two block barriers inside and
-// leaves a third partial (sum of y) in red[2] for the caller to read after ITS next barrier.
+// balanced partition of the N rows over the persistent grid: every CTA owns rpc consecutive rows (a multiple of 4, so
+// that tile base addresses stay 16-byte aligned), walked in 128-row tiles; only the last tile of a CTA is partial
+struct RuRange {
+  long lo, hi;  // rows [lo, hi)
+  int ntiles;
+};
+__device__ __forceinline__ RuRange ru_range(long N, long rpc) {
+  RuRange g;
+  g.lo = (long)blockIdx.x * rpc;
+  g.hi = g.lo + rpc < N ? g.lo + rpc : N;
+  g.ntiles = g.hi > g.lo ? (int)((g.hi - g.lo + RU_ROWS - 1) / RU_ROWS) : 0;
+  return g;
+}
+
+// LayerNorm of the row held as four column quarters by threads r, r+128, r+256, r+384 (modules.py:74-78: biased
+// variance, eps inside the sqrt).  y = gamma * ((x - mean) * rstd) + beta for columns < H, 0 beyond.
+// red: [3][128][4] floats.  Two row barriers inside; the partial sums of y are left in red[2] for the caller to read
+// after ITS next row barrier.  `between` runs right after the first barrier (every thread has finished reading its
+// input row by then).
 struct RuLn {
   float mean, rstd, xsum;
 };
-__device__ __forceinline__ RuLn ru_layernorm(const float (&x)[32], float (&y)[32], const float* __restrict__ gamma,
-                                             const float* __restrict__ beta, float eps, int r, int ch, int c0, int H,
-                                             float* __restrict__ red) {
+template <class F>
+__device__ __forceinline__ RuLn ru_layernorm(const float (&x)[16], float (&y)[16], const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, float eps, int r, int qd, int c0, int H,
+                                             float* __restrict__ red, F&& between) {
   float sp = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) sp += x[i];  // columns >= H hold zeros
-  red[r * 2 + ch] = sp;
-  __syncthreads();
+  for (int i = 0; i < 16; ++i) sp += x[i];  // columns >= H hold zeros
+  red[r * 4 + qd] = sp;
+  ru_row_sync();
+  between();
   RuLn o;
-  o.xsum = red[r * 2] + red[r * 2 + 1];
+  {
+    const float4 p = *reinterpret_cast<const float4*>(red + r * 4);
+    o.xsum = (p.x + p.y) + (p.z + p.w);
+  }
   o.mean = o.xsum / (float)H;
   float qp = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const float d = (c0 + i < H) ? x[i] - o.mean : 0.f;
     y[i] = d;
     qp += d * d;
   }
-  red[256 + r * 2 + ch] = qp;
-  __syncthreads();
-  const float var = (red[256 + r * 2] + red[256 + r * 2 + 1]) / (float)H;
-  o.rstd = 1.0f / sqrtf(var + eps);
+  red[512 + r * 4 + qd] = qp;
+  ru_row_sync();
+  {
+    const float4 p = *reinterpret_cast<const float4*>(red + 512 + r * 4);
+    o.rstd = 1.0f / sqrtf(((p.x + p.y) + (p.z + p.w)) / (float)H + eps);
+  }
   float yp = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = c0 + i;
-    y[i] = (c < H) ? gamma[c] * (y[i] * o.rstd) + beta[c] : 0.f;
-    yp += y[i];
+  for (int i = 0; i < 16; i += 4) {
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c0 + i);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c0 + i);
+    y[i + 0] = (c0 + i + 0 < H) ? g.x * (y[i + 0] * o.rstd) + b.x : 0.f;
+    y[i + 1] = (c0 + i + 1 < H) ? g.y * (y[i + 1] * o.rstd) + b.y : 0.f;
+    y[i + 2] = (c0 + i + 2 < H) ? g.z * (y[i + 2] * o.rstd) + b.z : 0.f;
+    y[i + 3] = (c0 + i + 3 < H) ? g.w * (y[i + 3] * o.rstd) + b.w : 0.f;
+    yp += (y[i] + y[i + 1]) + (y[i + 2] + y[i + 3]);
   }
-  red[512 + r * 2 + ch] = yp;
+  red[1024 + r * 4 + qd] = yp;
   return o;
 }
 
@@ -257,13 +310,14 @@ struct RuLnQkvArgs {
   const unsigned char* img;  // this block's weight images
   float eps;
   float *qn, *Q, *K, *V, *mean, *rstd, *kmask, *qmask;
-  long N, ntiles;
+  long N, rpc;  // rows, rows per CTA
   int H;
 };
 
 __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_qkv_fwd_kernel(RuLnQkvArgs a) {
   CAST_DYN_SMEM(unsigned char, sm);
-  __shared__ __align__(8) uint64_t bars[3];  // weights landed | Q product done | K,V product done
+  // weights landed | x staged | LN(x) staged | K,V product done | Q product done
+  __shared__ __align__(8) uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   const RuShape s = ru_shape(a.H);
   const int H = a.H;
@@ -275,15 +329,18 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_qkv_fwd_kernel(RuLnQkvArg
   float* out0 = tin + s.dense / 4;
   float* out1 = out0 + s.dense / 4;
   float* vec = out1 + s.dense / 4;  // gamma | beta | bq | bk | bv, 64 floats each
-  float* red = vec + 5 * 64;        // [3][128][2]
-  const int t = threadIdx.x, warp = t >> 5, r = t & 127, ch = t >> 7, c0 = 32 * ch;
+  float* red = vec + 5 * 64;        // [3][128][4]
+  const int t = threadIdx.x, warp = t >> 5, r = t & 127, qd = (t >> 7) & 3, c0 = 16 * qd;
   const bool have_cols = c0 < H;
-  const int ntot = RU_ROWS * H;
+  long long* trace = g_rowk_trace;
+  RU_STAMP(0, 0);
 
   if (t == 0) {
     umma::mbar_init(&bars[0], 1);
-    umma::mbar_init(&bars[1], 1);
-    umma::mbar_init(&bars[2], 1);
+    umma::mbar_init(&bars[1], RU_ROW_THREADS / 32);
+    umma::mbar_init(&bars[2], RU_ROW_THREADS / 32);
+    umma::mbar_init(&bars[3], 1);
+    umma::mbar_init(&bars[4], 1);
   }
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
   for (int i = t; i < 5 * 64; i += RU_THREADS) {
@@ -295,94 +352,106 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_qkv_fwd_kernel(RuLnQkvArg
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  if (t == 0) {
-    umma::mbar_arrive_expect_tx(&bars[0], (uint32_t)(s.img1 + s.img2));
-    umma::bulk_g2s(wq, a.img + ru_img_offset(s, 0), (uint32_t)s.img1, &bars[0]);
-    umma::bulk_g2s(wkv, a.img + ru_img_offset(s, 1), (uint32_t)s.img2, &bars[0]);
-  }
-  auto nvalid_of = [&](long tile) {
-    const long left = (a.N - tile * RU_ROWS) * H;
-    return left < (long)ntot ? left : (long)ntot;
-  };
-  if ((long)blockIdx.x < a.ntiles) ru_tile_load_async(tin, a.x + (long)blockIdx.x * ntot, nvalid_of(blockIdx.x), ntot);
+  const RuRange rg = ru_range(a.N, a.rpc);
   const uint32_t idesc_q = umma::idesc_tf32(128, s.NP), idesc_kv = umma::idesc_tf32(128, 2 * s.NP);
-  const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
-  const float *gam = vec, *bet = vec + 64;
 
-  int it = 0;
-  for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-    const long row0 = tile * RU_ROWS, row = row0 + r;
-    const long nvalid = nvalid_of(tile);
-    const uint32_t par = (uint32_t)(it & 1);
+  if (warp == RU_ROW_THREADS / 32) {  // ---------------------------------------------------------------- MMA warp
+    if ((t & 31) == 0 && rg.ntiles > 0) {
+      umma::mbar_arrive_expect_tx(&bars[0], (uint32_t)(s.img1 + s.img2));
+      umma::bulk_g2s(wq, a.img + ru_img_offset(s, 0), (uint32_t)s.img1, &bars[0]);
+      umma::bulk_g2s(wkv, a.img + ru_img_offset(s, 1), (uint32_t)s.img2, &bars[0]);
+      ru_wait(&bars[0], 0);
+      for (int it = 0; it < rg.ntiles; ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        ru_wait(&bars[1], par);  // raw x staged: K | V = x [Wk | Wv]
+        umma::fence_after_sync();
+        ru_issue(tmem + (uint32_t)s.NP, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(wkv),
+                 umma::smem_u32(wkv + s.img2 / 2), (uint32_t)(2 * s.NP * 16 + 16), s.KS, idesc_kv, 0u);
+        umma::mma_commit(&bars[3]);
+        ru_wait(&bars[2], par);  // LN(x) staged (the row warps waited for the K|V product first): Q = LN(x) Wq
+        umma::fence_after_sync();
+        ru_issue(tmem, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(wq), umma::smem_u32(wq + s.img1 / 2),
+                 (uint32_t)(s.NP * 16 + 16), s.KS, idesc_q, 0u);
+        umma::mma_commit(&bars[4]);
+      }
+    }
+    __syncwarp();
+  } else {  // ------------------------------------------------------------------------------------------ row warps
+    const int ntot = RU_ROWS * H;
+    auto rows_of = [&](int it) {
+      const long left = rg.hi - (rg.lo + (long)it * RU_ROWS);
+      return left < RU_ROWS ? left : (long)RU_ROWS;
+    };
+    if (rg.ntiles > 0) ru_tile_load_async(tin, a.x + rg.lo * H, rows_of(0) * H, ntot);
+    const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
+    for (int it = 0; it < rg.ntiles; ++it) {
+      const long row0 = rg.lo + (long)it * RU_ROWS, row = row0 + r;
+      const long vrows = rows_of(it), nvalid = vrows * H;
+      const uint32_t par = (uint32_t)(it & 1);
+      cp_async_wait<0>();
+      ru_row_sync();
+      RU_STAMP(it, 1);
+      float x[16], q[16];
+      ru_row_load(tin, r, c0, H, x);
+      ru_stage(a_hi, a_lo, r, qd, s.SL, x);  // (the previous tile's Q product, the last reader of the operand, is done)
+      ru_operand_ready(&bars[1]);
+      RU_STAMP(it, 2);
+      const RuLn ln = ru_layernorm(x, q, vec, vec + 64, a.eps, r, qd, c0, H, red, [&]() {
+        if (it + 1 < rg.ntiles) ru_tile_load_async(tin, a.x + (row0 + RU_ROWS) * H, rows_of(it + 1) * H, ntot);
+      });
+      RU_STAMP(it, 3);
+      ru_row_store(out0, r, c0, H, q);
+      ru_wait(&bars[3], par);  // K | V accumulated; the operand tile is free again
+      umma::fence_after_sync();
+      RU_STAMP(it, 4);
+      ru_stage(a_hi, a_lo, r, qd, s.SL, q);
+      ru_operand_ready(&bars[2]);
+      ru_row_sync();
+      RU_STAMP(it, 5);
+      if (qd == 0 && row < rg.hi) {
+        const float4 p = *reinterpret_cast<const float4*>(red + 1024 + r * 4);
+        const float ysum = (p.x + p.y) + (p.z + p.w);
+        a.mean[row] = ln.mean;
+        a.rstd[row] = ln.rstd;
+        if (a.kmask) a.kmask[row] = ln.xsum != 0.f ? 1.f : 0.f;
+        if (a.qmask) a.qmask[row] = ysum != 0.f ? 1.f : 0.f;
+      }
+      ru_tile_store(a.qn + row0 * H, out0, nvalid);
+      float v[16];
+      if (have_cols) {  // K = x Wk + bk
+        umma::tmem_ld16(tmem + lane_base + (uint32_t)(s.NP + c0), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += vec[3 * 64 + c0 + i];
+        ru_row_store(out1, r, c0, H, v);
+      }
+      ru_row_sync();
+      RU_STAMP(it, 6);
+      ru_tile_store(a.K + row0 * H, out1, nvalid);
+      if (have_cols) {  // V = x Wv + bv
+        umma::tmem_ld16(tmem + lane_base + (uint32_t)(2 * s.NP + c0), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += vec[4 * 64 + c0 + i];
+        ru_row_store(out0, r, c0, H, v);
+      }
+      ru_row_sync();
+      RU_STAMP(it, 7);
+      ru_tile_store(a.V + row0 * H, out0, nvalid);
+      ru_wait(&bars[4], par);
+      umma::fence_after_sync();
+      RU_STAMP(it, 8);
+      if (have_cols) {  // Q = LN(x) Wq + bq
+        umma::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += vec[2 * 64 + c0 + i];
+        ru_row_store(out1, r, c0, H, v);
+      }
+      umma::fence_before_sync();
+      ru_row_sync();
+      ru_tile_store(a.Q + row0 * H, out1, nvalid);
+      RU_STAMP(it, 9);
+    }
     cp_async_wait<0>();
-    __syncthreads();
-    float x[32], q[32];
-    ru_row_load(tin, r, c0, H, x);
-    const RuLn ln = ru_layernorm(x, q, gam, bet, a.eps, r, ch, c0, H, red);
-    // (everybody has read its row of `tin` before the first barrier inside ru_layernorm)
-    if (tile + gridDim.x < a.ntiles)
-      ru_tile_load_async(tin, a.x + (tile + gridDim.x) * ntot, nvalid_of(tile + gridDim.x), ntot);
-    ru_row_store(out0, r, c0, H, q);
-    ru_stage(a_hi, a_lo, r, ch, s.SL, q);
-    umma::fence_smem_to_async();
-    __syncthreads();
-    if (ch == 0 && row < a.N) {
-      const float ysum = red[512 + r * 2] + red[512 + r * 2 + 1];
-      a.mean[row] = ln.mean;
-      a.rstd[row] = ln.rstd;
-      if (a.kmask) a.kmask[row] = ln.xsum != 0.f ? 1.f : 0.f;
-      if (a.qmask) a.qmask[row] = ysum != 0.f ? 1.f : 0.f;
-    }
-    if (t == 0) {
-      umma::fence_after_sync();
-      if (it == 0) ru_wait(&bars[0], 0);
-      ru_issue(tmem, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(wq),
-               umma::smem_u32(wq + s.img1 / 2), (uint32_t)(s.NP * 16 + 16), s.KS, idesc_q, 0u);
-      umma::mma_commit(&bars[1]);
-    }
-    ru_tile_store(a.qn + row0 * H, out0, nvalid);
-    ru_wait(&bars[1], par);  // the Q product has consumed the operand tile
-    umma::fence_after_sync();
-    ru_stage(a_hi, a_lo, r, ch, s.SL, x);
-    umma::fence_smem_to_async();
-    __syncthreads();
-    if (t == 0) {
-      umma::fence_after_sync();
-      ru_issue(tmem + (uint32_t)s.NP, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(wkv),
-               umma::smem_u32(wkv + s.img2 / 2), (uint32_t)(2 * s.NP * 16 + 16), s.KS, idesc_kv, 0u);
-      umma::mma_commit(&bars[2]);
-    }
-    float v[32];
-    if (have_cols) {  // Q = LN(x) Wq + bq
-      umma::tmem_ld32(tmem + lane_base + (uint32_t)c0, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += vec[2 * 64 + ((c0 + i) & 63)];
-      ru_row_store(out1, r, c0, H, v);
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    ru_tile_store(a.Q + row0 * H, out1, nvalid);
-    ru_wait(&bars[2], par);
-    umma::fence_after_sync();
-    if (have_cols) {  // K = x Wk + bk
-      umma::tmem_ld32(tmem + lane_base + (uint32_t)(s.NP + c0), v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += vec[3 * 64 + ((c0 + i) & 63)];
-      ru_row_store(out0, r, c0, H, v);
-    }
-    __syncthreads();
-    ru_tile_store(a.K + row0 * H, out0, nvalid);
-    if (have_cols) {  // V = x Wv + bv
-      umma::tmem_ld32(tmem + lane_base + (uint32_t)(2 * s.NP + c0), v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += vec[4 * 64 + ((c0 + i) & 63)];
-      ru_row_store(out1, r, c0, H, v);
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    ru_tile_store(a.V + row0 * H, out1, nvalid);
   }
-  cp_async_wait<0>();
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_free(tmem, 256);
@@ -397,13 +466,14 @@ struct RuLnFfnArgs {
   const unsigned long long* step;
   int site_h, site_o;
   float *zn, *h1d, *xout, *mean, *rstd;
-  long N, ntiles;
+  long N, rpc;
   int H;
 };
 
 __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_ffn_fwd_kernel(RuLnFfnArgs a) {
   CAST_DYN_SMEM(unsigned char, sm);
-  __shared__ __align__(8) uint64_t bars[3];  // weights landed | first product done | second product done
+  // weights landed | LN(y) staged | hidden staged | first product done | second product done
+  __shared__ __align__(8) uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   const RuShape s = ru_shape(a.H);
   const int H = a.H;
@@ -416,14 +486,17 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_ffn_fwd_kernel(RuLnFfnArg
   float* out1 = out0 + s.dense / 4;
   float* vec = out1 + s.dense / 4;  // gamma | beta | b1 | b2
   float* red = vec + 4 * 64;
-  const int t = threadIdx.x, warp = t >> 5, r = t & 127, ch = t >> 7, c0 = 32 * ch;
+  const int t = threadIdx.x, warp = t >> 5, r = t & 127, qd = (t >> 7) & 3, c0 = 16 * qd;
   const bool have_cols = c0 < H;
-  const int ntot = RU_ROWS * H;
+  long long* trace = g_rowk_trace;
+  RU_STAMP(0, 0);
 
   if (t == 0) {
     umma::mbar_init(&bars[0], 1);
-    umma::mbar_init(&bars[1], 1);
-    umma::mbar_init(&bars[2], 1);
+    umma::mbar_init(&bars[1], RU_ROW_THREADS / 32);
+    umma::mbar_init(&bars[2], RU_ROW_THREADS / 32);
+    umma::mbar_init(&bars[3], 1);
+    umma::mbar_init(&bars[4], 1);
   }
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
   for (int i = t; i < 4 * 64; i += RU_THREADS) {
@@ -435,108 +508,120 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_ffn_fwd_kernel(RuLnFfnArg
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  if (t == 0) {
-    umma::mbar_arrive_expect_tx(&bars[0], (uint32_t)(2 * s.img1));
-    umma::bulk_g2s(w1, a.img + ru_img_offset(s, 2), (uint32_t)(2 * s.img1), &bars[0]);  // W1T and W2T are adjacent
-  }
-  auto nvalid_of = [&](long tile) {
-    const long left = (a.N - tile * RU_ROWS) * H;
-    return left < (long)ntot ? left : (long)ntot;
-  };
-  if ((long)blockIdx.x < a.ntiles) ru_tile_load_async(tin, a.y + (long)blockIdx.x * ntot, nvalid_of(blockIdx.x), ntot);
+  const RuRange rg = ru_range(a.N, a.rpc);
   const uint32_t idesc = umma::idesc_tf32(128, s.NP);
-  const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
   const uint32_t wpitch = (uint32_t)(s.NP * 16 + 16);
-  const Drop dh = make_drop(a.rate, a.seed, a.step, a.site_h);
-  const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
 
-  int it = 0;
-  for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-    const long row0 = tile * RU_ROWS, row = row0 + r;
-    const long nvalid = nvalid_of(tile);
-    const uint32_t par = (uint32_t)(it & 1);
+  if (warp == RU_ROW_THREADS / 32) {  // ---------------------------------------------------------------- MMA warp
+    if ((t & 31) == 0 && rg.ntiles > 0) {
+      umma::mbar_arrive_expect_tx(&bars[0], (uint32_t)(2 * s.img1));
+      umma::bulk_g2s(w1, a.img + ru_img_offset(s, 2), (uint32_t)(2 * s.img1), &bars[0]);  // W1T and W2T are adjacent
+      ru_wait(&bars[0], 0);
+      for (int it = 0; it < rg.ntiles; ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        ru_wait(&bars[1], par);
+        umma::fence_after_sync();
+        ru_issue(tmem, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w1), umma::smem_u32(w1 + s.img1 / 2),
+                 wpitch, s.KS, idesc, 0u);
+        umma::mma_commit(&bars[3]);
+        ru_wait(&bars[2], par);
+        umma::fence_after_sync();
+        ru_issue(tmem + (uint32_t)s.NP, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w2),
+                 umma::smem_u32(w2 + s.img1 / 2), wpitch, s.KS, idesc, 0u);
+        umma::mma_commit(&bars[4]);
+      }
+    }
+    __syncwarp();
+  } else {  // ------------------------------------------------------------------------------------------ row warps
+    const int ntot = RU_ROWS * H;
+    auto rows_of = [&](int it) {
+      const long left = rg.hi - (rg.lo + (long)it * RU_ROWS);
+      return left < RU_ROWS ? left : (long)RU_ROWS;
+    };
+    if (rg.ntiles > 0) ru_tile_load_async(tin, a.y + rg.lo * H, rows_of(0) * H, ntot);
+    const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
+    const Drop dh = make_drop(a.rate, a.seed, a.step, a.site_h);
+    const Drop dout = make_drop(a.rate, a.seed, a.step, a.site_o);
+    for (int it = 0; it < rg.ntiles; ++it) {
+      const long row0 = rg.lo + (long)it * RU_ROWS, row = row0 + r;
+      const long vrows = rows_of(it), nvalid = vrows * H;
+      const uint32_t par = (uint32_t)(it & 1);
+      const float m = (row < rg.hi && a.ids) ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;  // fetched early, used last
+      cp_async_wait<0>();
+      ru_row_sync();
+      RU_STAMP(it, 1);
+      float x[16], zn[16];
+      ru_row_load(tin, r, c0, H, x);
+      const RuLn ln = ru_layernorm(x, zn, vec, vec + 64, a.eps, r, qd, c0, H, red, [&]() {
+        if (it + 1 < rg.ntiles) ru_tile_load_async(tin, a.y + (row0 + RU_ROWS) * H, rows_of(it + 1) * H, ntot);
+      });
+      RU_STAMP(it, 2);
+      ru_stage(a_hi, a_lo, r, qd, s.SL, zn);  // (the previous tile's second product is done: operand tile free)
+      ru_operand_ready(&bars[1]);
+      ru_row_store(out0, r, c0, H, zn);
+      if (qd == 0 && row < rg.hi) {
+        a.mean[row] = ln.mean;
+        a.rstd[row] = ln.rstd;
+      }
+      ru_row_sync();
+      RU_STAMP(it, 3);
+      ru_tile_store(a.zn + row0 * H, out0, nvalid);
+      ru_wait(&bars[3], par);
+      umma::fence_after_sync();
+      RU_STAMP(it, 4);
+      float v[16];
+      if (have_cols) {  // hidden = dropout(relu(zn W1 + b1))
+        umma::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const int c = c0 + i;
+          float m0, m1;
+          drop_mul2(dh, (unsigned long long)(row * H + c), m0, m1);
+          v[i] = (c < H) ? fmaxf(v[i] + vec[2 * 64 + c], 0.f) * m0 : 0.f;
+          v[i + 1] = (c + 1 < H) ? fmaxf(v[i + 1] + vec[2 * 64 + c + 1], 0.f) * m1 : 0.f;
+        }
+        ru_row_store(out1, r, c0, H, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      ru_stage(a_hi, a_lo, r, qd, s.SL, v);
+      ru_operand_ready(&bars[2]);
+      ru_row_sync();
+      RU_STAMP(it, 5);
+      ru_tile_store(a.h1d + row0 * H, out1, nvalid);
+      ru_wait(&bars[4], par);
+      umma::fence_after_sync();
+      RU_STAMP(it, 6);
+      if (have_cols) {  // xout = (dropout(hidden W2 + b2) + zn) * mask
+        umma::tmem_ld16(tmem + lane_base + (uint32_t)(s.NP + c0), v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const int c = c0 + i;
+          float m0, m1;
+          drop_mul2(dout, (unsigned long long)(row * H + c), m0, m1);
+          v[i] = ((v[i] + vec[3 * 64 + c]) * m0 + zn[i]) * m;
+          v[i + 1] = ((v[i + 1] + vec[3 * 64 + ((c + 1) & 63)]) * m1 + zn[i + 1]) * m;
+        }
+        ru_row_store(out0, r, c0, H, v);
+      }
+      umma::fence_before_sync();
+      ru_row_sync();
+      ru_tile_store(a.xout + row0 * H, out0, nvalid);
+      RU_STAMP(it, 7);
+    }
     cp_async_wait<0>();
-    __syncthreads();
-    float x[32], zn[32];
-    ru_row_load(tin, r, c0, H, x);
-    const RuLn ln = ru_layernorm(x, zn, vec, vec + 64, a.eps, r, ch, c0, H, red);
-    if (tile + gridDim.x < a.ntiles)
-      ru_tile_load_async(tin, a.y + (tile + gridDim.x) * ntot, nvalid_of(tile + gridDim.x), ntot);
-    ru_row_store(out0, r, c0, H, zn);
-    ru_stage(a_hi, a_lo, r, ch, s.SL, zn);
-    umma::fence_smem_to_async();
-    __syncthreads();
-    if (ch == 0 && row < a.N) {
-      a.mean[row] = ln.mean;
-      a.rstd[row] = ln.rstd;
-    }
-    if (t == 0) {
-      umma::fence_after_sync();
-      if (it == 0) ru_wait(&bars[0], 0);
-      ru_issue(tmem, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w1), umma::smem_u32(w1 + s.img1 / 2),
-               wpitch, s.KS, idesc, 0u);
-      umma::mma_commit(&bars[1]);
-    }
-    ru_tile_store(a.zn + row0 * H, out0, nvalid);
-    ru_wait(&bars[1], par);
-    umma::fence_after_sync();
-    float v[32];
-    if (have_cols) {  // hidden = dropout(relu(zn W1 + b1))
-      umma::tmem_ld32(tmem + lane_base + (uint32_t)c0, v);
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const int c = c0 + i;
-        float m0, m1;
-        drop_mul2(dh, (unsigned long long)(row * H + c), m0, m1);
-        v[i] = (c < H) ? fmaxf(v[i] + vec[2 * 64 + (c & 63)], 0.f) * m0 : 0.f;
-        v[i + 1] = (c + 1 < H) ? fmaxf(v[i + 1] + vec[2 * 64 + ((c + 1) & 63)], 0.f) * m1 : 0.f;
-      }
-      ru_row_store(out1, r, c0, H, v);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.f;
-    }
-    ru_stage(a_hi, a_lo, r, ch, s.SL, v);
-    umma::fence_smem_to_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    if (t == 0) {
-      umma::fence_after_sync();
-      ru_issue(tmem + (uint32_t)s.NP, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w2),
-               umma::smem_u32(w2 + s.img1 / 2), wpitch, s.KS, idesc, 0u);
-      umma::mma_commit(&bars[2]);
-    }
-    ru_tile_store(a.h1d + row0 * H, out1, nvalid);
-    ru_wait(&bars[2], par);
-    umma::fence_after_sync();
-    if (have_cols) {  // xout = (dropout(hidden W2 + b2) + zn) * mask
-      umma::tmem_ld32(tmem + lane_base + (uint32_t)(s.NP + c0), v);
-      const float m = (row < a.N && a.ids) ? (a.ids[row] != 0 ? 1.f : 0.f) : 1.f;
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const int c = c0 + i;
-        float m0, m1;
-        drop_mul2(dout, (unsigned long long)(row * H + c), m0, m1);
-        v[i] = ((v[i] + vec[3 * 64 + (c & 63)]) * m0 + zn[i]) * m;
-        v[i + 1] = ((v[i + 1] + vec[3 * 64 + ((c + 1) & 63)]) * m1 + zn[i + 1]) * m;
-      }
-      ru_row_store(out0, r, c0, H, v);
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    ru_tile_store(a.xout + row0 * H, out0, nvalid);
   }
-  cp_async_wait<0>();
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_free(tmem, 128);
 }
 
 static size_t ru_ln_qkv_smem(const RuShape& s) {
-  return (size_t)s.img1 + s.img2 + 2 * (size_t)s.SL * RU_PA + 3 * (size_t)s.dense + (5 * 64 + 3 * 256) * sizeof(float);
+  return (size_t)s.img1 + s.img2 + 2 * (size_t)s.SL * RU_PA + 3 * (size_t)s.dense + (5 * 64 + 3 * 512) * sizeof(float);
 }
 static size_t ru_ln_ffn_smem(const RuShape& s) {
-  return 2 * (size_t)s.img1 + 2 * (size_t)s.SL * RU_PA + 3 * (size_t)s.dense + (4 * 64 + 3 * 256) * sizeof(float);
+  return 2 * (size_t)s.img1 + 2 * (size_t)s.SL * RU_PA + 3 * (size_t)s.dense + (4 * 64 + 3 * 512) * sizeof(float);
 }
 
 constexpr int RU_NUM_SMS = 148;
@@ -587,8 +672,9 @@ extern "C" int cast_rowk_presplit(const float* const* weights, int nblocks, int 
     for (int b = 0; b < nb; ++b)
       for (int j = 0; j < 5; ++j)
         if (!a.w[b][j]) return set_error(CAST_ERR_BAD_ARG, "rowk_presplit: null weight pointer");
-    CAST_LAUNCH(ru_presplit_kernel, dim3((unsigned)(nb * RU_NIMG)), dim3(256), 0, (cudaStream_t)stream, a, H,
-                static_cast<unsigned char*>(images) + (size_t)b0 * per);
+    const RuShape s = ru_shape(H);
+    CAST_LAUNCH(ru_presplit_kernel, dim3((unsigned)cdiv(2L * s.NP * 4 * s.SL, 256), RU_NIMG, (unsigned)nb), dim3(256), 0,
+                (cudaStream_t)stream, a, H, static_cast<unsigned char*>(images) + (size_t)b0 * per);
   }
   return check_launch("rowk_presplit");
 }
@@ -602,11 +688,12 @@ extern "C" int cast_rowk_ln_qkv_fwd(const float* x, const float* gamma, const fl
   if (!cast_rowk_supported(H)) return set_error(CAST_ERR_UNSUPPORTED, "rowk_ln_qkv_fwd: hidden_units not supported");
   const RuShape s = ru_shape(H);
   const long ntiles = cdiv(N, RU_ROWS);
+  const int grid = (int)(ntiles < g_rowk_max_ctas ? ntiles : g_rowk_max_ctas);
+  const long rpc = cdiv(cdiv(N, grid), 4) * 4;
   RuLnQkvArgs a{x, gamma, beta, bq, bk, bv, static_cast<const unsigned char*>(images), eps, qn, Q, K, V, mean, rstd,
-                kmask, qmask, N, ntiles, H};
+                kmask, qmask, N, rpc, H};
   const size_t smem = ru_ln_qkv_smem(s);
   CAST_RU_SMEM(ru_ln_qkv_fwd_kernel, smem)
-  const int grid = (int)(ntiles < g_rowk_max_ctas ? ntiles : g_rowk_max_ctas);
   CAST_LAUNCH(ru_ln_qkv_fwd_kernel, dim3(grid), dim3(RU_THREADS), smem, (cudaStream_t)stream, a);
   return check_launch("rowk_ln_qkv_fwd");
 }
@@ -622,13 +709,23 @@ extern "C" int cast_rowk_ln_ffn_fwd(const float* y, const float* gamma, const fl
   if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "rowk_ln_ffn_fwd: drop_rate");
   const RuShape s = ru_shape(H);
   const long ntiles = cdiv(N, RU_ROWS);
+  const int grid = (int)(ntiles < g_rowk_max_ctas ? ntiles : g_rowk_max_ctas);
+  const long rpc = cdiv(cdiv(N, grid), 4) * 4;
   RuLnFfnArgs a{y, gamma, beta, b1, b2, static_cast<const unsigned char*>(images), ids, eps, drop_rate, seed, step,
-                site_hidden, site_out, zn, h1d, xout, mean, rstd, N, ntiles, H};
+                site_hidden, site_out, zn, h1d, xout, mean, rstd, N, rpc, H};
   const size_t smem = ru_ln_ffn_smem(s);
   CAST_RU_SMEM(ru_ln_ffn_fwd_kernel, smem)
-  const int grid = (int)(ntiles < g_rowk_max_ctas ? ntiles : g_rowk_max_ctas);
   CAST_LAUNCH(ru_ln_ffn_fwd_kernel, dim3(grid), dim3(RU_THREADS), smem, (cudaStream_t)stream, a);
   return check_launch("rowk_ln_ffn_fwd");
+}
+
+/* tuning hook: device buffer of 148*4*16 int64 that thread 0 of every CTA fills with clock64() phase stamps (NULL: off) */
+extern "C" int cast_rowk_set_trace(void* device_buffer) {
+#ifndef CAST_EMU
+  long long* p = static_cast<long long*>(device_buffer);
+  if (cudaMemcpyToSymbol(g_rowk_trace, &p, sizeof(p)) != cudaSuccess) return set_error(CAST_ERR_CUDA, "rowk_set_trace");
+#endif
+  return CAST_OK;
 }
 
 /* 1 if a tcgen05 row kernel gave up waiting on one of its barriers since the last call (synchronises the device) */

@@ -376,6 +376,9 @@ class Engine:
         nb = len(tb.blocks)
         fused = self.use_fused and bool(self.lib.cast_fused_supported(H))
         rowk = self.rowk_active()
+        if rowk and getattr(c, "presplit_pending", False):   # join the side-stream weight split (launch_fwd_bwd)
+            torch.cuda.current_stream(self.device).wait_stream(c.side2)
+            c.presplit_pending = False
         P = self.P
         for i, b in enumerate(tb.blocks):
             pre = f"{tower}.{i}."
@@ -561,6 +564,10 @@ class Engine:
     def rowk_active(self):
         return self.use_rowk and self.use_fused and bool(self.rowk_block)
 
+    def rowk_presplit(self, stream):
+        self._call(self.lib.cast_rowk_presplit, self.rowk_wptrs, len(self.rowk_block), self.H,
+                   self.rowk_img.data_ptr(), self.rowk_img.numel(), stream)
+
     def rowk_image(self, pre: str) -> int:
         return self.rowk_img.data_ptr() + self.rowk_block[pre] * self.rowk_img_bytes
 
@@ -568,9 +575,8 @@ class Engine:
         """Builds seq_emb [N,H] from the ids already resident in c.keys3 / c.cids; returns the buffer."""
         plan = self.plan
         ids = c.keys3[0]
-        if self.rowk_active():  # weights moved since the last step: refresh the tf32 hi/lo operand images
-            self._call(self.lib.cast_rowk_presplit, self.rowk_wptrs, len(self.rowk_block), self.H,
-                       self.rowk_img.data_ptr(), self.rowk_img.numel(), self._stream())
+        if self.rowk_active() and not getattr(c, "presplit_pending", False):
+            self.rowk_presplit(self._stream())   # weights moved since the last step: refresh the operand images
         streams: Dict[str, torch.Tensor] = {}
         for j, (tname, key) in enumerate((("time_emb", "time"), ("hours_emb", "hours"), ("days_emb", "days"))):
             if tname in plan.tables:
@@ -730,6 +736,13 @@ class Engine:
                 self._call(self.lib.cast_scatter_sort, c.keys3.data_ptr(), 3, c.N, V, c.sws.data_ptr(), c.sws_bytes,
                            c.side.cuda_stream)
             c.presorted = True
+            if self.rowk_active():   # the weight operand images are needed by the first row kernel, not by the embedding
+                if getattr(c, "side2", None) is None:
+                    c.side2 = torch.cuda.Stream(device=self.device)
+                c.side2.wait_stream(main)
+                with torch.cuda.stream(c.side2):
+                    self.rowk_presplit(c.side2.cuda_stream)
+                c.presplit_pending = True
         c.reduce_jobs = []
         c.fuse_tail = self.tail_fusable()
         self.forward(c, train=True)

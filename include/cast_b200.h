@@ -141,6 +141,8 @@ int cast_rowk_ln_ffn_fwd(const float* y, const float* gamma, const float* beta, 
 int cast_rowk_status(int* timed_out);
 /* test / tuning hook: cap the persistent grid (default and maximum: one CTA per SM) */
 int cast_rowk_set_grid(int max_ctas);
+/* tuning hook: device buffer of 148*4*16 int64 filled with clock64() phase stamps by the row kernels (NULL: off) */
+int cast_rowk_set_trace(void* device_buffer);
 /* Row-kernel backend (A/B testing): bit 0 = backward kernels on the tensor cores (mma.sync 3xTF32), bit 1 = forward
  * kernels; default 3; 0 = FP32 FFMA kernels. */
 int cast_fused_set_backend(int backend);

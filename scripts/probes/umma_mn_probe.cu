@@ -96,6 +96,48 @@ __global__ void bulk_store_probe(float* dst, int* status) {
   }
 }
 
+
+// ---- chain timing: 7 k-steps x 3 passes (lo*hi, hi*lo, hi*hi) as the row kernels issue them, N = 64 or 128,
+// accumulating into ONE tensor-memory tile (dependent chain) or into THREE tiles round-robin (one per pass)
+__global__ void chain_probe(int N, int nacc, int reps, long long* clk, int* status) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int t = threadIdx.x;
+  for (int i = t; i < 200000 / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.001f * (i % 97);
+  if (t < 32) umma::tmem_alloc(&slot, 512);
+  if (t == 0) umma::mbar_init(&bar, 1);
+  umma::fence_smem_to_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = slot;
+  if (t == 0) {
+    const uint32_t idesc = umma::idesc_tf32(128, N);
+    const uint32_t pa = 2064, pb = N * 16 + 16;
+    const uint32_t a_hi = umma::smem_u32(sm), a_lo = a_hi + 14 * pa, b_hi = a_lo + 14 * pa, b_lo = b_hi + 14 * pb;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      uint64_t dah = umma::smem_desc(a_hi, pa, 128), dal = umma::smem_desc(a_lo, pa, 128);
+      uint64_t dbh = umma::smem_desc(b_hi, pb, 128), dbl = umma::smem_desc(b_lo, pb, 128);
+      for (int ks = 0; ks < 7; ++ks) {
+        umma::mma_tf32(tmem, dal, dbh, idesc, 1u);
+        umma::mma_tf32(tmem + (nacc == 3 ? N : 0), dah, dbl, idesc, 1u);
+        umma::mma_tf32(tmem + (nacc == 3 ? 2 * N : 0), dah, dbh, idesc, 1u);
+        dah = umma::desc_advance(dah, 2 * pa); dal = umma::desc_advance(dal, 2 * pa);
+        dbh = umma::desc_advance(dbh, 2 * pb); dbl = umma::desc_advance(dbl, 2 * pb);
+      }
+    }
+    const long long t1 = clock64();
+    umma::mma_commit(&bar);
+    if (!umma::mbar_wait(&bar, 0)) *status = 3;
+    const long long t2 = clock64();
+    clk[0] = t1 - t0; clk[1] = t2 - t0;
+  }
+  __syncthreads();
+  if (t < 32) umma::tmem_free(tmem, 512);
+}
+
 static uint32_t idesc(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -273,6 +315,21 @@ int main() {
     int bad = 0;
     for (int t = 0; t < 128; ++t) for (int c = 0; c < 50; ++c) bad += h[t * 50 + c] != t * 100.f + c;
     printf("bulk store shared->global (25600 B): %s, %d bad elements\n", cudaGetErrorString(e), bad);
+  }
+  // ---------------- test 8: realistic 21-MMA chains, one accumulator vs three
+  {
+    long long* dclk; int* dst; cudaMalloc(&dclk, 16); cudaMalloc(&dst, 4);
+    cudaFuncSetAttribute(chain_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000);
+    for (int N : {64, 128})
+      for (int nacc : {1, 3})
+        for (int reps : {1, 8}) {
+          cudaMemset(dst, 0, 4);
+          chain_probe<<<1, 128, 200000>>>(N, nacc, reps, dclk, dst);
+          cudaError_t e = cudaDeviceSynchronize();
+          long long h[2]; int st; cudaMemcpy(h, dclk, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&st, dst, 4, cudaMemcpyDeviceToHost);
+          printf("chain N=%3d accumulators=%d reps=%d: issue %.1f clk/mma, done %.1f clk/mma (%lld total) %s status %d\n", N, nacc, reps,
+                 h[0] / (21.0 * reps), h[1] / (21.0 * reps), h[1], cudaGetErrorString(e), st);
+        }
   }
   return 0;
 }

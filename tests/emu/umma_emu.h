@@ -13,6 +13,7 @@
 #pragma once
 #include <sched.h>
 #include <assert.h>
+#include <atomic>
 #include <mutex>
 
 namespace cast_emu {
@@ -155,6 +156,26 @@ inline void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   assert(lane0 == ((cast_emu::t_lin / 32) % 4) * 32 && col0 + 32 <= 512);
   float(*t)[512] = cast_emu::tmem();
   for (int i = 0; i < 32; ++i) v[i] = t[lane0 + cast_emu::t_lin % 32][col0 + i];
+}
+
+inline void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  const int lane0 = (int)(taddr >> 16), col0 = (int)(taddr & 0xFFFFu);
+  assert(lane0 == ((cast_emu::t_lin / 32) % 4) * 32 && col0 + 16 <= 512);
+  float(*t)[512] = cast_emu::tmem();
+  for (int i = 0; i < 16; ++i) v[i] = t[lane0 + cast_emu::t_lin % 32][col0 + i];
+}
+
+// named barrier: generation-counting spin barrier (blocks run one after another, so one static set suffices)
+inline void named_sync(int id, int nthreads) {
+  static std::atomic<int> count[16], gen[16];
+  assert(id > 0 && id < 16);
+  const int g = gen[id].load();
+  if (count[id].fetch_add(1) + 1 == nthreads) {
+    count[id].store(0);
+    gen[id].fetch_add(1);
+  } else {
+    while (gen[id].load() == g) sched_yield();
+  }
 }
 
 }  // namespace umma
