@@ -170,6 +170,77 @@ def cpu_reference_arm(batch_size, steps, warmup, seed=20191019):
     return batch_size * steps / dt, dt / steps, torch.get_num_threads()
 
 
+def dp_parity_check(model, eng, c, dev_batches, B, world, rank, dev, shard):
+    """(1) every rank holds bit-identical replicated parameters after the timed steps; (2) gradients of ONE data-parallel
+    step over N x B sequences equal (1e-5 of each tensor's max) those of the same N x B sequences processed by a single
+    rank without any exchange — dense weights through the all-reduce, item-table rows through whichever path the run
+    uses (replicated scatter or, row-sharded, the owner pull over peer memory).  Dropout is off for (2): ranks draw
+    independent masks by design."""
+    import torch.distributed as dist
+    region = eng.P["item_emb"].numel() if shard else 0
+    wi = eng.w[region:].view(torch.int32).long()
+    chk = torch.stack([wi.sum(), (wi * (torch.arange(wi.numel(), device=dev) % 8191 + 1)).sum()])
+    allchk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allchk, chk)
+    identical = all(bool(torch.equal(allchk[0], x)) for x in allchk)
+    saved = (eng.w.clone(), eng.m.clone(), eng.v.clone(), eng.adam_state.clone(), eng.rate)
+    eng.rate = 0.0
+    k3, c3 = dev_batches[0]
+    c.keys3.copy_(k3)
+    c.cids.copy_(c3)
+    eng.launch_fwd_bwd(c)
+    eng.grad_allreduce(c)
+    torch.cuda.synchronize(dev)
+    g_dp = eng.gbuf.clone()
+    # the same global batch on every rank, no exchange
+    gk3 = [torch.zeros_like(k3) for _ in range(world)]
+    gc3 = [torch.zeros_like(c3) for _ in range(world)]
+    dist.all_gather(gk3, k3)
+    dist.all_gather(gc3, c3)
+    cg = eng.ctx(B * world)
+    cg.keys3.copy_(torch.cat([x.view(3, B, -1) for x in gk3], 1).reshape(3, -1))
+    cg.cids.copy_(torch.cat([x.view(3, B, -1) for x in gc3], 1).reshape(3, -1))
+    eng.launch_fwd_bwd(cg)
+    if shard:   # own rows of the gradient from this rank's own sorted entries (they cover the whole batch now)
+        import ctypes as C
+        nsrc, rows, rowscale, scale = cg.shard_src
+        ko, po = C.c_size_t(), C.c_size_t()
+        eng.lib.cast_scatter_sorted_offsets(cg.N, nsrc, world * eng.shard_R, C.byref(ko), C.byref(po))
+        rows_a = (C.c_void_p * nsrc)(*[t.data_ptr() for t in rows])
+        rs_a = (C.c_void_p * nsrc)(*[(t.data_ptr() if t is not None else None) for t in rowscale])
+        eng._call(eng.lib.cast_scatter_apply_range, nsrc, cg.N, rows_a, rs_a, (C.c_float * nsrc)(*scale), eng.H,
+                  eng.G["item_emb"].data_ptr(), cg.sws.data_ptr() + ko.value, cg.sws.data_ptr() + po.value,
+                  rank * eng.shard_R, (rank + 1) * eng.shard_R, cg.spart.data_ptr(), cg.spart_bytes, 0, eng._stream())
+    torch.cuda.synchronize(dev)
+    g_1 = eng.gbuf.clone()
+    worst, worst_name = 0.0, ""
+    for name, off in eng.offsets.items():
+        if name.endswith("k.b"):      # analytically zero (softmax shift invariance): rounding noise only
+            continue
+        n = eng.P[name].numel()
+        a_, b_ = g_dp[off:off + n], g_1[off:off + n]
+        e = float((a_ - b_).abs().max() / b_.abs().max().clamp_min(1e-30))
+        if e > worst:
+            worst, worst_name = e, name
+    sums_ok = bool(g_dp[-2] == g_1[-2]) and abs(float(g_dp[-4] - g_1[-4])) <= 1e-5 * abs(float(g_1[-4]))
+    t = torch.tensor([worst, 0.0 if sums_ok else 1.0, 0.0 if identical else 1.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eng.w.copy_(saved[0]); eng.m.copy_(saved[1]); eng.v.copy_(saved[2]); eng.adam_state.copy_(saved[3])
+    eng.rate = saved[4]
+    if eng.after_adam is not None:
+        eng.after_adam()
+    worst = float(t[0].item())
+    ok = worst <= 1e-5 and t[1].item() == 0 and t[2].item() == 0
+    return {"ok": bool(ok), "replicas_bit_identical": bool(t[2].item() == 0), "grad_max_rel_err_vs_single_rank": worst,
+            "worst_tensor_rank0": worst_name, "loss_and_count_match": bool(t[1].item() == 0), "tolerance": 1e-5,
+            "global_batch": B * world, "item_table": "row-sharded" if shard else "replicated"}
+
+
+def bench_config(batch_per_gpu, gpus):
+    """the workload both arms name (identical dict in both lines; how each arm ran it is under `notes` / `sample`)"""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * gpus}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,8 +254,10 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
     ap.add_argument("--no_eval", action="store_true")
-    ap.add_argument("--shard_item_table", action="store_true", help="row-shard the item-table update across ranks "
-                    "(default for --config c5 when --gpus > 1)")
+    ap.add_argument("--shard_item_table", action="store_true", help="row-shard the item table across ranks: 1/N of the "
+                    "table, its gradient and Adam slots per GPU, lookups over NVLink peer memory (default for "
+                    "--config c5 when --gpus > 1)")
+    ap.add_argument("--no_dp_parity", action="store_true")
     a = ap.parse_args()
     select_config(a.config)
     a.warmup = max(a.warmup, 3)
@@ -194,14 +267,14 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        steps = min(a.steps, 10)
-        v, sps, cores = cpu_reference_arm(a.batch_size, steps, min(a.warmup, 2))
-        sample = f"{steps} training steps of B={a.batch_size} sequences (fwd+bwd+TF-Adam), PyTorch-CPU oracle"
+        v, sps, cores = cpu_reference_arm(a.batch_size, a.steps, a.warmup)
+        sample = (f"{a.steps} timed training steps (after {a.warmup} warm-up steps) of B={a.batch_size} sequences "
+                  f"(fwd+bwd+TF-Adam) on the box's host cores, PyTorch-CPU oracle; one process whatever --gpus says")
         print(json.dumps({
             "impl": "reference", "metric": "train_seqs_per_sec", "value": v, "unit": "seq/s", "n_gpus": a.gpus,
-            "steps": steps, "warmup": min(a.warmup, 2), "ms_per_step": sps * 1e3, "higher_is_better": True,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": a.batch_size},
+            "config": bench_config(a.batch_size, a.gpus),
             "cpu_baseline": {"value": v, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -215,9 +288,9 @@ def main():
     B, T, H = a.batch_size, args.maxlen, args.hidden_units
     shard = world > 1 and (a.shard_item_table or a.config == "c5")
     model = cast_b200.build_model(CFG["model"], USERNUM, ITEMNUM, 5, args, device=dev, use_graph=True,
-                                  item_row_align=world if shard else 1)
+                                  item_shard=(rank, world) if shard else None)
     eng = model.engine
-    cdist.attach(eng, shard_item_table=shard)
+    cdist.attach(eng)
     lib = eng.lib
     batches = synth_batches(8, B, T, ITEMNUM, seed=20191019 + 1000 * rank)
     c = eng.ctx(B)
@@ -285,24 +358,40 @@ def main():
     # ---- (2b) evaluation throughput (BASELINE metric "eval users/sec"): host candidate arrays in, ranks out, through
     # the public batched API — forward at maxlen 200 + 101-candidate scoring, and the full-catalog tcgen05 ranking
     eval_out = None
-    if rank == 0 and not a.no_eval and CFG["model"].startswith("sasrec"):
-        rs = np.random.RandomState(7)
-        EU, EB = 2048, 512
-        eseq = np.concatenate([b[0] for b in synth_batches(EU // B, B, T, ITEMNUM, seed=99)], 0)[:EU]
+    if not a.no_eval and CFG["model"].startswith("sasrec"):
+        # users are sharded over the ranks (each rank scores its own users); with a row-sharded item table
+        # the full-catalog mode is a collective: all-gathered user vectors x own item shard + one integer all-reduce
+        rs = np.random.RandomState(7 + rank)
+        EU, EB = 2048, 512       # users per rank, users per call
+        if CFG["items"] > 200000:
+            EU, EB = 512, 256
+        eseq = np.concatenate([b[0] for b in synth_batches(max(1, EU // B), B, T, ITEMNUM, seed=99 + rank)], 0)[:EU]
+        EU = eseq.shape[0]
         ecand = rs.randint(1, ITEMNUM + 1, (EU, 101)).astype(np.int32)
         res = {}
         for name, fn in (("101", lambda s_, c_: model.score_candidates(s_, c_)),
                          ("full", lambda s_, c_: model.score_full_catalog(s_, c_[:, 0]))):
             fn(eseq[:EB], ecand[:EB])  # warm (buffers, smem attributes)
-            torch.cuda.synchronize(dev)
+            barrier()
             t0 = time.perf_counter()
             for s0 in range(0, EU, EB):
                 fn(eseq[s0:s0 + EB], ecand[s0:s0 + EB])
             torch.cuda.synchronize(dev)
-            res[name] = EU / (time.perf_counter() - t0)
-        eval_out = {"users_per_sec_101": res["101"], "users_per_sec_full_catalog": res["full"], "users": EU,
-                    "batch_users": EB, "unit": "users/s",
-                    "note": "host int32 arrays in, ranks out (H2D + forward + scoring + D2H inside the timed region)"}
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            res[name] = world * EU / float(tt.item())
+        eval_out = {"users_per_sec_101": res["101"], "users_per_sec_full_catalog": res["full"], "users": EU * world,
+                    "batch_users": EB, "unit": "users/s", "ranks": world, "catalog_items": ITEMNUM,
+                    "item_table": "row-sharded" if shard else "replicated",
+                    "note": "users sharded over the ranks, whole-job users / max-over-ranks wall time; host int32 "
+                            "arrays in, ranks out (H2D + forward + scoring + D2H inside the timed region)"}
+
+    # ---- (2c) data-parallel parity ON THE BOX (world > 1): replicas bit-identical after the timed steps, and one
+    # N-rank step == the same global batch processed by one rank (dropout off: ranks draw independent masks)
+    dp_parity = None
+    if world > 1 and not a.no_dp_parity:
+        dp_parity = dp_parity_check(model, eng, c, dev_batches, B, world, rank, dev, shard)
 
     # ---- (3) per-kernel CUDA-event profile (eager launches on the same stream) -> dominant kernel roofline
     roofline, kernels = None, None
@@ -314,14 +403,18 @@ def main():
     out = {"metric": "train_seqs_per_sec", "value": value, "unit": "seq/s", "n_gpus": world, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                      "parallelism": f"dp{world}" + ("+item-table-row-sharded-update" if shard else ""), "l2": "flushed (256 MiB write) between timed steps",
-                      "timing": "per-step CUDA events on the launch stream, max over ranks",
-                      "input_path": "pre-generated synthetic batches (not the reference sampler)"},
+           "config": bench_config(B, world),
+           "notes": {"parallelism": f"dp{world}" + ("+item-table-row-sharded(1/%d per GPU, NVLink peer gathers, "
+                                                     "owner-pull gradient)" % world if shard else ""),
+                     "l2": "flushed (256 MiB write) between timed steps",
+                     "timing": "per-step CUDA events on the launch stream, max over ranks",
+                     "input_path": "pre-generated synthetic batches (not the reference sampler)"},
            "e2e": e2e, "gpu_launches": int(launches_per_step) * a.steps, "launches_per_step": int(launches_per_step),
            "clocks": clk}
     if eval_out is not None:
         out["eval"] = eval_out
+    if dp_parity is not None:
+        out["dp_parity"] = dp_parity
     if roofline is not None:
         out["roofline"] = roofline
         out["kernel_profile"] = kernels
@@ -334,6 +427,8 @@ def main():
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    if dp_parity is not None and not dp_parity["ok"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -77,7 +77,15 @@ SIGNATURES = {
     "cast_adam_tf_range": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, I, P]),
     "cast_score_rank_cand": (I, [P, L, P, I, I, L, P, I, P, P, P, P]),
     "cast_score_rank_full_workspace_bytes": (SZ, [L, I, I]),
-    "cast_score_rank_full": (I, [P, L, P, I, I, L, P, P, P, I, P, P, P, P, SZ, P]),
+    "cast_score_rank_full": (I, [P, L, P, I, I, L, P, P, P, P, I, P, P, P, P, SZ, P]),
+    "cast_embed_fwd_sharded": (I, [P, P, I, I, I, L, I, F, P, P, F, U64, P, I, P, P, P]),
+    "cast_logits_loss_sharded": (I, [P, P, I, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "cast_score_rank_cand_sharded": (I, [P, L, P, I, I, I, L, P, I, P, P, P, P]),
+    "cast_scatter_sort_sharded": (I, [P, I, L, I, I, I, P, SZ, P]),
+    "cast_scatter_sorted_offsets": (I, [L, I, I, P, P]),
+    "cast_scatter_apply_range": (I, [I, L, P, P, P, I, P, P, P, C.c_uint, C.c_uint, P, SZ, I, P]),
+    "cast_peer_open": (I, [P, P]),
+    "cast_peer_close": (I, [P]),
     "cast_score_rank_full_status": (I, [P, L, I, P, P]),
 }
 

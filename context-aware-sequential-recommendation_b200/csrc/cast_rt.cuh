@@ -30,6 +30,23 @@ int check_launch(const char* what);
 
 static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
+// The item table as the gather kernels see it: one [V, H] array, or n row shards owned by the n ranks of the box
+// (SURVEY §8e "row-sharded item table": cyclic ownership, id -> shard id % n, local row id / n, +1 on shards 1..n-1
+// whose local row 0 is a never-referenced pad so that EVERY shard keeps "row 0 is not an item").  `shards` is a device
+// array of device pointers; entries of other ranks are peer mappings read over NVLink.
+struct TableRef {
+  const float* base;
+  const float* const* shards;
+  int n;
+  __device__ __forceinline__ const float* row(int id, int H) const {
+    if (!shards) return base + (long)id * H;
+    const int o = id % n;
+    return shards[o] + (long)(id / n + (o ? 1 : 0)) * H;
+  }
+};
+static inline TableRef table_ref(const float* base) { return TableRef{base, nullptr, 1}; }
+static inline TableRef table_ref(const float* const* shards, int n) { return TableRef{nullptr, shards, n}; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

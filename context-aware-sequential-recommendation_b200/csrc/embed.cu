@@ -6,7 +6,7 @@
 
 namespace cast {
 
-__global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __restrict__ table, int V, int H, long N,
+__global__ void embed_fwd_kernel(const int* __restrict__ ids, TableRef table, int V, int H, long N,
                                  int T, float scale, const float* __restrict__ pos, const float* __restrict__ add,
                                  float rate, unsigned long long seed, const unsigned long long* step, int site,
                                  const int* __restrict__ mask_ids, float* __restrict__ out) {
@@ -17,7 +17,7 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __res
   const bool live = (id > 0) && (id < V);  // row 0 is the zero pad (modules.py:154-156)
   const float m = mask_ids ? (mask_ids[row] != 0 ? 1.f : 0.f) : 1.f;
   const Drop d = make_drop(rate, seed, step, site);
-  const float* trow = table + (long)(live ? id : 0) * H;
+  const float* trow = table.row(live ? id : 0, H);
   const float* prow = pos ? pos + (long)(row % T) * H : nullptr;
   const float* arow = add ? add + row * H : nullptr;
   for (int c = lane; c < H; c += 32) {
@@ -127,9 +127,23 @@ extern "C" int cast_embed_fwd(const int* ids, const float* table, int V, int H, 
   if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "embed_fwd: drop_rate");
   if (N == 0) return CAST_OK;
   const int wpb = 8;
-  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, ids, table,
-              V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
+  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, ids,
+              table_ref(table), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
   return check_launch("embed_fwd");
+}
+
+extern "C" int cast_embed_fwd_sharded(const int* ids, const float* const* shards, int nshards, int V, int H, long N,
+                                      int T, float scale, const float* pos, const float* add, float drop_rate,
+                                      unsigned long long seed, const unsigned long long* step, int site,
+                                      const int* mask_ids, float* out, void* stream) {
+  if (!ids || !shards || nshards < 1 || !out || H <= 0 || N < 0 || T <= 0 || V <= 0)
+    return set_error(CAST_ERR_BAD_ARG, "embed_fwd_sharded");
+  if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "embed_fwd_sharded: drop_rate");
+  if (N == 0) return CAST_OK;
+  const int wpb = 8;
+  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, ids,
+              table_ref(shards, nshards), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
+  return check_launch("embed_fwd_sharded");
 }
 
 extern "C" int cast_mask_dropout(const float* in, const int* mask_ids, float drop_rate, unsigned long long seed,

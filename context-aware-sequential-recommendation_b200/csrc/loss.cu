@@ -10,7 +10,7 @@ namespace cast {
 constexpr int LOSS_WARPS = 8;
 constexpr int LOSS_ROWS_PER_CTA = 64;
 
-__global__ void logits_loss_kernel(const float* __restrict__ seq, const float* __restrict__ table, int V, int H,
+__global__ void logits_loss_kernel(const float* __restrict__ seq, TableRef table, int V, int H,
                                    long N, const int* __restrict__ pos, const int* __restrict__ neg,
                                    float* __restrict__ pos_logits, float* __restrict__ neg_logits,
                                    float* __restrict__ dseq, float* __restrict__ gpos, float* __restrict__ gneg,
@@ -24,8 +24,8 @@ __global__ void logits_loss_kernel(const float* __restrict__ seq, const float* _
     if (n >= N) break;
     const int pi = pos[n], ni = neg[n];
     const bool pl = pi > 0 && pi < V, nl = ni > 0 && ni < V;
-    const float* prow = table + (long)(pl ? pi : 0) * H;
-    const float* nrow = table + (long)(nl ? ni : 0) * H;
+    const float* prow = table.row(pl ? pi : 0, H);
+    const float* nrow = table.row(nl ? ni : 0, H);
     const float* srow = seq + n * H;
     float dp = 0.f, dn = 0.f;
     for (int c = lane; c < H; c += 32) {
@@ -88,7 +88,7 @@ __global__ void loss_final_kernel(const float* __restrict__ partial, int nparts,
 // sums and of dgamma / dbeta are left for the step's batched reduction.
 __global__ void __launch_bounds__(32 * LOSS_WARPS)
 lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                const float* __restrict__ table, int V, int H, long N, const int* __restrict__ pos,
+                TableRef table, int V, int H, long N, const int* __restrict__ pos,
                 const int* __restrict__ neg, float* __restrict__ seq, float* __restrict__ pos_logits,
                 float* __restrict__ neg_logits, float* __restrict__ gpos, float* __restrict__ gneg,
                 float* __restrict__ dx, float* __restrict__ partial_loss, float* __restrict__ partial_ln) {
@@ -107,8 +107,8 @@ lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
     if (n >= N) break;
     const int pi = pos[n], ni = neg[n];
     const bool pl = pi > 0 && pi < V, nl = ni > 0 && ni < V;
-    const float* prow = table + (long)(pl ? pi : 0) * H;
-    const float* nrow = table + (long)(nl ? ni : 0) * H;
+    const float* prow = table.row(pl ? pi : 0, H);
+    const float* nrow = table.row(nl ? ni : 0, H);
     const float* xr = x + n * H;
     const float v0 = h0 ? xr[c0] : 0.f, v1 = h1 ? xr[c1] : 0.f;
     const float p0 = (pl && h0) ? prow[c0] : 0.f, p1 = (pl && h1) ? prow[c1] : 0.f;
@@ -200,8 +200,8 @@ extern "C" int cast_lnf_loss(const float* x, const float* gamma, const float* be
     return set_error(CAST_ERR_WORKSPACE, "lnf_loss: workspace too small");
   const int ncta = (int)cdiv(N, LOSS_ROWS_PER_CTA);
   float* pl = static_cast<float*>(workspace);
-  CAST_LAUNCH(lnf_loss_kernel, dim3(ncta), dim3(32 * LOSS_WARPS), 0, (cudaStream_t)stream, x, gamma, beta, eps, table, V,
-              H, N, pos, neg, seq_emb, pos_logits, neg_logits, gpos, gneg, dx, pl, pl + (size_t)ncta * 3);
+  CAST_LAUNCH(lnf_loss_kernel, dim3(ncta), dim3(32 * LOSS_WARPS), 0, (cudaStream_t)stream, x, gamma, beta, eps,
+              table_ref(table), V, H, N, pos, neg, seq_emb, pos_logits, neg_logits, gpos, gneg, dx, pl, pl + (size_t)ncta * 3);
   return check_launch("lnf_loss");
 }
 
@@ -220,10 +220,29 @@ extern "C" int cast_logits_loss(const float* seq_emb, const float* table, int V,
     return set_error(CAST_ERR_WORKSPACE, "logits_loss: workspace too small");
   const int ncta = (int)cdiv(N, LOSS_ROWS_PER_CTA);
   float* partial = static_cast<float*>(workspace);
-  CAST_LAUNCH(logits_loss_kernel, dim3(ncta), dim3(32 * LOSS_WARPS), 0, (cudaStream_t)stream, seq_emb, table, V, H, N,
-              pos, neg, pos_logits, neg_logits, dseq, gpos, gneg, partial);
+  CAST_LAUNCH(logits_loss_kernel, dim3(ncta), dim3(32 * LOSS_WARPS), 0, (cudaStream_t)stream, seq_emb,
+              table_ref(table), V, H, N, pos, neg, pos_logits, neg_logits, dseq, gpos, gneg, partial);
   int rc = check_launch("logits_loss");
   if (rc || !sums) return rc;  // sums == null: the [parts][3] partials stay in the workspace (cast_reduce_partials_batch)
+  CAST_LAUNCH(loss_final_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, partial, ncta, sums);
+  return check_launch("loss_final");
+}
+
+/* cast_logits_loss with the item table row-sharded over the ranks of the box (TableRef, cast_rt.cuh) */
+extern "C" int cast_logits_loss_sharded(const float* seq_emb, const float* const* shards, int nshards, int V, int H,
+                                        long N, const int* pos, const int* neg, float* pos_logits, float* neg_logits,
+                                        float* sums, float* dseq, float* gpos, float* gneg, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (!seq_emb || !shards || nshards < 1 || !pos || !neg || V <= 0 || H <= 0 || N <= 0)
+    return set_error(CAST_ERR_BAD_ARG, "logits_loss_sharded");
+  if (!workspace || workspace_bytes < cast_logits_loss_workspace_bytes(N))
+    return set_error(CAST_ERR_WORKSPACE, "logits_loss_sharded: workspace too small");
+  const int ncta = (int)cdiv(N, LOSS_ROWS_PER_CTA);
+  float* partial = static_cast<float*>(workspace);
+  CAST_LAUNCH(logits_loss_kernel, dim3(ncta), dim3(32 * LOSS_WARPS), 0, (cudaStream_t)stream, seq_emb,
+              table_ref(shards, nshards), V, H, N, pos, neg, pos_logits, neg_logits, dseq, gpos, gneg, partial);
+  int rc = check_launch("logits_loss_sharded");
+  if (rc || !sums) return rc;
   CAST_LAUNCH(loss_final_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, partial, ncta, sums);
   return check_launch("loss_final");
 }

@@ -117,8 +117,9 @@ constexpr int SEG_CHUNK = 64;  // sorted entries walked by one warp (two per lan
 // skewed the id distribution is (popular items own thousands of entries).
 template <int NV>
 __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay,
-                                       long total, long N, ScatterSrc src, int V, int H, float* __restrict__ dtable,
-                                       float* __restrict__ part, int* __restrict__ pkey, int accumulate) {
+                                       long total, long N, ScatterSrc src, unsigned klo, unsigned khi, int H,
+                                       float* __restrict__ dtable, float* __restrict__ part, int* __restrict__ pkey,
+                                       int accumulate) {
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long beg = w * SEG_CHUNK;
@@ -136,7 +137,7 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
     mk[q] = e < end ? skeys[e] : 0xffffffffu;
     mf[q] = 0.f;
     mrow[q] = nullptr;
-    if (e < end && mk[q] != 0u && mk[q] < (unsigned)V) {
+    if (e < end && mk[q] != 0u && mk[q] >= klo && mk[q] < khi) {
       const unsigned p = spay[e];
       const int s = (int)(p / N);
       const long n = (long)p - (long)s * N;
@@ -145,7 +146,9 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
     }
   }
   const unsigned last_key = __shfl_sync(0xffffffffu, mk[(cnt - 1) >> 5], (cnt - 1) & 31);
-  if (last_key == 0u) {  // sorted => the whole chunk is padding (id 0): contributes nothing
+  const unsigned first_key = __shfl_sync(0xffffffffu, mk[0], 0);
+  // sorted => the whole chunk is padding (id 0) or lies outside the key range of this call: contributes nothing
+  if (last_key == 0u || last_key < klo || first_key >= khi) {
     if (lane == 0) { pkey[w * 2 + 0] = -1; pkey[w * 2 + 1] = -1; }
     return;
   }
@@ -187,11 +190,12 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
             const int c = lane + 32 * i;
             if (c < H) part[(w * 2 + 0) * H + c] = acc[i];
           }
-        } else if (cur != 0u && cur < (unsigned)V) {
+        } else if (cur != 0u && cur >= klo && cur < khi) {
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
-            if (c < H) dtable[(long)cur * H + c] = accumulate ? dtable[(long)cur * H + c] + acc[i] : acc[i];
+            const long o = (long)(cur - klo) * H + c;
+            if (c < H) dtable[o] = accumulate ? dtable[o] + acc[i] : acc[i];
           }
         }
 #pragma unroll
@@ -218,11 +222,12 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
       const int c = lane + 32 * i;
       if (c < H) part[(w * 2 + 1) * H + c] = acc[i];
     }
-  } else if (cur != 0u && cur < (unsigned)V) {
+  } else if (cur != 0u && cur >= klo && cur < khi) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
-      if (c < H) dtable[(long)cur * H + c] = accumulate ? dtable[(long)cur * H + c] + acc[i] : acc[i];
+      const long o = (long)(cur - klo) * H + c;
+      if (c < H) dtable[o] = accumulate ? dtable[o] + acc[i] : acc[i];
     }
   }
   if (lane == 0) {
@@ -236,12 +241,12 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
 // chunk order) folded in a fixed order at the end => still a fixed summation tree, with ST_U loads in flight.
 template <int NV>
 __global__ void segment_stitch_kernel(const float* __restrict__ part, const int* __restrict__ pkey, long nchunks,
-                                      int V, int H, float* __restrict__ dtable, int accumulate) {
+                                      unsigned klo, unsigned khi, int H, float* __restrict__ dtable, int accumulate) {
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nchunks) return;
   const int key = pkey[w * 2 + 1];
-  if (key <= 0 || key >= V) return;
+  if (key <= 0 || (unsigned)key < klo || (unsigned)key >= khi) return;
   constexpr int ST_U = NV <= 2 ? 8 : (NV <= 4 ? 4 : (NV <= 8 ? 2 : 1));
   long L = 0;  // chunks w+1 .. w+L continue the run
   for (;;) {
@@ -278,8 +283,24 @@ __global__ void segment_stitch_kernel(const float* __restrict__ part, const int*
       float s = part[(w * 2 + 1) * H + c];
 #pragma unroll
       for (int u = 0; u < ST_U; ++u) s += acc[u][i];
-      dtable[(long)key * H + c] = accumulate ? dtable[(long)key * H + c] + s : s;
+      const long o = (long)((unsigned)key - klo) * H + c;
+      dtable[o] = accumulate ? dtable[o] + s : s;
     }
+  }
+}
+
+// row-sharded table (TableRef, cast_rt.cuh): id -> owner-major key  (id % n) * R + id / n (+ 1 on shards 1..n-1), so
+// that the sorted entries are grouped by owning rank and, inside a rank, by local row; ids outside (0, V) -> 0 = padding
+__global__ void shard_keys_kernel(const int* __restrict__ ids, long total, int V, int n, int R,
+                                  unsigned* __restrict__ out) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int id = ids[i];
+    unsigned k = 0u;
+    if (id > 0 && id < V) {
+      const int o = id % n;
+      k = (unsigned)o * (unsigned)R + (unsigned)(id / n + (o ? 1 : 0));
+    }
+    out[i] = k;
   }
 }
 
@@ -295,8 +316,9 @@ static inline void key_plan(int V, int* passes, int* dbits) {
 
 using namespace cast;
 
+// per-call scratch of the reduce half: chunk partials [nseg][2][H] followed by their keys [nseg][2]
 extern "C" size_t cast_scatter_partial_bytes(long N, int nsrc, int H) {
-  return (size_t)cdiv(N * nsrc, SEG_CHUNK) * 2 * (size_t)H * sizeof(float);
+  return (size_t)cdiv(N * nsrc, SEG_CHUNK) * 2 * ((size_t)H * sizeof(float) + sizeof(int));
 }
 
 extern "C" size_t cast_scatter_workspace_bytes(long N, int nsrc, int V) {
@@ -304,13 +326,13 @@ extern "C" size_t cast_scatter_workspace_bytes(long N, int nsrc, int V) {
   const long nchunks = cdiv(total, RS_CHUNK);
   (void)V;
   const long nseg = cdiv(total, SEG_CHUNK);
-  return (size_t)(4 * total + 256 * nchunks) * sizeof(unsigned) + (size_t)nseg * 2 * sizeof(int) + 64;
+  return (size_t)(5 * total + 256 * nchunks) * sizeof(unsigned) + (size_t)nseg * 2 * sizeof(int) + 64;
 }
 
 // Sort half of the scatter: depends on the ids only, so the engine runs it on a side stream at the start of the step,
 // concurrently with the forward pass; the sorted (key, entry) arrays stay in the workspace for cast_scatter_apply.
-extern "C" int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+static int scatter_sort_impl(const int* keys, int nsrc, long N, int V, int nshards, int rows_per_shard,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   if (!keys || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0) return set_error(CAST_ERR_BAD_ARG, "scatter_sort");
   const long total = N * nsrc;
   if (total >= (1L << 32)) return set_error(CAST_ERR_UNSUPPORTED, "scatter_sort: too many entries");
@@ -321,14 +343,22 @@ extern "C" int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void*
   unsigned* base = static_cast<unsigned*>(workspace);
   unsigned* bufK[2] = {base, base + total};
   unsigned* bufP[2] = {base + 2 * total, base + 3 * total};
-  unsigned* hist = base + 4 * total;
+  unsigned* hist = base + 5 * total;
   const unsigned* kin = reinterpret_cast<const unsigned*>(keys);
   const unsigned* pin = nullptr;
-  int passes, dbits;
+  int passes, dbits, rc;
+  if (nshards > 1) {  // sort by (owner, local row)
+    if ((long)nshards * rows_per_shard < V) return set_error(CAST_ERR_BAD_ARG, "scatter_sort: shards do not cover V");
+    unsigned* tk = base + 4 * total;
+    CAST_LAUNCH(shard_keys_kernel, dim3((unsigned)cdiv(total, 256) < 1184u ? (unsigned)cdiv(total, 256) : 1184u),
+                dim3(256), 0, st, keys, total, V, nshards, rows_per_shard, tk);
+    if ((rc = check_launch("shard_keys"))) return rc;
+    kin = tk;
+    V = nshards * rows_per_shard;
+  }
   key_plan(V, &passes, &dbits);
   const unsigned mask = (1u << dbits) - 1u;
   const int nblk = (int)cdiv(nchunks, RS_WARPS);
-  int rc;
   for (int p = 0; p < passes; ++p) {
     unsigned* kout = bufK[p & 1];
     unsigned* pout = bufP[p & 1];
@@ -345,27 +375,42 @@ extern "C" int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void*
   return CAST_OK;
 }
 
-// Reduce half: fixed-order segment sums of the rows over the arrays cast_scatter_sort left in the workspace.
-extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, const float* const* rowscale,
-                                  const float* scale, int V, int H, float* dtable, void* workspace,
-                                  size_t workspace_bytes, void* partial, size_t partial_bytes, int accumulate,
-                                  void* stream) {
-  if (!rows || !scale || !dtable || nsrc < 1 || nsrc > 4 || N <= 0 || V <= 0 || H <= 0 || H > 1024)
+extern "C" int cast_scatter_sort(const int* keys, int nsrc, long N, int V, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  return scatter_sort_impl(keys, nsrc, N, V, 1, 0, workspace, workspace_bytes, stream);
+}
+
+/* the same sort on owner-major keys (row-sharded table: nshards ranks x rows_per_shard local rows, TableRef) */
+extern "C" int cast_scatter_sort_sharded(const int* keys, int nsrc, long N, int V, int nshards, int rows_per_shard,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (nshards < 1 || rows_per_shard < 1) return set_error(CAST_ERR_BAD_ARG, "scatter_sort_sharded");
+  return scatter_sort_impl(keys, nsrc, N, V, nshards, rows_per_shard, workspace, workspace_bytes, stream);
+}
+
+/* byte offsets, inside a sort workspace for (N, nsrc, key range Vkeys), of the sorted keys and of their payloads */
+extern "C" int cast_scatter_sorted_offsets(long N, int nsrc, int Vkeys, size_t* keys_offset, size_t* payload_offset) {
+  if (N <= 0 || nsrc < 1 || Vkeys <= 0 || !keys_offset || !payload_offset)
+    return set_error(CAST_ERR_BAD_ARG, "scatter_sorted_offsets");
+  const long total = N * nsrc;
+  int passes, dbits;
+  key_plan(Vkeys, &passes, &dbits);
+  const int last = (passes - 1) & 1;   // buffer pair the final pass wrote
+  *keys_offset = ((size_t)last * total) * sizeof(unsigned);
+  *payload_offset = (2 * (size_t)total + (size_t)last * total) * sizeof(unsigned);
+  return CAST_OK;
+}
+
+// Reduce half: fixed-order segment sums of the rows whose sorted key lies in [klo, khi), written to dtable row key - klo
+static int scatter_apply_impl(int nsrc, long N, const float* const* rows, const float* const* rowscale,
+                              const float* scale, int H, float* dtable, long dtable_rows, const unsigned* kin,
+                              const unsigned* pin, unsigned klo, unsigned khi, void* partial, size_t partial_bytes,
+                              int accumulate, void* stream) {
+  if (!rows || !scale || !dtable || !kin || !pin || nsrc < 1 || nsrc > 4 || N <= 0 || H <= 0 || H > 1024 || khi <= klo)
     return set_error(CAST_ERR_BAD_ARG, "scatter_apply");
   const long total = N * nsrc;
-  if (!workspace || workspace_bytes < cast_scatter_workspace_bytes(N, nsrc, V))
-    return set_error(CAST_ERR_WORKSPACE, "scatter_apply: workspace too small");
   if (!partial || partial_bytes < cast_scatter_partial_bytes(N, nsrc, H))
     return set_error(CAST_ERR_WORKSPACE, "scatter_apply: partial buffer too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nchunks = (int)cdiv(total, RS_CHUNK);
-  unsigned* base = static_cast<unsigned*>(workspace);
-  int passes, dbits;
-  key_plan(V, &passes, &dbits);
-  const int last = (passes - 1) & 1;   // buffer pair the final pass wrote
-  const unsigned* kin = base + (size_t)last * total;
-  const unsigned* pin = base + 2 * total + (size_t)last * total;
-  unsigned* hist = base + 4 * total;
   int rc;
   ScatterSrc src;
   for (int s = 0; s < 4; ++s) {
@@ -376,19 +421,19 @@ extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, co
   // rows nobody touches (and row 0) must read as zero: dense-gradient semantics of the reference
   // (accumulate: dtable already holds the sum of an earlier call over other sources; every row is written at most
   // once per call, so adding to it is race-free and keeps a fixed summation order)
-  if (!accumulate) cudaMemsetAsync(dtable, 0, (size_t)V * H * sizeof(float), st);
+  if (!accumulate) cudaMemsetAsync(dtable, 0, (size_t)dtable_rows * H * sizeof(float), st);
   const long nseg = cdiv(total, SEG_CHUNK);
-  int* pkey = reinterpret_cast<int*>(hist + 256L * nchunks);
   float* part = static_cast<float*>(partial);
+  int* pkey = reinterpret_cast<int*>(part + (size_t)nseg * 2 * H);
   const int wpb = 4;
   const dim3 grid((unsigned)cdiv(nseg, wpb)), block(32 * wpb);
 #define CAST_SEG(NV)                                                                                            \
   {                                                                                                             \
-    CAST_LAUNCH(segment_partial_kernel<NV>, grid, block, 0, st, kin, pin, total, N, src, V, H, dtable, part,    \
-                pkey, accumulate);                                                                              \
+    CAST_LAUNCH(segment_partial_kernel<NV>, grid, block, 0, st, kin, pin, total, N, src, klo, khi, H, dtable,   \
+                part, pkey, accumulate);                                                                        \
     if ((rc = check_launch("segment_partial"))) return rc;                                                      \
-    CAST_LAUNCH(segment_stitch_kernel<NV>, grid, block, 0, st, (const float*)part, (const int*)pkey, nseg, V, H, \
-                dtable, accumulate);                                                                            \
+    CAST_LAUNCH(segment_stitch_kernel<NV>, grid, block, 0, st, (const float*)part, (const int*)pkey, nseg, klo, \
+                khi, H, dtable, accumulate);                                                                    \
   }
   if (H <= 64) CAST_SEG(2)
   else if (H <= 128) CAST_SEG(4)
@@ -397,6 +442,36 @@ extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, co
   else CAST_SEG(32)
 #undef CAST_SEG
   return check_launch("segment_stitch");
+}
+
+// ... over the arrays cast_scatter_sort left in the workspace, whole table
+extern "C" int cast_scatter_apply(int nsrc, long N, const float* const* rows, const float* const* rowscale,
+                                  const float* scale, int V, int H, float* dtable, void* workspace,
+                                  size_t workspace_bytes, void* partial, size_t partial_bytes, int accumulate,
+                                  void* stream) {
+  if (N <= 0 || nsrc < 1 || V <= 0) return set_error(CAST_ERR_BAD_ARG, "scatter_apply");
+  if (!workspace || workspace_bytes < cast_scatter_workspace_bytes(N, nsrc, V))
+    return set_error(CAST_ERR_WORKSPACE, "scatter_apply: workspace too small");
+  size_t ko, po;
+  cast_scatter_sorted_offsets(N, nsrc, V, &ko, &po);
+  const unsigned char* w = static_cast<const unsigned char*>(workspace);
+  return scatter_apply_impl(nsrc, N, rows, rowscale, scale, H, dtable, V, reinterpret_cast<const unsigned*>(w + ko),
+                            reinterpret_cast<const unsigned*>(w + po), 0u, (unsigned)V, partial, partial_bytes,
+                            accumulate, stream);
+}
+
+/* Owner side of the row-sharded embedding gradient: fold the entries of ONE rank's sorted arrays
+ * (sorted_keys / sorted_payload: device pointers, possibly that rank's memory read over NVLink; made by
+ * cast_scatter_sort_sharded for N x nsrc entries) whose owner-major key lies in [key_lo, key_hi) — this rank's rows —
+ * into dtable [key_hi - key_lo, H] (row = key - key_lo).  rows / rowscale are that rank's source tensors.  Called once
+ * per rank in rank order (accumulate = 0 for the first) the sum over ranks has a fixed order: bit-reproducible. */
+extern "C" int cast_scatter_apply_range(int nsrc, long N, const float* const* rows, const float* const* rowscale,
+                                        const float* scale, int H, float* dtable, const void* sorted_keys,
+                                        const void* sorted_payload, unsigned key_lo, unsigned key_hi, void* partial,
+                                        size_t partial_bytes, int accumulate, void* stream) {
+  return scatter_apply_impl(nsrc, N, rows, rowscale, scale, H, dtable, (long)key_hi - (long)key_lo,
+                            static_cast<const unsigned*>(sorted_keys), static_cast<const unsigned*>(sorted_payload),
+                            key_lo, key_hi, partial, partial_bytes, accumulate, stream);
 }
 
 extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float* const* rows,

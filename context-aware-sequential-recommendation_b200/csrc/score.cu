@@ -7,7 +7,7 @@
 
 namespace cast {
 
-__global__ void score_rank_cand_kernel(const float* __restrict__ seq_last, long ld, const float* __restrict__ table,
+__global__ void score_rank_cand_kernel(const float* __restrict__ seq_last, long ld, TableRef table,
                                        int V, int H, long U, const int* __restrict__ cand, int C,
                                        float* __restrict__ logits, int* __restrict__ cgt, int* __restrict__ ceq) {
   const int lane = threadIdx.x & 31;
@@ -19,7 +19,7 @@ __global__ void score_rank_cand_kernel(const float* __restrict__ seq_last, long 
   {
     const int id = cand[u * C];
     const bool live = id > 0 && id < V;
-    const float* row = table + (long)(live ? id : 0) * H;
+    const float* row = table.row(live ? id : 0, H);
     float acc = 0.f;
     for (int k = 0; k < H; ++k) acc = __fadd_rn(acc, __fmul_rn(s[k], live ? row[k] : 0.f));
     l0 = acc;
@@ -28,7 +28,7 @@ __global__ void score_rank_cand_kernel(const float* __restrict__ seq_last, long 
   for (int c = lane; c < C; c += 32) {
     const int id = cand[u * C + c];
     const bool live = id > 0 && id < V;
-    const float* row = table + (long)(live ? id : 0) * H;
+    const float* row = table.row(live ? id : 0, H);
     float acc = 0.f;
     for (int k = 0; k < H; ++k) acc = __fadd_rn(acc, __fmul_rn(s[k], live ? row[k] : 0.f));
     if (logits) logits[u * C + c] = acc;
@@ -59,6 +59,18 @@ extern "C" int cast_score_rank_cand(const float* seq_last, long ld, const float*
     return set_error(CAST_ERR_BAD_ARG, "score_rank_cand");
   const int wpb = 4;
   CAST_LAUNCH(score_rank_cand_kernel, dim3((unsigned)cdiv(U, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, seq_last,
-              ld, table, V, H, U, cand, C, logits, count_greater, count_equal);
+              ld, table_ref(table), V, H, U, cand, C, logits, count_greater, count_equal);
   return check_launch("score_rank_cand");
+}
+
+/* cast_score_rank_cand with the item table row-sharded over the ranks of the box (TableRef, cast_rt.cuh) */
+extern "C" int cast_score_rank_cand_sharded(const float* seq_last, long ld, const float* const* shards, int nshards,
+                                            int V, int H, long U, const int* cand, int C, float* logits,
+                                            int* count_greater, int* count_equal, void* stream) {
+  if (!seq_last || !shards || nshards < 1 || !cand || V <= 0 || H <= 0 || U <= 0 || C <= 0)
+    return set_error(CAST_ERR_BAD_ARG, "score_rank_cand_sharded");
+  const int wpb = 4;
+  CAST_LAUNCH(score_rank_cand_kernel, dim3((unsigned)cdiv(U, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, seq_last,
+              ld, table_ref(shards, nshards), V, H, U, cand, C, logits, count_greater, count_equal);
+  return check_launch("score_rank_cand_sharded");
 }

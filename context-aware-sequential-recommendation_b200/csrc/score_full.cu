@@ -60,7 +60,8 @@ __global__ void tile_norm_kernel(const float* __restrict__ inorm, int V, int til
 
 // per user: |u|_2 bound and the canonical target score (target id outside [1,V) scores 0 like the zero-pad row)
 __global__ void user_prep_kernel(const float* __restrict__ users, long ldu, const float* __restrict__ table, int V,
-                                 int H, long U, const int* __restrict__ target, float* __restrict__ unorm,
+                                 int H, long U, const int* __restrict__ target,
+                                 const float* __restrict__ tscore_in, float* __restrict__ unorm,
                                  float* __restrict__ tscore) {
   const int lane = threadIdx.x & 31;
   const long u = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -72,7 +73,8 @@ __global__ void user_prep_kernel(const float* __restrict__ users, long ldu, cons
   if (lane == 0) {
     unorm[u] = sqrtf(s) * NORM_SLACK;
     const int t = target[u];
-    tscore[u] = (t > 0 && t < V) ? canonical_dot(ur, table + (long)t * H, H) : 0.f;
+    // tscore_in: the target lives in another rank's shard of the table; its canonical score was computed there
+    tscore[u] = tscore_in ? tscore_in[u] : ((t > 0 && t < V) ? canonical_dot(ur, table + (long)t * H, H) : 0.f);
   }
 }
 
@@ -460,7 +462,8 @@ extern "C" size_t cast_score_rank_full_workspace_bytes(long U, int V, int H) {
 }
 
 extern "C" int cast_score_rank_full(const float* seq_last, long ld, const float* table, int V, int H, long U,
-                                    const int* target, const int* rated_ptr, const int* rated_idx, int mode,
+                                    const int* target, const float* target_score, const int* rated_ptr,
+                                    const int* rated_idx, int mode,
                                     int* count_greater, int* count_equal, unsigned long long* stats, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   if (!seq_last || !table || !target || !count_greater || !count_equal || V <= 1 || H <= 0 || U <= 0 ||
@@ -480,7 +483,7 @@ extern "C" int cast_score_rank_full(const float* seq_last, long ld, const float*
   cudaMemsetAsync(err, 0, sizeof(int), st);
   if (stats) cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), st);
   CAST_LAUNCH(user_prep_kernel, dim3((unsigned)cdiv(U, 4)), dim3(128), 0, st, seq_last, ld, table, V, H, U, target,
-              unorm, tscore);
+              target_score, unorm, tscore);
   if ((rc = check_launch("score_full(user_prep)"))) return rc;
 #ifdef CAST_EMU
   mode = 1;  // the host emulation has no tensor cores; the exact path defines the same integers

@@ -1,5 +1,6 @@
 """Data-parallel training over the GPUs of one box: one process per GPU, `torch.distributed` (NCCL over NVLink 5 /
-NVSwitch) for the single exchange the path has — the gradient all-reduce.
+NVSwitch) for the gradient all-reduce; with a row-sharded item table (BASELINE config 5) the table traffic bypasses the
+collective library altogether: kernels read the owning rank's memory over NVLink peer mappings (PeerArena).
 
 The reference is single-device; the semantics kept here are those of its loss: the gradient is the
 derivative of  sum(loss terms) / sum(istarget)  over the WHOLE batch (models/sasrec.py:105-108).  Each rank therefore
@@ -11,6 +12,7 @@ summation order.
 from __future__ import annotations
 
 import os
+from types import SimpleNamespace
 
 import torch
 import torch.distributed as dist
@@ -32,27 +34,91 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
-def _reduce_scatter(out, inp, group):
-    try:
-        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
-    except (RuntimeError, NotImplementedError):  # gloo (CPU tests) has no reduce-scatter: same result via all-reduce
-        dist.all_reduce(inp, op=dist.ReduceOp.SUM, group=group)
-        r = dist.get_rank(group)
-        out.copy_(inp[r * out.numel():(r + 1) * out.numel()])
+class PeerArena:
+    """Memory of this rank that the other ranks of the box read directly from their kernels (item-table shard, sorted
+    gradient entries and their source rows): on GPUs ordinary device allocations whose CUDA IPC handles are exchanged
+    through the process group and mapped with peer access (loads go over NVLink / NVSwitch, `cast_peer_open`); in the
+    CPU tests (gloo, host-emulated kernels) POSIX shared memory.  `ptrs(t)` is a collective: every rank passes its own
+    tensor and gets the address of each rank's tensor in ITS address space (own entry: the local pointer)."""
+
+    def __init__(self, lib, device, group=None):
+        self.lib, self.device, self.group = lib, torch.device(device), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._opened = {}      # IPC handle bytes / shm name -> base address in this process
+        self._shm = []         # (SharedMemory, base address, size) segments this rank created
+        self._keep = []
+
+    # ---- CPU backend: tensors allocated here live in named shared memory
+    def alloc(self, numel: int, dtype):
+        from multiprocessing import shared_memory
+        import ctypes
+        nbytes = max(16, int(numel) * torch.empty(0, dtype=dtype).element_size())
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        base = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+        self._shm.append((shm, base, nbytes))
+        return torch.frombuffer(shm.buf, dtype=dtype, count=int(numel))
+
+    def _describe(self, t: torch.Tensor):
+        if t.device.type == "cuda":
+            st = t.untyped_storage()
+            info = st._share_cuda_()      # (device, ipc handle, storage size, offset of the storage in its allocation, ...)
+            return ("ipc", bytes(info[1]), int(info[3]) + t.storage_offset() * t.element_size())
+        p = t.data_ptr()
+        for shm, base, nbytes in self._shm:
+            if base <= p < base + nbytes:
+                return ("shm", shm.name, p - base)
+        raise ValueError("PeerArena.ptrs: CPU tensors must come from PeerArena.alloc")
+
+    def _open(self, kind, key):
+        if key in self._opened:
+            return self._opened[key]
+        if kind == "ipc":
+            import ctypes
+            out = ctypes.c_void_p()
+            rc = self.lib.cast_peer_open(key, ctypes.byref(out))
+            if rc != 0:
+                from . import _lib
+                _lib.check(self.lib, rc, "cast_peer_open")
+            base = int(out.value)
+        else:
+            from multiprocessing import shared_memory
+            import ctypes
+            shm = shared_memory.SharedMemory(name=key)
+            self._keep.append(shm)
+            base = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+        self._opened[key] = base
+        return base
+
+    def ptrs(self, t: torch.Tensor):
+        mine = self._describe(t)
+        every = [None] * self.world
+        dist.all_gather_object(every, mine, group=self.group)
+        out = []
+        for r, (kind, key, off) in enumerate(every):
+            out.append(t.data_ptr() if r == self.rank else self._open(kind, key) + off)
+        return out
+
+    def close(self):
+        for shm in self._keep:
+            try:
+                shm.close()
+            except Exception:
+                pass
+        for shm, _, _ in self._shm:
+            try:
+                shm.close()
+                shm.unlink()
+            except Exception:
+                pass
 
 
-def attach(engine, group=None, shard_item_table: bool = False):
-    """Make `engine.launch_train_step` data parallel over `group` (default: the world group).
-
-    shard_item_table=True (large catalogs, BASELINE config 5): the item table's UPDATE is row-sharded.  Rank r owns the
-    contiguous rows [r*R, (r+1)*R) of the (padded) table: the table gradient is reduce-scattered instead of
-    all-reduced, each rank runs the dense TF-Adam only over its rows (28 B/param of HBM traffic divided by N — at
-    1M x 256 that is 7.2 GB -> 0.9 GB per step per GPU), and the updated rows are all-gathered over NVLink so every
-    rank keeps a full replica for its purely local forward/backward gathers (a 1 GB replica is 0.6 % of a B200's
-    HBM).  Exchanged bytes equal those of one all-reduce; the optimizer's HBM traffic and FLOPs drop by N.
-    The engine must have been built with item_row_align = world size (or a multiple)."""
+def attach(engine, group=None, arena=None):
+    """Make `engine.launch_train_step` data parallel over `group` (default: the world group): replicated parameters,
+    one flat all-reduce of [gradient numerators | loss_sum, auc_sum, count] per step."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return engine
+    if engine.item_shard is not None:
+        return attach_sharded(engine, group, arena)
     engine.world_size = dist.get_world_size(group)
     engine.rank = dist.get_rank(group)
     # identical replicas: rank 0's parameters and optimizer state win
@@ -61,37 +127,87 @@ def attach(engine, group=None, shard_item_table: bool = False):
     # independent dropout streams per rank (one global batch, different positions)
     engine.seed = (engine.seed + 0x9E3779B1 * engine.rank) & 0xFFFFFFFFFFFF
 
-    if not shard_item_table:
-        def allreduce(c):
-            dist.all_reduce(engine.gbuf, op=dist.ReduceOp.SUM, group=group)
+    def allreduce(c):
+        dist.all_reduce(engine.gbuf, op=dist.ReduceOp.SUM, group=group)
 
-        engine.grad_allreduce = allreduce
-        return engine
+    engine.grad_allreduce = allreduce
+    return engine
 
-    from types import SimpleNamespace
-    world, rank = engine.world_size, engine.rank
-    rows, H = engine.item_rows_padded, engine.H
-    if rows % world:
-        raise ValueError(f"item table has {rows} (padded) rows: build the engine with item_row_align={world}")
-    region = rows * H
-    n = region // world
-    sh = SimpleNamespace(region=region, n=n, lo=rank * n,
-                         g_shard=torch.zeros(n, dtype=torch.float32, device=engine.device),
-                         w_tmp=torch.zeros(n, dtype=torch.float32, device=engine.device))
-    engine.shard = sh
-    g_item, g_rest = engine.gbuf[:region], engine.gbuf[region:]
-    w_item = engine.w[:region]
+
+def attach_sharded(engine, group=None, arena: "PeerArena | None" = None):
+    """Data parallelism with the item table ROW-SHARDED over the ranks (BASELINE config 5).  Each rank
+    holds 1/world of the table, of its gradient and of its Adam slots; the dense weights stay replicated.  Per step:
+
+      forward / backward   the embedding, positive and negative lookups read rows from the owning rank's shard over
+                           NVLink (peer mappings; no exchange step, no staging buffers); every rank sorts its
+                           (item id, entry) pairs by (owner, local row) on a side stream
+      all-reduce           [dense-weight gradients | loss_sum, auc_sum, count] — also the barrier after which every
+                           rank's sorted entries and source rows are final
+      owner pull           each rank folds, rank by rank in rank order, the entries that hit ITS rows (read from the
+                           peers' memory) into its dense gradient shard: fixed order, no atomics, no table collective
+      TF-Adam              one launch over [own shard | dense weights]  (28 B/param of table traffic divided by world)
+      barrier              shards are updated and the exported buffers may be overwritten
+
+    The engine must have been built with item_shard=(rank, world)."""
+    if engine.item_shard is None:
+        raise ValueError("attach_sharded: build the engine with item_shard=(rank, world)")
+    import ctypes as C
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if engine.item_shard != (rank, world):
+        raise ValueError(f"engine was built for shard {engine.item_shard}, process group says {(rank, world)}")
+    engine.world_size, engine.rank = world, rank
+    seeds = [None] * world
+    dist.all_gather_object(seeds, int(engine.seed), group=group)
+    if len(set(seeds)) != 1:   # each rank drew its rows of the table from the same stream only if the seeds agree
+        raise ValueError(f"row-sharded item table: every rank must build the engine with the same seed, got {seeds}")
+    arena = arena or PeerArena(engine.lib, engine.device, group)
+    engine.arena = arena
+    # dense weights and optimizer state: rank 0 wins; the table shards are consistent by construction (same draws)
+    region = engine.P["item_emb"].numel()
+    for t in (engine.w[region:], engine.m[region:], engine.v[region:], engine.adam_state):
+        dist.broadcast(t, src=0, group=group)
+    engine.seed = (engine.seed + 0x9E3779B1 * rank) & 0xFFFFFFFFFFFF
+    shards = arena.ptrs(engine.w)          # the shard is the first tensor of the flat parameter buffer
+    engine.shard_ptrs = torch.tensor(shards, dtype=torch.int64, device=engine.device)
+    R, H = engine.shard_R, engine.H
+    flag = torch.zeros(1, dtype=torch.float32, device=engine.device)
+
+    def build_peer_view(c):
+        """pointers to every rank's sorted entries and source rows for this batch size (collective, first step only)"""
+        nsrc, rows, rowscale, scale = c.shard_src
+        ko, po = C.c_size_t(), C.c_size_t()
+        engine.lib.cast_scatter_sorted_offsets(c.N, nsrc, world * R, C.byref(ko), C.byref(po))
+        ws = arena.ptrs(c.sws)
+        uniq = {}
+        for t in rows + [r for r in rowscale if r is not None]:
+            if id(t) not in uniq:
+                uniq[id(t)] = arena.ptrs(t)
+        view = []
+        for p in range(world):
+            rows_a = (C.c_void_p * nsrc)(*[uniq[id(t)][p] for t in rows])
+            rs_a = (C.c_void_p * nsrc)(*[(uniq[id(t)][p] if t is not None else None) for t in rowscale])
+            view.append((rows_a, rs_a, ws[p] + ko.value, ws[p] + po.value))
+        c.peer = SimpleNamespace(view=view, scale=(C.c_float * nsrc)(*scale), nsrc=nsrc)
 
     def exchange(c):
-        _reduce_scatter(sh.g_shard, g_item, group)
-        dist.all_reduce(g_rest, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(engine.gbuf[region:], op=dist.ReduceOp.SUM, group=group)
+        if c.peer is None:
+            build_peer_view(c)
+        pv = c.peer
+        for p in range(world):
+            rows_a, rs_a, keys_p, pay_p = pv.view[p]
+            engine._call(engine.lib.cast_scatter_apply_range, pv.nsrc, c.N, rows_a, rs_a, pv.scale, H,
+                         engine.G["item_emb"].data_ptr(), keys_p, pay_p, rank * R, (rank + 1) * R, c.spart.data_ptr(),
+                         c.spart_bytes, 1 if p else 0, engine._stream())
 
-    def gather_table():
-        sh.w_tmp.copy_(w_item[sh.lo:sh.lo + n])
-        dist.all_gather_into_tensor(w_item, sh.w_tmp, group=group)
+    def end_of_step():
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=group)
 
     engine.grad_allreduce = exchange
-    engine.after_adam = gather_table
+    engine.after_adam = end_of_step
+    if engine.device.type == "cuda":
+        torch.cuda.synchronize(engine.device)
+    dist.barrier(group=group)      # every shard is initialised before anybody gathers from it
     return engine
 
 

@@ -82,19 +82,24 @@ def model_plan(model: str, args) -> SimpleNamespace:
     return p
 
 
-def param_shapes(plan, args, itemnum: int, item_row_align: int = 1):
-    """Ordered (name, shape, fan_in, fan_out | None) — tables first so the l2_emb region is contiguous.  The item
-    table comes first and is followed by `item_emb.pad` zero rows up to a multiple of item_row_align rows, so that
-    its region of the flat buffers splits evenly into row shards (dist.attach(shard_item_table=True))."""
+def shard_rows(itemnum: int, world: int) -> int:
+    """Rows of one rank's shard of the item table (uniform over ranks): cyclic ownership id -> rank id % world, local
+    row id // world, +1 on ranks > 0 whose local row 0 is a never-referenced pad (csrc/cast_rt.cuh TableRef)."""
+    return (itemnum + 1 + world - 1) // world + 1
+
+
+def param_shapes(plan, args, itemnum: int, item_rows: Optional[int] = None):
+    """Ordered (name, shape, fan_in, fan_out | None) — tables first so the l2_emb region is contiguous.  With a
+    row-sharded item table (item_rows = rows of this rank's shard) the first tensor is the local shard; its glorot
+    fan-in stays the full vocabulary."""
     H, T = args.hidden_units, args.maxlen
     out = []
     rows = {"item_emb": itemnum + 1, "time_emb": args.max_bins + 1, **TABLE_ROWS}
     for t in plan.tables:
+        if t == "item_emb" and item_rows is not None:
+            out.append((t, (item_rows, H), rows[t], H))
+            continue
         out.append((t, (rows[t], H), rows[t], H))
-        if t == "item_emb":
-            pad = (-rows[t]) % max(1, item_row_align)
-            if pad:
-                out.append(("item_emb.pad", (pad, H), None, 0.0))
     if plan.learned_pos:
         out.append(("pos_emb", (T, H), T, H))
     n_tables = len(out)
@@ -124,7 +129,10 @@ class Engine:
     """Owns parameters, optimizer state, activations and launches.  One instance per process / GPU."""
 
     def __init__(self, model: str, usernum: int, itemnum: int, args, device=None, lib=None, seed: Optional[int] = None,
-                 item_row_align: int = 1):
+                 item_shard: Optional[tuple] = None, alloc=None):
+        """item_shard = (rank, world): this process owns one row shard of the item table (BASELINE config 5; the
+        other shards are read over NVLink peer mappings once dist.attach has exchanged them).  alloc(numel, dtype) ->
+        tensor: allocator for the buffers peers read (CPU tests: POSIX shared memory; default torch)."""
         self.lib = lib if lib is not None else _lib.load_library()
         self.timing = None
         self.use_fused = True
@@ -144,12 +152,15 @@ class Engine:
         self.l2 = float(getattr(args, "l2_emb", 0.0))
         self.seed = int(seed if seed is not None else (getattr(args, "seed", 0) or 0))
         self.beta1, self.beta2, self.eps = 0.9, 0.98, 1e-8  # models/sasrec.py:120 (beta2=0.98), TF defaults else
-        shapes, n_tables = param_shapes(self.plan, args, itemnum, item_row_align)
-        self.item_rows_padded = (itemnum + 1) + (-(itemnum + 1)) % max(1, item_row_align)
+        self.item_shard = tuple(item_shard) if item_shard is not None and item_shard[1] > 1 else None
+        self.V_items = itemnum + 1
+        self.shard_R = shard_rows(itemnum, self.item_shard[1]) if self.item_shard else None
+        self.alloc = alloc
+        shapes, n_tables = param_shapes(self.plan, args, itemnum, self.shard_R)
         self.shapes = shapes
         total = sum(int(np.prod(s)) for _, s, _, _ in shapes)
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.w = torch.zeros(total, **f32)
+        self.w = self._peer_zeros(total, torch.float32)
         self.gbuf = torch.zeros(total + 4, **f32)  # gradients + {loss_sum, auc_sum, count, pad}: one collective
         self.g = self.gbuf[:total]
         self.sums = self.gbuf[total:]
@@ -186,10 +197,18 @@ class Engine:
             self.rowk_wptrs = (C.c_void_p * len(ptrs))(*ptrs)
         self.world_size = 1
         self.grad_allreduce = None  # set by dist.attach(); called between backward and Adam
-        self.shard = None           # set by dist.attach(shard_item_table=True): row-sharded item-table update
-        self.after_adam = None      # ... and the all-gather of the updated rows that follows Adam
+        self.after_adam = None      # set by dist.attach_sharded(): the barrier that ends a row-sharded step
+        self.shard_ptrs = None      # ... device array of the ranks' item-table shard pointers (own + peer mappings)
 
     # ------------------------------------------------------------------ plumbing
+    def _peer_zeros(self, numel, dtype):
+        """a buffer other ranks may read (item-table shard, sorted gradient entries, their source rows)"""
+        if self.alloc is not None and self.item_shard is not None:
+            t = self.alloc(int(numel), dtype)
+            t.zero_()
+            return t
+        return torch.zeros(int(numel), dtype=dtype, device=self.device)
+
     def _stream(self):
         if self.device.type == "cuda":
             return torch.cuda.current_stream(self.device).cuda_stream
@@ -220,14 +239,31 @@ class Engine:
                 self.P[name].fill_(float(fan_out))
             else:
                 limit = math.sqrt(6.0 / (fan_in + fan_out))
+                if name == "item_emb" and self.item_shard is not None:
+                    # the same draws as the unsharded table, then this rank's rows
+                    full = (torch.rand((self.V_items, shape[1]), generator=gen, dtype=torch.float64) * 2 - 1)
+                    self.P[name].copy_(self.shard_of(full.mul(limit).float()).to(self.device))
+                    continue
                 vals = (torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1).mul(limit).float()
                 self.P[name].copy_(vals.to(self.device))
         self.m.zero_()
         self.v.zero_()
 
+    def shard_of(self, full: torch.Tensor) -> torch.Tensor:
+        """rows of the full [V, H] item table (or of any per-item tensor) that live in this rank's shard, in local order"""
+        rank, world = self.item_shard
+        out = torch.zeros((self.shard_R,) + tuple(full.shape[1:]), dtype=full.dtype)
+        mine = full[rank::world]
+        off = 1 if rank else 0
+        out[off:off + mine.shape[0]] = mine
+        return out
+
     def load_parameters(self, params: Dict[str, "torch.Tensor | np.ndarray"]):
         for k, v in params.items():
-            self.P[k].copy_(torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).to(self.device))
+            v = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v)
+            if k == "item_emb" and self.item_shard is not None and v.shape[0] == self.V_items:
+                v = self.shard_of(v)
+            self.P[k].copy_(v.to(self.device))
 
     def state_step(self) -> int:
         return int(self.adam_state[1].item())
@@ -241,6 +277,8 @@ class Engine:
         N = B * T
         lib = self.lib
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        # buffers the other ranks read during the row-sharded gradient exchange (dist.attach_sharded)
+        fp = (lambda *s: self._peer_zeros(int(np.prod(s)), torch.float32).view(*s)) if self.item_shard else f
         c = SimpleNamespace(B=B, N=N)
         c.keys3 = torch.zeros(3, N, dtype=torch.int32, device=dev)   # input_seq | pos | neg
         c.cids = torch.zeros(3, N, dtype=torch.int32, device=dev)    # time_seq | hours | days
@@ -261,7 +299,8 @@ class Engine:
                     nws = self.lib.cast_block_bwd_workspace_bytes(N, H) // 4 + 16
                     b.ws_ffn, b.ws_qkv = f(nws), f(nws)
                 blocks.append(b)
-            c.tw[tower] = SimpleNamespace(blocks=blocks, out=f(N, H), muf=f(N), rsf=f(N), dx_in=f(N, H), x_in=None)
+            c.tw[tower] = SimpleNamespace(blocks=blocks, out=(fp if tower == "main" else f)(N, H), muf=f(N), rsf=f(N),
+                                          dx_in=f(N, H), x_in=None)
         # attention backward scratch: P~ and dS of one block ([2][h*B,T,T]), shared by all blocks (d <= 64 only)
         c.attn_ws = None
         if H // h <= 64 and 2 * B * h * T * T * 4 <= (2 << 30):
@@ -271,14 +310,14 @@ class Engine:
         c.demb = {t: f(N, H) for t in self.plan.tables if t != "item_emb"}
         if self.plan.merge:
             k = len(self.plan.merge[0])
-            c.cat, c.mlp_h, c.mlp_out = f(N, k * H), f(N, k * H), f(N, H)
+            c.cat, c.mlp_h, c.mlp_out = f(N, k * H), f(N, k * H), fp(N, H)
             c.dcat, c.dmlp_h, c.dmlp_o = f(N, k * H), f(N, k * H), f(N, H)
             c.dsrc = {s: f(N, H) for s in self.plan.merge[0]}
-        c.pos_logits, c.neg_logits, c.gpos, c.gneg = f(N), f(N), f(N), f(N)
+        c.pos_logits, c.neg_logits, c.gpos, c.gneg = f(N), f(N), fp(N), fp(N)
         c.sums = self.sums  # loss_sum, auc_sum, count (tail of the gradient buffer)
         c.dseq = f(N, H)
         c.t = [f(N, H) for _ in range(7)]  # gradient scratch
-        c.g0 = f(N, H)
+        c.g0 = fp(N, H)
         kmax = (len(self.plan.merge[0]) if self.plan.merge else 1) * H
         c.splits = int(max(1, min(296, N // 128)))
         ws = max(lib.cast_layernorm_bwd_workspace_bytes(N, H),
@@ -288,9 +327,13 @@ class Engine:
         c.ws = torch.empty(ws // 4 + 16, dtype=torch.float32, device=dev)
         c.ws_bytes = ws
         vmax = max(self.P[t].shape[0] for t in self.plan.tables)
+        if self.item_shard:
+            vmax = max(vmax, self.item_shard[1] * self.shard_R)   # owner-major key range of the sharded sort
         sws = lib.cast_scatter_workspace_bytes(N, 3, vmax)
-        c.sws = torch.empty(sws // 4 + 16, dtype=torch.int32, device=dev)
+        c.sws = self._peer_zeros(sws // 4 + 16, torch.int32) if self.item_shard else \
+            torch.empty(sws // 4 + 16, dtype=torch.int32, device=dev)
         c.sws_bytes = sws
+        c.peer = None   # pointers into the other ranks' buffers, exchanged on the first sharded step
         spb = lib.cast_scatter_partial_bytes(N, 3, H)
         c.spart = torch.empty(spb // 4 + 16, dtype=torch.float32, device=dev)
         c.spart_bytes = spb
@@ -339,6 +382,11 @@ class Engine:
 
     def embed_fwd(self, ids, table, out, pos=None, add=None, rate=0.0, site=0, mask_ids=None):
         N = ids.numel()
+        if self.item_shard is not None and table is self.P["item_emb"]:
+            self._call(self.lib.cast_embed_fwd_sharded, ids.data_ptr(), self.shard_ptrs.data_ptr(), self.item_shard[1],
+                       self.V_items, self.H, N, self.T, float(self.H ** 0.5), self._p(pos), self._p(add), rate,
+                       self.seed, self.step_ptr, site, self._p(mask_ids), out.data_ptr(), self._stream())
+            return
         self._call(self.lib.cast_embed_fwd, ids.data_ptr(), table.data_ptr(), table.shape[0], self.H, N, self.T,
                    float(self.H ** 0.5), self._p(pos), self._p(add), rate, self.seed, self.step_ptr, site,
                    self._p(mask_ids), out.data_ptr(), self._stream())
@@ -354,6 +402,17 @@ class Engine:
         rows_a = (C.c_void_p * nsrc)(*[r.data_ptr() for r in rows])
         rs_a = (C.c_void_p * nsrc)(*[(r.data_ptr() if r is not None else None) for r in rowscale])
         sc_a = (C.c_float * nsrc)(*scale)
+        if table_name == "item_emb" and self.item_shard is not None:
+            if getattr(c, "presorted", False):
+                torch.cuda.current_stream(self.device).wait_stream(c.side)
+                c.presorted = False
+            else:
+                self._call(self.lib.cast_scatter_sort_sharded, keys.data_ptr(), nsrc, N, self.V_items,
+                           self.item_shard[1], self.shard_R, c.sws.data_ptr(), c.sws_bytes, self._stream())
+            if rows[0] is not c.g0:    # peers read the input-sequence gradient from the exported buffer
+                c.g0.copy_(rows[0])
+            c.shard_src = (nsrc, [c.g0] + list(rows[1:]), list(rowscale), list(scale))
+            return
         if table_name == "item_emb" and getattr(c, "presorted", False):
             torch.cuda.current_stream(self.device).wait_stream(c.side)   # join the side-stream sort
             c.presorted = False
@@ -601,7 +660,7 @@ class Engine:
     def tail_fusable(self):
         """final LayerNorm + loss + LayerNorm backward in one launch: the main tower's output must be seq_emb itself"""
         plan = self.plan
-        return (self.use_fused and bool(self.lib.cast_fused_supported(self.H))
+        return (self.use_fused and bool(self.lib.cast_fused_supported(self.H)) and self.item_shard is None
                 and not (plan.merge and plan.merge[3] == "post"))
 
     def loss_tail_fused(self, c):
@@ -629,11 +688,15 @@ class Engine:
                                         device=self.device)
             ws, ws_bytes, sums = c.ws_loss, c.ws_loss.numel() * 4, None
             c.reduce_jobs.append((c.ws_loss.data_ptr(), self.lib.cast_logits_loss_parts(c.N), 3, c.sums, 3))
-        self._call(self.lib.cast_logits_loss, c.seq_emb.data_ptr(), self.P["item_emb"].data_ptr(),
-                   self.P["item_emb"].shape[0], self.H, c.N, c.keys3[1].data_ptr(), c.keys3[2].data_ptr(),
-                   c.pos_logits.data_ptr(), c.neg_logits.data_ptr(), self._p(sums),
-                   c.dseq.data_ptr() if with_grad else None, c.gpos.data_ptr() if with_grad else None,
-                   c.gneg.data_ptr() if with_grad else None, ws.data_ptr(), ws_bytes, self._stream())
+        tail = (c.keys3[1].data_ptr(), c.keys3[2].data_ptr(), c.pos_logits.data_ptr(), c.neg_logits.data_ptr(),
+                self._p(sums), c.dseq.data_ptr() if with_grad else None, c.gpos.data_ptr() if with_grad else None,
+                c.gneg.data_ptr() if with_grad else None, ws.data_ptr(), ws_bytes, self._stream())
+        if self.item_shard is not None:
+            self._call(self.lib.cast_logits_loss_sharded, c.seq_emb.data_ptr(), self.shard_ptrs.data_ptr(),
+                       self.item_shard[1], self.V_items, self.H, c.N, *tail)
+        else:
+            self._call(self.lib.cast_logits_loss, c.seq_emb.data_ptr(), self.P["item_emb"].data_ptr(),
+                       self.P["item_emb"].shape[0], self.H, c.N, *tail)
 
     def backward(self, c):
         """Un-normalised gradients of sum(loss terms) into self.g (the 1/sum(istarget) factor — global under data
@@ -697,29 +760,12 @@ class Engine:
         c.reduce_jobs = []
 
     def adam(self, c):
-        # gradients are divided by sums[2] = sum(istarget) (global under data parallelism) inside the kernel
-        if self.shard is not None:
-            return self._adam_sharded()
+        # gradients are divided by sums[2] = sum(istarget) (global under data parallelism) inside the kernel; with a
+        # row-sharded item table the flat buffers hold this rank's shard first, so the same launch updates it
         self._call(self.lib.cast_adam_tf_step, self.w.data_ptr(), self.g.data_ptr(), self.m.data_ptr(),
                    self.v.data_ptr(), self.n_params, self.lr, self.beta1, self.beta2, self.eps,
                    self.sums[2:].data_ptr(), self.l2, 0, self.l2_hi if self.l2 else 0, self.adam_state.data_ptr(),
                    self._stream())
-
-    def _adam_sharded(self):
-        """Row-sharded item table (dist.attach(shard_item_table=True)): this rank applies TF-Adam to its own rows
-        (gradient = the reduce-scattered shard) and to the replicated remainder; the beta powers advance once."""
-        sh = self.shard
-        lo, n = sh.lo, sh.n            # element range of the own shard inside the item-table region
-        rest = sh.region               # first element after the (padded) item table
-        nrest = self.n_params - rest
-        l2 = self.l2
-        self._call(self.lib.cast_adam_tf_range, self.w[lo:].data_ptr(), sh.g_shard.data_ptr(),
-                   self.m[lo:].data_ptr(), self.v[lo:].data_ptr(), n, self.lr, self.beta1, self.beta2, self.eps,
-                   self.sums[2:].data_ptr(), l2, 0, n if l2 else 0, self.adam_state.data_ptr(), 0, self._stream())
-        self._call(self.lib.cast_adam_tf_range, self.w[rest:].data_ptr(), self.g[rest:].data_ptr(),
-                   self.m[rest:].data_ptr(), self.v[rest:].data_ptr(), nrest, self.lr, self.beta1, self.beta2,
-                   self.eps, self.sums[2:].data_ptr(), l2, 0, max(0, self.l2_hi - rest) if l2 else 0,
-                   self.adam_state.data_ptr(), 1, self._stream())
 
     def launch_fwd_bwd(self, c):
         # The sort of the (item id, entry) pairs for the embedding gradient depends on the ids only: it runs on a side
@@ -732,9 +778,13 @@ class Engine:
                 c.side = torch.cuda.Stream(device=self.device)
             c.side.wait_stream(main)
             with torch.cuda.stream(c.side):
-                V = self.P["item_emb"].shape[0]
-                self._call(self.lib.cast_scatter_sort, c.keys3.data_ptr(), 3, c.N, V, c.sws.data_ptr(), c.sws_bytes,
-                           c.side.cuda_stream)
+                if self.item_shard is not None:
+                    self._call(self.lib.cast_scatter_sort_sharded, c.keys3.data_ptr(), 3, c.N, self.V_items,
+                               self.item_shard[1], self.shard_R, c.sws.data_ptr(), c.sws_bytes, c.side.cuda_stream)
+                else:
+                    V = self.P["item_emb"].shape[0]
+                    self._call(self.lib.cast_scatter_sort, c.keys3.data_ptr(), 3, c.N, V, c.sws.data_ptr(),
+                               c.sws_bytes, c.side.cuda_stream)
             c.presorted = True
             if self.rowk_active():   # the weight operand images are needed by the first row kernel, not by the embedding
                 if getattr(c, "side2", None) is None:

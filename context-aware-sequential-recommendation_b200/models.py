@@ -21,10 +21,10 @@ class _Model:
     registry_name = "sasrec"
 
     def __init__(self, usernum, itemnum, args, *, device=None, use_graph: bool = True, _lib=None, seed=None,
-                 item_row_align: int = 1):
+                 item_shard=None, alloc=None):
         self.usernum, self.itemnum, self.args = usernum, itemnum, args
         self.engine = Engine(self.registry_name, usernum, itemnum, args, device=device, lib=_lib, seed=seed,
-                             item_row_align=item_row_align)
+                             item_shard=item_shard, alloc=alloc)
         self.use_graph = bool(use_graph) and self.engine.device.type == "cuda"
         self.attention_weights = None
         self.launches_per_step = None
@@ -109,6 +109,20 @@ class _Model:
         else:
             eng.launch_train_step(c)
 
+    def _score_cand(self, last, ld, B, cand, Cn, logits, cgt=None, ceq=None):
+        """logits (+ rank counts) of per-user candidate lists; the item rows come from the local table or, with a
+        row-sharded table, from the owning ranks' shards"""
+        eng = self.engine
+        p = eng._p
+        if eng.item_shard is not None:
+            eng._call(eng.lib.cast_score_rank_cand_sharded, last.data_ptr(), ld, eng.shard_ptrs.data_ptr(),
+                      eng.item_shard[1], eng.V_items, eng.H, B, cand.data_ptr(), Cn, logits.data_ptr(), p(cgt), p(ceq),
+                      eng._stream())
+        else:
+            eng._call(eng.lib.cast_score_rank_cand, last.data_ptr(), ld, eng.P["item_emb"].data_ptr(),
+                      eng.P["item_emb"].shape[0], eng.H, B, cand.data_ptr(), Cn, logits.data_ptr(), p(cgt), p(ceq),
+                      eng._stream())
+
     # ------------------------------------------------------------------ reference protocol
     def train_step_async(self, u, seq, pos, neg, time_seq=None, hours=None, days=None):
         """Enqueue one training step; returns the device tensor {sum loss terms, sum auc terms, sum istarget}."""
@@ -153,8 +167,7 @@ class _Model:
         cand = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(item_idx, (B, Cn)))).to(eng.device)
         logits = torch.empty(B, Cn, dtype=torch.float32, device=eng.device)
         last = c.seq_emb.view(B, T, H)[:, T - 1, :]
-        eng._call(eng.lib.cast_score_rank_cand, last.data_ptr(), T * H, eng.P["item_emb"].data_ptr(),
-                  eng.P["item_emb"].shape[0], H, B, cand.data_ptr(), Cn, logits.data_ptr(), None, None, eng._stream())
+        self._score_cand(last, T * H, B, cand, Cn, logits)
         self.attention_weights = c.attn
         return [logits.cpu().numpy(), c.attn.cpu().numpy()]
 
@@ -170,9 +183,7 @@ class _Model:
         cgt = torch.empty(B, dtype=torch.int32, device=eng.device)
         ceq = torch.empty(B, dtype=torch.int32, device=eng.device)
         last = c.seq_emb.view(B, T, H)[:, T - 1, :]
-        eng._call(eng.lib.cast_score_rank_cand, last.data_ptr(), T * H, eng.P["item_emb"].data_ptr(),
-                  eng.P["item_emb"].shape[0], H, B, cand_t.data_ptr(), Cn, logits.data_ptr(), cgt.data_ptr(),
-                  ceq.data_ptr(), eng._stream())
+        self._score_cand(last, T * H, B, cand_t, Cn, logits, cgt, ceq)
         return logits.cpu().numpy(), cgt.cpu().numpy(), ceq.cpu().numpy()
 
     def score_full_catalog(self, seq, target, rated=None, time_seq=None, hours=None, days=None, mode: int = 0):
@@ -180,6 +191,8 @@ class _Model:
         rated (rated: optional list of id collections, one per user).  mode 0 = tcgen05 tensor-core GEMM with exact
         band re-scoring, mode 1 = exact brute force.  Returns (count_greater [U], count_equal [U]) int32 arrays."""
         eng = self.engine
+        if eng.item_shard is not None:
+            return self._score_full_catalog_sharded(seq, target, rated, time_seq, hours, days, mode)
         c = self.forward_eval(seq, time_seq, hours, days)
         B, T, H = c.B, eng.T, eng.H
         dev = eng.device
@@ -203,7 +216,7 @@ class _Model:
             ws = self._pinned[("sfws", B)] = torch.empty(wsb // 4 + 16, dtype=torch.int32, device=dev)
         last = c.seq_emb.view(B, T, H)[:, T - 1, :]
         eng._call(eng.lib.cast_score_rank_full, last.data_ptr(), T * H, eng.P["item_emb"].data_ptr(), V, H, B,
-                  tgt.data_ptr(), eng._p(rptr), eng._p(ridx), mode, cgt.data_ptr(), ceq.data_ptr(), None,
+                  tgt.data_ptr(), None, eng._p(rptr), eng._p(ridx), mode, cgt.data_ptr(), ceq.data_ptr(), None,
                   ws.data_ptr(), wsb, eng._stream())
         if mode == 0:
             import ctypes
@@ -212,6 +225,70 @@ class _Model:
             if flag.value != 0:
                 raise RuntimeError("score_rank_full: tensor-core pass watchdog fired")
         return cgt.cpu().numpy(), ceq.cpu().numpy()
+
+    def _score_full_catalog_sharded(self, seq, target, rated, time_seq, hours, days, mode):
+        """Full-catalog ranks with the item table sharded by row: every rank runs the
+        forward pass for ITS users, the last-position vectors of all ranks are all-gathered, each rank counts — on the
+        tensor cores — the items of its own shard that beat the target (whose canonical score is gathered from the
+        owning shard), and ONE integer all-reduce adds the per-shard counts up.  Collective: all ranks call it with
+        their own users (same count on every rank)."""
+        import torch.distributed as dist
+        eng = self.engine
+        rank, world = eng.item_shard
+        dev = eng.device
+        c = self.forward_eval(seq, time_seq, hours, days)
+        B, T, H = c.B, eng.T, eng.H
+        last = c.seq_emb.view(B, T, H)[:, T - 1, :].contiguous()
+        tgt_loc = torch.from_numpy(np.ascontiguousarray(np.asarray(target, dtype=np.int32).reshape(-1))).to(dev)
+        U = B * world
+        last_all = torch.empty(U, H, dtype=torch.float32, device=dev)
+        tgt_all = torch.empty(U, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(last_all, last)
+        dist.all_gather_into_tensor(tgt_all, tgt_loc)
+        rated_all = [None] * world
+        dist.all_gather_object(rated_all, None if rated is None else [sorted(set(int(i) for i in r)) for r in rated])
+        # canonical target scores: one gather from the owning shards
+        tscore = torch.empty(U, 1, dtype=torch.float32, device=dev)
+        self._score_cand(last_all, H, U, tgt_all.view(U, 1), 1, tscore)
+        # this shard's view: local row of the target (0 = not here), local rows of the rated items
+        tg = tgt_all.cpu().numpy().astype(np.int64)
+        off = 1 if rank else 0
+        tl = np.where((tg % world == rank) & (tg > 0) & (tg < eng.V_items), tg // world + off, 0).astype(np.int32)
+        rptr = ridx = None
+        if rated is not None:
+            ptr = np.zeros(U + 1, np.int32)
+            flat = []
+            u = 0
+            for rl in rated_all:
+                for r in rl:
+                    ids = np.asarray(r, dtype=np.int64)
+                    ids = ids[(ids % world == rank) & (ids > 0) & (ids < eng.V_items)] // world + off
+                    flat.append(ids)
+                    ptr[u + 1] = ptr[u] + len(ids)
+                    u += 1
+            idx = np.concatenate(flat + [np.zeros(1, np.int64)]).astype(np.int32)
+            rptr, ridx = torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev)
+        v_loc = (eng.V_items - rank + world - 1) // world + off      # rows of this shard that hold items (+ the pad)
+        cgt = torch.zeros(U, dtype=torch.int32, device=dev)
+        ceq = torch.zeros(U, dtype=torch.int32, device=dev)
+        if v_loc > 1:
+            wsb = eng.lib.cast_score_rank_full_workspace_bytes(U, v_loc, H)
+            ws = self._pinned.get(("sfws", U))
+            if ws is None:
+                ws = self._pinned[("sfws", U)] = torch.empty(wsb // 4 + 16, dtype=torch.int32, device=dev)
+            eng._call(eng.lib.cast_score_rank_full, last_all.data_ptr(), H, eng.P["item_emb"].data_ptr(), v_loc, H, U,
+                      torch.from_numpy(tl).to(dev).data_ptr(), tscore.data_ptr(), eng._p(rptr), eng._p(ridx), mode,
+                      cgt.data_ptr(), ceq.data_ptr(), None, ws.data_ptr(), wsb, eng._stream())
+            if mode == 0 and dev.type == "cuda":
+                import ctypes
+                flag = ctypes.c_int(0)
+                eng._call(eng.lib.cast_score_rank_full_status, ws.data_ptr(), U, v_loc, ctypes.byref(flag), eng._stream())
+                if flag.value != 0:
+                    raise RuntimeError("score_rank_full: tensor-core pass watchdog fired")
+        both = torch.stack([cgt, ceq])
+        dist.all_reduce(both, op=dist.ReduceOp.SUM)
+        mine = slice(rank * B, (rank + 1) * B)
+        return both[0, mine].cpu().numpy(), both[1, mine].cpu().numpy()
 
     # parameter access by role name
     def state_dict(self):

@@ -24,6 +24,10 @@ def _work(name, a, B, T, H, h):
         return 6.0 * a[9] * a[10] * a[10], 4.0 * 5 * a[9] * a[10]
     if name == "cast_ln_ffn_fwd":   # 2 GEMMs        (a[13]=N, a[14]=H)
         return 4.0 * a[13] * a[14] * a[14], 4.0 * 4 * a[13] * a[14]
+    if name == "cast_rowk_ln_qkv_fwd":  # tcgen05 version (a[7]=N, a[8]=H)
+        return 6.0 * a[7] * a[8] * a[8], 4.0 * 5 * a[7] * a[8]
+    if name == "cast_rowk_ln_ffn_fwd":  # tcgen05 version (a[12]=N, a[13]=H)
+        return 4.0 * a[12] * a[13] * a[13], 4.0 * 4 * a[12] * a[13]
     if name == "cast_ffn_bwd":      # 2 dgrad + 2 wgrad  (a[14]=N, a[15]=H)
         return 8.0 * a[14] * a[15] * a[15], 4.0 * 5 * a[14] * a[15]
     if name == "cast_qkv_bwd":      # 3 dgrad + 3 wgrad  (a[12]=N, a[13]=H)
@@ -56,6 +60,7 @@ def profile_step(model, c, steps=5):
     eng = model.engine
     B, T, H, h = c.B, eng.T, eng.H, eng.h
     saved_allreduce, eng.grad_allreduce = eng.grad_allreduce, None  # rank-local profiling: no collective in here
+    saved_after, eng.after_adam = eng.after_adam, None
     eng.launch_train_step(c)  # warm
     torch.cuda.synchronize(eng.device)
     eng.timing = []
@@ -64,6 +69,7 @@ def profile_step(model, c, steps=5):
     torch.cuda.synchronize(eng.device)
     rec, eng.timing = eng.timing, None
     eng.grad_allreduce = saved_allreduce
+    eng.after_adam = saved_after
     agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
     for name, a, e0, e1 in rec:
         ms = e0.elapsed_time(e1)
@@ -97,7 +103,7 @@ def load_peaks(root):
 
 
 COMPUTE_BOUND = ("cast_attn_fwd", "cast_attn_bwd", "cast_gemm", "cast_qkv_bwd", "cast_ffn_bwd", "cast_ln_qkv_fwd",
-                 "cast_ln_ffn_fwd")
+                 "cast_ln_ffn_fwd", "cast_rowk_ln_qkv_fwd", "cast_rowk_ln_ffn_fwd")
 
 
 def ncu_traffic(root, name):

@@ -48,6 +48,37 @@ int cast_embed_fwd(const int* ids, const float* table, int V, int H, long N, int
                    const float* add, float drop_rate, unsigned long long seed, const unsigned long long* step,
                    int site, const int* mask_ids, float* out, void* stream);
 
+/* ---- row-sharded item table (BASELINE config 5): ownership is cyclic, item id -> rank id % n, local row
+ * id / n (+1 on ranks 1..n-1, whose local row 0 is a pad, so that "row 0 is not an item" holds on every shard).
+ * `shards` is a DEVICE array of n device pointers to the ranks' [rows_per_shard, H] shards (own shard + peer mappings
+ * read over NVLink, cast_peer_open).  The *_sharded gathers are otherwise identical to their namesakes. */
+int cast_embed_fwd_sharded(const int* ids, const float* const* shards, int nshards, int V, int H, long N, int T,
+                           float scale, const float* pos, const float* add, float drop_rate, unsigned long long seed,
+                           const unsigned long long* step, int site, const int* mask_ids, float* out, void* stream);
+int cast_logits_loss_sharded(const float* seq_emb, const float* const* shards, int nshards, int V, int H, long N,
+                             const int* pos, const int* neg, float* pos_logits, float* neg_logits, float* sums,
+                             float* dseq, float* gpos, float* gneg, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int cast_score_rank_cand_sharded(const float* seq_last, long ld, const float* const* shards, int nshards, int V, int H,
+                                 long U, const int* cand, int C, float* logits, int* count_greater, int* count_equal,
+                                 void* stream);
+/* Embedding-gradient exchange without a table collective: every rank sorts its (id, entry) pairs by owner-major key
+ * (cast_scatter_sort_sharded) and leaves the sorted arrays + its source rows in memory its peers can read; every owner
+ * then folds, rank by rank in rank order, the entries that belong to its rows into its dense gradient shard
+ * (cast_scatter_apply_range; keys of rank r: [r*rows_per_shard, (r+1)*rows_per_shard)).  cast_scatter_sorted_offsets
+ * locates the sorted arrays inside a sort workspace. */
+int cast_scatter_sort_sharded(const int* keys, int nsrc, long N, int V, int nshards, int rows_per_shard,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int cast_scatter_sorted_offsets(long N, int nsrc, int Vkeys, size_t* keys_offset, size_t* payload_offset);
+int cast_scatter_apply_range(int nsrc, long N, const float* const* rows, const float* const* rowscale,
+                             const float* scale, int H, float* dtable, const void* sorted_keys,
+                             const void* sorted_payload, unsigned key_lo, unsigned key_hi, void* partial,
+                             size_t partial_bytes, int accumulate, void* stream);
+/* CUDA IPC: map a peer process's device allocation (64-byte cudaIpcMemHandle obtained there) into this process with
+ * peer access enabled; returns the base pointer of the allocation.  One open per handle and process. */
+int cast_peer_open(const void* ipc_handle64, void** base_ptr);
+int cast_peer_close(void* base_ptr);
+
 /* element-wise backward of `x -> dropout(x) * mask`: out_masked = in*mask, out_masked_dropped = in*mask*dropout
  * (either output may be null).  Used for sasrec.py:59-62 and modules.py:307-311 backward. */
 int cast_mask_dropout(const float* in, const int* mask_ids, float drop_rate, unsigned long long seed,
@@ -290,11 +321,15 @@ int cast_score_rank_cand(const float* seq_last, long ld, const float* table, int
  * CSR of each user's already-seen item ids (unique per user; null => nothing excluded).
  * mode 0: tcgen05 tensor-core GEMM (3xTF32 split, accumulator in TMEM) + exact re-scoring of the error band;
  * mode 1: exact brute force.  Both return identical integers.  stats (optional, device, 2 x u64): [0] = number of
- * band candidates re-scored exactly. */
+ * band candidates re-scored exactly.
+ * target_score (optional, [U]): item-sharded evaluation: `table` is this rank's row shard, `target` the
+ * LOCAL row to leave out (0 when the target lives elsewhere) and its canonical score is handed in; the per-shard counts
+ * of all ranks add up (one integer all-reduce) to the whole-catalog counts. */
 size_t cast_score_rank_full_workspace_bytes(long U, int V, int H);
 int cast_score_rank_full(const float* seq_last, long ld, const float* table, int V, int H, long U, const int* target,
-                         const int* rated_ptr, const int* rated_idx, int mode, int* count_greater, int* count_equal,
-                         unsigned long long* stats, void* workspace, size_t workspace_bytes, void* stream);
+                         const float* target_score, const int* rated_ptr, const int* rated_idx, int mode,
+                         int* count_greater, int* count_equal, unsigned long long* stats, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* Synchronises the stream and reports the tensor-core pass's watchdog flag (0 = ok). */
 int cast_score_rank_full_status(const void* workspace, long U, int V, int* host_flag, void* stream);
 

@@ -20,7 +20,7 @@ wsb = lib.cast_score_rank_full_workspace_bytes(U, V, H)
 ws = torch.empty(wsb // 4 + 16, dtype=torch.int32, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 def run():
-    rc = lib.cast_score_rank_full(users.data_ptr(), H, table.data_ptr(), V, H, U, target.data_ptr(), None, None, mode,
+    rc = lib.cast_score_rank_full(users.data_ptr(), H, table.data_ptr(), V, H, U, target.data_ptr(), None, None, None, mode,
                                   cgt.data_ptr(), ceq.data_ptr(), stats.data_ptr(), ws.data_ptr(), wsb, st)
     assert rc == 0, lib.cast_last_error_string()
 run(); torch.cuda.synchronize()

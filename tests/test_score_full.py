@@ -42,7 +42,7 @@ def run(kind, U, V, H, mode, seed=0, ld_extra=0, ties=True):
     wsb = lib.cast_score_rank_full_workspace_bytes(U, V, H)
     ws = torch.empty(wsb // 4 + 16, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else None
-    rc = lib.cast_score_rank_full(tu.data_ptr(), H + ld_extra, tt.data_ptr(), V, H, U, tg.data_ptr(), tp.data_ptr(),
+    rc = lib.cast_score_rank_full(tu.data_ptr(), H + ld_extra, tt.data_ptr(), V, H, U, tg.data_ptr(), None, tp.data_ptr(),
                                   ti.data_ptr(), mode, cgt.data_ptr(), ceq.data_ptr(), stats.data_ptr(),
                                   ws.data_ptr(), wsb, stream)
     assert rc == 0, lib.cast_last_error_string()
