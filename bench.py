@@ -387,6 +387,38 @@ def main():
                     "note": "users sharded over the ranks, whole-job users / max-over-ranks wall time; host int32 "
                             "arrays in, ranks out (H2D + forward + scoring + D2H inside the timed region)"}
 
+    # ---- (2a') where a multi-GPU step goes: [forward+backward graph | exchange | Adam graph | end-of-step barrier]
+    step_split = None
+    if world > 1 and c.graph is not None and c.graph[1] is not None:
+        names = ("fwd_bwd", "exchange", "adam", "barrier")
+        acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        nrep = 5
+        for i in range(nrep + 2):
+            k3, c3 = dev_batches[i % len(dev_batches)]
+            c.keys3.copy_(k3)
+            c.cids.copy_(c3)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            evs[0].record()
+            c.graph[0].replay()
+            evs[1].record()
+            if eng.grad_allreduce is not None:
+                eng.grad_allreduce(c)
+            evs[2].record()
+            c.graph[1].replay()
+            evs[3].record()
+            if eng.after_adam is not None:
+                eng.after_adam()
+            evs[4].record()
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                acc += torch.tensor([evs[j].elapsed_time(evs[j + 1]) for j in range(4)], dtype=torch.float64, device=dev)
+        acc /= nrep
+        torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.MAX)
+        step_split = {n: float(v) for n, v in zip(names, acc.tolist())}
+        step_split["unit"] = "ms (max over ranks, L2 not flushed)"
+        step_split["exchange_is"] = ("all-reduce of dense gradients + owner pull of the item-table rows over NVLink"
+                                     if shard else "all-reduce of the flat gradient buffer")
+
     # ---- (2c) data-parallel parity ON THE BOX (world > 1): replicas bit-identical after the timed steps, and one
     # N-rank step == the same global batch processed by one rank (dropout off: ranks draw independent masks)
     dp_parity = None
@@ -415,6 +447,10 @@ def main():
         out["eval"] = eval_out
     if dp_parity is not None:
         out["dp_parity"] = dp_parity
+    if step_split is not None:
+        out["step_split"] = step_split
+    out["hbm_per_gpu"] = {"params_mb": eng.w.numel() * 4 / 1e6, "item_table_rows_local": int(eng.P["item_emb"].shape[0]),
+                          "item_table_rows_total": ITEMNUM + 1}
     if roofline is not None:
         out["roofline"] = roofline
         out["kernel_profile"] = kernels

@@ -48,26 +48,36 @@ class PeerArena:
         self._shm = []         # (SharedMemory, base address, size) segments this rank created
         self._keep = []
 
-    # ---- CPU backend: tensors allocated here live in named shared memory
     def alloc(self, numel: int, dtype):
-        from multiprocessing import shared_memory
+        """a zeroed buffer the other ranks can map: cudaMalloc + IPC handle (GPU) / named shared memory (CPU tests)"""
         import ctypes
-        nbytes = max(16, int(numel) * torch.empty(0, dtype=dtype).element_size())
+        nbytes = max(256, int(numel) * torch.empty(0, dtype=dtype).element_size())
+        if self.device.type == "cuda":
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            rc = self.lib.cast_peer_alloc(nbytes, ctypes.byref(ptr), handle)
+            if rc != 0:
+                from . import _lib
+                _lib.check(self.lib, rc, "cast_peer_alloc")
+            base = int(ptr.value)
+
+            class _Raw:   # torch wraps foreign device memory through the CUDA array interface (no copy, no ownership)
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (base, False), "version": 2}
+
+            t = torch.as_tensor(_Raw(), device=self.device)
+            self._shm.append((("ipc", handle.raw), base, nbytes))
+            return t.view(dtype)[:int(numel)]
+        from multiprocessing import shared_memory
         shm = shared_memory.SharedMemory(create=True, size=nbytes)
         base = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
         self._shm.append((shm, base, nbytes))
         return torch.frombuffer(shm.buf, dtype=dtype, count=int(numel))
 
     def _describe(self, t: torch.Tensor):
-        if t.device.type == "cuda":
-            st = t.untyped_storage()
-            info = st._share_cuda_()      # (device, ipc handle, storage size, offset of the storage in its allocation, ...)
-            return ("ipc", bytes(info[1]), int(info[3]) + t.storage_offset() * t.element_size())
         p = t.data_ptr()
-        for shm, base, nbytes in self._shm:
+        for seg, base, nbytes in self._shm:
             if base <= p < base + nbytes:
-                return ("shm", shm.name, p - base)
-        raise ValueError("PeerArena.ptrs: CPU tensors must come from PeerArena.alloc")
+                return (seg[0], seg[1], p - base) if isinstance(seg, tuple) else ("shm", seg.name, p - base)
+        raise ValueError("PeerArena.ptrs: the tensor must come from PeerArena.alloc")
 
     def _open(self, kind, key):
         if key in self._opened:
@@ -104,12 +114,16 @@ class PeerArena:
                 shm.close()
             except Exception:
                 pass
-        for shm, _, _ in self._shm:
+        for seg, base, _ in self._shm:
             try:
-                shm.close()
-                shm.unlink()
+                if isinstance(seg, tuple):
+                    self.lib.cast_peer_free(base)
+                else:
+                    seg.close()
+                    seg.unlink()
             except Exception:
                 pass
+        self._shm = []
 
 
 def attach(engine, group=None, arena=None):
@@ -160,7 +174,10 @@ def attach_sharded(engine, group=None, arena: "PeerArena | None" = None):
     dist.all_gather_object(seeds, int(engine.seed), group=group)
     if len(set(seeds)) != 1:   # each rank drew its rows of the table from the same stream only if the seeds agree
         raise ValueError(f"row-sharded item table: every rank must build the engine with the same seed, got {seeds}")
-    arena = arena or PeerArena(engine.lib, engine.device, group)
+    arena = arena or getattr(engine, "arena", None)
+    if arena is None:
+        raise ValueError("attach_sharded: the engine's peer-visible buffers must come from a PeerArena "
+                         "(Engine(..., item_shard=...) creates one when torch.distributed is initialised)")
     engine.arena = arena
     # dense weights and optimizer state: rank 0 wins; the table shards are consistent by construction (same draws)
     region = engine.P["item_emb"].numel()

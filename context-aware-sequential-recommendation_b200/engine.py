@@ -156,6 +156,11 @@ class Engine:
         self.V_items = itemnum + 1
         self.shard_R = shard_rows(itemnum, self.item_shard[1]) if self.item_shard else None
         self.alloc = alloc
+        self.arena = None
+        if self.item_shard is not None and alloc is None:
+            from . import dist as _dist      # peer-visible buffers (table shard, sorted entries, source rows)
+            self.arena = _dist.PeerArena(self.lib, self.device)
+            self.alloc = self.arena.alloc
         shapes, n_tables = param_shapes(self.plan, args, itemnum, self.shard_R)
         self.shapes = shapes
         total = sum(int(np.prod(s)) for _, s, _, _ in shapes)

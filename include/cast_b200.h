@@ -74,8 +74,11 @@ int cast_scatter_apply_range(int nsrc, long N, const float* const* rows, const f
                              const float* scale, int H, float* dtable, const void* sorted_keys,
                              const void* sorted_payload, unsigned key_lo, unsigned key_hi, void* partial,
                              size_t partial_bytes, int accumulate, void* stream);
-/* CUDA IPC: map a peer process's device allocation (64-byte cudaIpcMemHandle obtained there) into this process with
- * peer access enabled; returns the base pointer of the allocation.  One open per handle and process. */
+/* Peer memory (CUDA IPC).  cast_peer_alloc: a zeroed device allocation other processes of the box may map, and its
+ * 64-byte cudaIpcMemHandle; cast_peer_open maps a peer's allocation into this process with peer access enabled and
+ * returns its base pointer (one open per handle and process); both are setup-time calls (they synchronise). */
+int cast_peer_alloc(size_t bytes, void** ptr, void* ipc_handle64);
+int cast_peer_free(void* ptr);
 int cast_peer_open(const void* ipc_handle64, void** base_ptr);
 int cast_peer_close(void* base_ptr);
 
