@@ -191,7 +191,7 @@ def dp_parity_check(model, eng, c, dev_batches, B, world, rank, dev, shard):
     eng.launch_fwd_bwd(c)
     eng.grad_allreduce(c)
     torch.cuda.synchronize(dev)
-    g_dp = eng.gbuf.clone()
+    g_dp = eng.adam_g.clone()        # the exchanged gradients (what Adam consumes)
     # the same global batch on every rank, no exchange
     gk3 = [torch.zeros_like(k3) for _ in range(world)]
     gc3 = [torch.zeros_like(c3) for _ in range(world)]

@@ -88,6 +88,8 @@ SIGNATURES = {
     "cast_peer_free": (I, [P]),
     "cast_peer_open": (I, [P, P]),
     "cast_peer_close": (I, [P]),
+    "cast_peer_barrier": (I, [P, I, I, P, P]),
+    "cast_peer_reduce": (I, [P, I, L, P, P]),
     "cast_score_rank_full_status": (I, [P, L, I, P, P]),
 }
 

@@ -105,7 +105,8 @@ struct ScatterSrc {
   float scale[4];
 };
 
-constexpr int SEG_CHUNK = 64;  // sorted entries walked by one warp (two per lane)
+constexpr int SEG_CHUNK = 32;  // sorted entries walked by one warp (SEG_Q per lane): short walks, many warps in flight
+constexpr int SEG_Q = SEG_CHUNK / 32;
 // entries whose row loads are in flight together (NV = columns per lane): bounded so the staging registers stay <= 64
 
 // Stage 1: every warp walks SEG_CHUNK consecutive sorted entries, lanes own columns.  Each lane first resolves two
@@ -126,13 +127,13 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
   if (beg >= total) return;
   const long end = beg + SEG_CHUNK < total ? beg + SEG_CHUNK : total;
   const int cnt = (int)(end - beg);
-  constexpr int SEG_U = NV <= 4 ? 8 : (NV <= 8 ? 4 : 2);
+  constexpr int SEG_U = NV <= 8 ? 8 : (NV <= 16 ? 4 : 2);
   // ---- this lane's two entries
-  unsigned mk[2];
-  float mf[2];
-  const float* mrow[2];
+  unsigned mk[SEG_Q];
+  float mf[SEG_Q];
+  const float* mrow[SEG_Q];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < SEG_Q; ++q) {
     const long e = beg + lane + 32 * q;
     mk[q] = e < end ? skeys[e] : 0xffffffffu;
     mf[q] = 0.f;
@@ -145,7 +146,7 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
       mrow[q] = src.rows[s] + n * H;
     }
   }
-  const unsigned last_key = __shfl_sync(0xffffffffu, mk[(cnt - 1) >> 5], (cnt - 1) & 31);
+  const unsigned last_key = __shfl_sync(0xffffffffu, mk[SEG_Q == 1 ? 0 : ((cnt - 1) >> 5)], (cnt - 1) & 31);
   const unsigned first_key = __shfl_sync(0xffffffffu, mk[0], 0);
   // sorted => the whole chunk is padding (id 0) or lies outside the key range of this call: contributes nothing
   if (last_key == 0u || last_key < klo || first_key >= khi) {
@@ -166,10 +167,10 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
 #pragma unroll
     for (int u = 0; u < SEG_U; ++u) {
       const int e = e0 + u;  // < 64; entries >= cnt carry key 0xffffffff / null row
-      const int q = e >> 5, sl = e & 31;
-      const unsigned kk = __shfl_sync(0xffffffffu, q ? mk[1] : mk[0], sl);
-      const float ff = __shfl_sync(0xffffffffu, q ? mf[1] : mf[0], sl);
-      const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)(q ? mrow[1] : mrow[0]), sl);
+      const int q = SEG_Q == 1 ? 0 : (e >> 5), sl = e & 31;
+      const unsigned kk = __shfl_sync(0xffffffffu, mk[q], sl);
+      const float ff = __shfl_sync(0xffffffffu, mf[q], sl);
+      const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)mrow[q], sl);
       const float* row = reinterpret_cast<const float*>(rp);
       k[u] = kk;
       f[u] = ff;

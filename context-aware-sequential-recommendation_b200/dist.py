@@ -126,9 +126,56 @@ class PeerArena:
         self._shm = []
 
 
+class PeerExchange:
+    """The step's cross-rank traffic as plain kernel launches over peer memory (no collective library inside the
+    step, so the whole step is ONE CUDA graph): a flag barrier over NVLink (`cast_peer_barrier`) and the rank-ordered
+    sum of the ranks' flat gradient buffers (`cast_peer_reduce`: every rank reads the n buffers and adds them in rank
+    order => the same bits on every rank, reproducible run to run).  The engine's gradient buffer is re-homed into
+    peer-visible memory; Adam and the loss read-back consume the reduced copy."""
+
+    def __init__(self, engine, arena, group=None, first: int = 0):
+        import ctypes as C
+        self.eng, self.arena = engine, arena
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.first = int(first)               # elements before `first` are not reduced (a row-sharded table's gradient)
+        dev = engine.device
+        total = engine.gbuf.numel()
+        gnew = arena.alloc(total, torch.float32)
+        gnew.copy_(engine.gbuf)
+        engine.rebind_gradients(gnew)
+        self.count = total - self.first
+        self.g_red = torch.zeros(total, dtype=torch.float32, device=dev)
+        engine.adam_g = self.g_red
+        gp = arena.ptrs(engine.gbuf)
+        self.g_ptrs = torch.tensor([p + 4 * self.first for p in gp], dtype=torch.int64, device=dev)
+        self.flags = arena.alloc(max(8, self.world), torch.int64)
+        self.flag_ptrs = torch.tensor(arena.ptrs(self.flags), dtype=torch.int64, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def barrier(self):
+        e = self.eng
+        e._call(e.lib.cast_peer_barrier, self.flag_ptrs.data_ptr(), self.rank, self.world, self.state.data_ptr(),
+                e._stream())
+
+    def reduce(self):
+        e = self.eng
+        e._call(e.lib.cast_peer_reduce, self.g_ptrs.data_ptr(), self.world, self.count,
+                self.g_red.data_ptr() + 4 * self.first, e._stream())
+
+    def timed_out(self) -> bool:
+        return bool(self.state[1].item())
+
+
+def use_peer_exchange(engine) -> bool:
+    """peer-memory exchange unless CAST_DP_EXCHANGE=nccl (the process-group all-reduce, kept for A/B runs)"""
+    return os.environ.get("CAST_DP_EXCHANGE", "peer") != "nccl"
+
+
 def attach(engine, group=None, arena=None):
-    """Make `engine.launch_train_step` data parallel over `group` (default: the world group): replicated parameters,
-    one flat all-reduce of [gradient numerators | loss_sum, auc_sum, count] per step."""
+    """Make `engine.launch_train_step` data parallel over `group` (default: the world group): replicated parameters;
+    per step the ranks' [gradient numerators | loss_sum, auc_sum, count] buffers are summed in rank order, either by
+    every rank reading its peers' buffers over NVLink between two flag barriers (default: no collective call, the step
+    stays one CUDA graph) or by one process-group all-reduce (CAST_DP_EXCHANGE=nccl)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return engine
     if engine.item_shard is not None:
@@ -140,6 +187,23 @@ def attach(engine, group=None, arena=None):
         dist.broadcast(t, src=0, group=group)
     # independent dropout streams per rank (one global batch, different positions)
     engine.seed = (engine.seed + 0x9E3779B1 * engine.rank) & 0xFFFFFFFFFFFF
+
+    if use_peer_exchange(engine):
+        arena = arena or PeerArena(engine.lib, engine.device, group)
+        engine.arena = arena
+        px = engine.peer_exchange = PeerExchange(engine, arena, group)
+
+        def exchange(c):
+            px.barrier()      # every rank's gradient buffer is final
+            px.reduce()       # (Adam consumes the reduced copy)
+            px.barrier()      # everybody has read everybody: the buffers may be overwritten by the next backward pass
+
+        engine.grad_allreduce = exchange
+        engine.exchange_capturable = True
+        if engine.device.type == "cuda":
+            torch.cuda.synchronize(engine.device)
+        dist.barrier(group=group)
+        return engine
 
     def allreduce(c):
         dist.all_reduce(engine.gbuf, op=dist.ReduceOp.SUM, group=group)
@@ -206,19 +270,31 @@ def attach_sharded(engine, group=None, arena: "PeerArena | None" = None):
             view.append((rows_a, rs_a, ws[p] + ko.value, ws[p] + po.value))
         c.peer = SimpleNamespace(view=view, scale=(C.c_float * nsrc)(*scale), nsrc=nsrc)
 
+    px = None
+    if use_peer_exchange(engine):
+        px = engine.peer_exchange = PeerExchange(engine, arena, group, first=region)
+        engine.exchange_capturable = True
+
     def exchange(c):
-        dist.all_reduce(engine.gbuf[region:], op=dist.ReduceOp.SUM, group=group)
+        if px is not None:
+            px.barrier()    # every rank's dense gradients, sorted entries and source rows are final
+            px.reduce()     # dense gradients + loss sums, rank order
+        else:
+            dist.all_reduce(engine.gbuf[region:], op=dist.ReduceOp.SUM, group=group)
         if c.peer is None:
             build_peer_view(c)
         pv = c.peer
         for p in range(world):
             rows_a, rs_a, keys_p, pay_p = pv.view[p]
             engine._call(engine.lib.cast_scatter_apply_range, pv.nsrc, c.N, rows_a, rs_a, pv.scale, H,
-                         engine.G["item_emb"].data_ptr(), keys_p, pay_p, rank * R, (rank + 1) * R, c.spart.data_ptr(),
+                         engine.adam_g.data_ptr(), keys_p, pay_p, rank * R, (rank + 1) * R, c.spart.data_ptr(),
                          c.spart_bytes, 1 if p else 0, engine._stream())
 
     def end_of_step():
-        dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=group)
+        if px is not None:
+            px.barrier()    # shards are updated; exported buffers may be overwritten
+        else:
+            dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=group)
 
     engine.grad_allreduce = exchange
     engine.after_adam = end_of_step

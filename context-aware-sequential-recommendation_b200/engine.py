@@ -202,6 +202,8 @@ class Engine:
             self.rowk_wptrs = (C.c_void_p * len(ptrs))(*ptrs)
         self.world_size = 1
         self.grad_allreduce = None  # set by dist.attach(); called between backward and Adam
+        self.adam_g = self.gbuf     # what Adam consumes: the local buffer, or the rank-ordered sum (dist.PeerExchange)
+        self.exchange_capturable = False   # the exchange is plain kernel launches => the step is one CUDA graph
         self.after_adam = None      # set by dist.attach_sharded(): the barrier that ends a row-sharded step
         self.shard_ptrs = None      # ... device array of the ranks' item-table shard pointers (own + peer mappings)
 
@@ -262,6 +264,25 @@ class Engine:
         off = 1 if rank else 0
         out[off:off + mine.shape[0]] = mine
         return out
+
+    def rebind_gradients(self, gbuf: torch.Tensor):
+        """move the flat gradient buffer (and every view of it) to `gbuf` — peer-visible memory for data parallelism"""
+        assert gbuf.numel() == self.gbuf.numel()
+        local = self.adam_g is self.gbuf
+        self.gbuf = gbuf
+        self.g = gbuf[:self.n_params]
+        self.sums = gbuf[self.n_params:]
+        for name, shape, _, _ in self.shapes:
+            off = self.offsets[name]
+            self.G[name] = self.g[off:off + int(np.prod(shape))].view(*shape)
+        if local:
+            self.adam_g = gbuf
+        for c in self._ctx.values():
+            c.sums = self.sums
+
+    def global_sums(self) -> torch.Tensor:
+        """{sum loss terms, sum auc terms, sum istarget, pad} of the whole (global) batch after the exchange"""
+        return self.adam_g[self.n_params:]
 
     def load_parameters(self, params: Dict[str, "torch.Tensor | np.ndarray"]):
         for k, v in params.items():
@@ -767,10 +788,10 @@ class Engine:
     def adam(self, c):
         # gradients are divided by sums[2] = sum(istarget) (global under data parallelism) inside the kernel; with a
         # row-sharded item table the flat buffers hold this rank's shard first, so the same launch updates it
-        self._call(self.lib.cast_adam_tf_step, self.w.data_ptr(), self.g.data_ptr(), self.m.data_ptr(),
+        self._call(self.lib.cast_adam_tf_step, self.w.data_ptr(), self.adam_g.data_ptr(), self.m.data_ptr(),
                    self.v.data_ptr(), self.n_params, self.lr, self.beta1, self.beta2, self.eps,
-                   self.sums[2:].data_ptr(), self.l2, 0, self.l2_hi if self.l2 else 0, self.adam_state.data_ptr(),
-                   self._stream())
+                   self.adam_g[self.n_params + 2:].data_ptr(), self.l2, 0, self.l2_hi if self.l2 else 0,
+                   self.adam_state.data_ptr(), self._stream())
 
     def launch_fwd_bwd(self, c):
         # The sort of the (item id, entry) pairs for the embedding gradient depends on the ids only: it runs on a side

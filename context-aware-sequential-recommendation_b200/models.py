@@ -78,12 +78,17 @@ class _Model:
         s = torch.cuda.Stream(device=eng.device)
         s.wait_stream(torch.cuda.current_stream(eng.device))
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        single = eng.grad_allreduce is None and eng.after_adam is None  # one process: the whole step is one graph
+        # one process, or an exchange made of kernel launches only (dist.PeerExchange): the whole step is one graph
+        single = (eng.grad_allreduce is None and eng.after_adam is None) or eng.exchange_capturable
         with torch.cuda.stream(s):
             with torch.cuda.graph(g1, stream=s):
                 eng.launch_fwd_bwd(c)
                 if single:
+                    if eng.grad_allreduce is not None:
+                        eng.grad_allreduce(c)
                     eng.adam(c)
+                    if eng.after_adam is not None:
+                        eng.after_adam()
             if not single:
                 with torch.cuda.graph(g2, stream=s):
                     eng.adam(c)
@@ -132,7 +137,7 @@ class _Model:
         c = eng.ctx(B)
         self._stage(c, seq, pos, neg, time_seq, hours, days)
         self.launch(c)
-        return eng.sums
+        return eng.global_sums()
 
     def train_step(self, u, seq, pos, neg, time_seq=None, hours=None, days=None):
         """== sess.run([model.auc, model.loss, model.train_op], feed) of reference main.py:212-219."""

@@ -81,6 +81,12 @@ int cast_peer_alloc(size_t bytes, void** ptr, void* ipc_handle64);
 int cast_peer_free(void* ptr);
 int cast_peer_open(const void* ipc_handle64, void** base_ptr);
 int cast_peer_close(void* base_ptr);
+/* Gradient exchange of data-parallel training over peer memory (no collective library in the step; everything below is
+ * a plain kernel launch, so the whole step is one CUDA graph): cast_peer_barrier = flag barrier over NVLink (flags:
+ * DEVICE array of n pointers to the ranks' n x u64 arrival arrays; state: this rank's {epoch, timed-out flag});
+ * cast_peer_reduce: out[i] = sum over ranks, in rank order, of grads[r][i] — the same bits on every rank. */
+int cast_peer_barrier(void* const* flags, int rank, int n, void* state, void* stream);
+int cast_peer_reduce(const void* const* grads, int n, long count, float* out, void* stream);
 
 /* element-wise backward of `x -> dropout(x) * mask`: out_masked = in*mask, out_masked_dropped = in*mask*dropout
  * (either output may be null).  Used for sasrec.py:59-62 and modules.py:307-311 backward. */

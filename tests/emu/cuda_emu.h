@@ -171,6 +171,7 @@ static inline int atomicMax(int* p, int v) {
 }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ---- math / misc intrinsics
 static inline float __fdividef(float a, float b) { return a / b; }

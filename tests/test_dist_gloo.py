@@ -30,9 +30,9 @@ def _load_batch(eng, gb, lo, hi):
     return c
 
 
-def _worker(rank, world, port, model, out, shard=False):
+def _worker(rank, world, port, model, out, shard=False, exchange="peer"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
+                      LOCAL_RANK=str(rank), CAST_DP_EXCHANGE=exchange)
     from cast_b200 import dist as cdist
     from cast_b200 import evaluation as cev
     cdist.init_from_env("gloo")
@@ -55,14 +55,14 @@ def _worker(rank, world, port, model, out, shard=False):
     w = [torch.zeros_like(eng.w) for _ in range(world)]
     g = [torch.zeros_like(eng.gbuf) for _ in range(world)]
     dist.all_gather(w, eng.w.clone())
-    dist.all_gather(g, eng.gbuf.clone())
+    dist.all_gather(g, eng.adam_g.clone())          # the exchanged gradients (what Adam consumed)
     region = eng.P["item_emb"].numel() if shard else 0
     assert torch.equal(w[0][region:], w[1][region:])     # replicas identical after the step
     if rank == 0:
         single = Engine(model, 80, 300, args, device=dev, lib=lib, seed=5)
         cs = _load_batch(single, gb, 0, B)
         single.launch_train_step(cs)
-        res = {"g_dp": eng.gbuf.numpy().copy(), "g_1": single.gbuf.numpy().copy(), "w_dp": eng.w.numpy().copy(),
+        res = {"g_dp": eng.adam_g.numpy().copy(), "g_1": single.gbuf.numpy().copy(), "w_dp": eng.w.numpy().copy(),
                "w_1": single.w.numpy().copy(), "hist": hist.numpy().copy(), "shard": (lo, hi),
                "offsets": dict(single.offsets), "sizes": {k: v.numel() for k, v in single.P.items()},
                "w_all": [x.numpy().copy() for x in w], "g_all": [x.numpy().copy() for x in g],
@@ -75,10 +75,12 @@ def _worker(rank, world, port, model, out, shard=False):
 
 
 @pytest.mark.emu
-@pytest.mark.parametrize("model", ["sasrec", "cast_1"])
-def test_two_rank_step_equals_single_process(tmp_path, model):
+@pytest.mark.parametrize("model,exchange", [("sasrec", "peer"), ("cast_1", "peer"), ("sasrec", "nccl")])
+def test_two_rank_step_equals_single_process(tmp_path, model, exchange):
+    """exchange = "peer": rank-ordered sum over peer memory between two flag barriers (dist.PeerExchange; shared memory
+    stands in for NVLink); "nccl": the process-group all-reduce (gloo here)."""
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(2, _free_port(), model, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), model, out, False, exchange), nprocs=2, join=True)
     r = torch.load(out, weights_only=False)
     g_dp, g_1 = r["g_dp"], r["g_1"]
     assert abs(g_dp[-2] - g_1[-2]) == 0            # sum(istarget): exact
