@@ -84,6 +84,8 @@ SIGNATURES = {
     "cast_scatter_sort_sharded": (I, [P, I, L, I, I, I, P, SZ, P]),
     "cast_scatter_sorted_offsets": (I, [L, I, I, P, P]),
     "cast_scatter_apply_range": (I, [I, L, P, P, P, I, P, P, P, C.c_uint, C.c_uint, P, SZ, I, P]),
+    "cast_scatter_stage_bytes": (SZ, [L, I, I]),
+    "cast_scatter_pull_range": (I, [I, L, P, P, P, I, P, P, P, C.c_uint, C.c_uint, P, SZ, P, SZ, I, P]),
     "cast_peer_alloc": (I, [SZ, P, P]),
     "cast_peer_free": (I, [P]),
     "cast_peer_open": (I, [P, P]),

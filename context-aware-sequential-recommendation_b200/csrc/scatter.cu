@@ -139,7 +139,7 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
     mf[q] = 0.f;
     mrow[q] = nullptr;
     if (e < end && mk[q] != 0u && mk[q] >= klo && mk[q] < khi) {
-      const unsigned p = spay[e];
+      const unsigned p = spay ? spay[e] : (unsigned)e;
       const int s = (int)(p / N);
       const long n = (long)p - (long)s * N;
       mf[q] = src.scale[s] * (src.rowscale[s] ? src.rowscale[s][n] : 1.0f);
@@ -305,6 +305,31 @@ __global__ void shard_keys_kernel(const int* __restrict__ ids, long total, int V
   }
 }
 
+// Owner pull, first half: the entries of a peer's sorted arrays whose key lies in [klo, khi) are fetched — one warp
+// per entry, thousands of independent rows in flight over NVLink — into local staging (row e of `stage`, factor
+// stage_f[e]); the segment sums then walk local memory.  (Walking the peer's rows directly serialises on NVLink
+// latency: 450 us instead of 40 us for 38k rows of 1 KB.)
+__global__ void pull_gather_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay, long total,
+                                   long N, ScatterSrc src, unsigned klo, unsigned khi, int H,
+                                   float* __restrict__ stage, float* __restrict__ stage_f) {
+  const int lane = threadIdx.x & 31;
+  const long e = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= total) return;
+  const unsigned k = skeys[e];
+  if (k == 0u || k < klo || k >= khi) return;
+  const unsigned p = spay[e];
+  const int s = (int)(p / N);
+  const long n = (long)p - (long)s * N;
+  const float* row = src.rows[s] + n * H;
+  float* out = stage + e * H;
+  if ((H & 3) == 0) {
+    for (int c = 4 * lane; c < H; c += 128) *reinterpret_cast<float4*>(out + c) = *reinterpret_cast<const float4*>(row + c);
+  } else {
+    for (int c = lane; c < H; c += 32) out[c] = row[c];
+  }
+  if (lane == 0) stage_f[e] = src.scale[s] * (src.rowscale[s] ? src.rowscale[s][n] : 1.0f);
+}
+
 // number of radix passes and digit width for a table of V rows (ids < V)
 static inline void key_plan(int V, int* passes, int* dbits) {
   int bits = 1;
@@ -406,7 +431,7 @@ static int scatter_apply_impl(int nsrc, long N, const float* const* rows, const 
                               const float* scale, int H, float* dtable, long dtable_rows, const unsigned* kin,
                               const unsigned* pin, unsigned klo, unsigned khi, void* partial, size_t partial_bytes,
                               int accumulate, void* stream) {
-  if (!rows || !scale || !dtable || !kin || !pin || nsrc < 1 || nsrc > 4 || N <= 0 || H <= 0 || H > 1024 || khi <= klo)
+  if (!rows || !scale || !dtable || !kin || nsrc < 1 || nsrc > 4 || N <= 0 || H <= 0 || H > 1024 || khi <= klo)
     return set_error(CAST_ERR_BAD_ARG, "scatter_apply");
   const long total = N * nsrc;
   if (!partial || partial_bytes < cast_scatter_partial_bytes(N, nsrc, H))
@@ -473,6 +498,45 @@ extern "C" int cast_scatter_apply_range(int nsrc, long N, const float* const* ro
   return scatter_apply_impl(nsrc, N, rows, rowscale, scale, H, dtable, (long)key_hi - (long)key_lo,
                             static_cast<const unsigned*>(sorted_keys), static_cast<const unsigned*>(sorted_payload),
                             key_lo, key_hi, partial, partial_bytes, accumulate, stream);
+}
+
+/* cast_scatter_apply_range for a PEER's entries: its in-range rows are first gathered into `stage`
+ * (cast_scatter_stage_bytes: N*nsrc rows + factors, local memory) with one warp per entry, then summed locally with
+ * the same arithmetic (bit-identical to cast_scatter_apply_range on the same data). */
+extern "C" size_t cast_scatter_stage_bytes(long N, int nsrc, int H) {
+  return (size_t)N * nsrc * ((size_t)H + 1) * sizeof(float) + 256;
+}
+
+extern "C" int cast_scatter_pull_range(int nsrc, long N, const float* const* rows, const float* const* rowscale,
+                                       const float* scale, int H, float* dtable, const void* sorted_keys,
+                                       const void* sorted_payload, unsigned key_lo, unsigned key_hi, void* stage,
+                                       size_t stage_bytes, void* partial, size_t partial_bytes, int accumulate,
+                                       void* stream) {
+  if (!rows || !scale || !sorted_keys || !sorted_payload || nsrc < 1 || nsrc > 4 || N <= 0 || H <= 0)
+    return set_error(CAST_ERR_BAD_ARG, "scatter_pull_range");
+  if (!stage || stage_bytes < cast_scatter_stage_bytes(N, nsrc, H))
+    return set_error(CAST_ERR_WORKSPACE, "scatter_pull_range: staging buffer too small");
+  const long total = N * nsrc;
+  ScatterSrc src;
+  for (int s = 0; s < 4; ++s) {
+    src.rows[s] = s < nsrc ? rows[s] : nullptr;
+    src.rowscale[s] = (s < nsrc && rowscale) ? rowscale[s] : nullptr;
+    src.scale[s] = s < nsrc ? scale[s] : 0.f;
+  }
+  float* st_rows = static_cast<float*>(stage);
+  float* st_f = st_rows + (size_t)total * H;
+  const int wpb = 8;
+  CAST_LAUNCH(pull_gather_kernel, dim3((unsigned)cdiv(total, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream,
+              static_cast<const unsigned*>(sorted_keys), static_cast<const unsigned*>(sorted_payload), total, N, src,
+              key_lo, key_hi, H, st_rows, st_f);
+  int rc = check_launch("pull_gather");
+  if (rc) return rc;
+  const float* lrows[1] = {st_rows};
+  const float* lscale_rows[1] = {st_f};
+  const float one[1] = {1.0f};
+  return scatter_apply_impl(1, total, lrows, lscale_rows, one, H, dtable, (long)key_hi - (long)key_lo,
+                            static_cast<const unsigned*>(sorted_keys), nullptr, key_lo, key_hi, partial, partial_bytes,
+                            accumulate, stream);
 }
 
 extern "C" int cast_scatter_rows(const int* keys, int nsrc, long N, const float* const* rows,

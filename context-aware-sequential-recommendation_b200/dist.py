@@ -268,7 +268,12 @@ def attach_sharded(engine, group=None, arena: "PeerArena | None" = None):
             rows_a = (C.c_void_p * nsrc)(*[uniq[id(t)][p] for t in rows])
             rs_a = (C.c_void_p * nsrc)(*[(uniq[id(t)][p] if t is not None else None) for t in rowscale])
             view.append((rows_a, rs_a, ws[p] + ko.value, ws[p] + po.value))
-        c.peer = SimpleNamespace(view=view, scale=(C.c_float * nsrc)(*scale), nsrc=nsrc)
+        stage = torch.empty(engine.lib.cast_scatter_stage_bytes(c.N, nsrc, H) // 4 + 16, dtype=torch.float32,
+                            device=engine.device)
+        # (the staged pass runs as ONE source of N*nsrc rows: its chunk partials need their own, larger scratch)
+        spart = torch.empty(engine.lib.cast_scatter_partial_bytes(c.N * nsrc, 1, H) // 4 + 16, dtype=torch.float32,
+                            device=engine.device)
+        c.peer = SimpleNamespace(view=view, scale=(C.c_float * nsrc)(*scale), nsrc=nsrc, stage=stage, spart=spart)
 
     px = None
     if use_peer_exchange(engine):
@@ -286,9 +291,15 @@ def attach_sharded(engine, group=None, arena: "PeerArena | None" = None):
         pv = c.peer
         for p in range(world):
             rows_a, rs_a, keys_p, pay_p = pv.view[p]
-            engine._call(engine.lib.cast_scatter_apply_range, pv.nsrc, c.N, rows_a, rs_a, pv.scale, H,
-                         engine.adam_g.data_ptr(), keys_p, pay_p, rank * R, (rank + 1) * R, c.spart.data_ptr(),
-                         c.spart_bytes, 1 if p else 0, engine._stream())
+            if p == rank:   # own entries: summed straight from the source rows
+                engine._call(engine.lib.cast_scatter_apply_range, pv.nsrc, c.N, rows_a, rs_a, pv.scale, H,
+                             engine.adam_g.data_ptr(), keys_p, pay_p, rank * R, (rank + 1) * R, c.spart.data_ptr(),
+                             c.spart_bytes, 1 if p else 0, engine._stream())
+            else:           # a peer's entries: gathered over NVLink with one warp per row, then summed locally
+                engine._call(engine.lib.cast_scatter_pull_range, pv.nsrc, c.N, rows_a, rs_a, pv.scale, H,
+                             engine.adam_g.data_ptr(), keys_p, pay_p, rank * R, (rank + 1) * R, pv.stage.data_ptr(),
+                             pv.stage.numel() * 4, pv.spart.data_ptr(), pv.spart.numel() * 4, 1 if p else 0,
+                             engine._stream())
 
     def end_of_step():
         if px is not None:

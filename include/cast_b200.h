@@ -74,6 +74,13 @@ int cast_scatter_apply_range(int nsrc, long N, const float* const* rows, const f
                              const float* scale, int H, float* dtable, const void* sorted_keys,
                              const void* sorted_payload, unsigned key_lo, unsigned key_hi, void* partial,
                              size_t partial_bytes, int accumulate, void* stream);
+/* cast_scatter_apply_range for a PEER's entries: its in-range rows are first gathered (one warp per entry: thousands
+ * of rows in flight over NVLink) into local staging of cast_scatter_stage_bytes, then summed locally; same arithmetic. */
+size_t cast_scatter_stage_bytes(long N, int nsrc, int H);
+int cast_scatter_pull_range(int nsrc, long N, const float* const* rows, const float* const* rowscale,
+                            const float* scale, int H, float* dtable, const void* sorted_keys,
+                            const void* sorted_payload, unsigned key_lo, unsigned key_hi, void* stage,
+                            size_t stage_bytes, void* partial, size_t partial_bytes, int accumulate, void* stream);
 /* Peer memory (CUDA IPC).  cast_peer_alloc: a zeroed device allocation other processes of the box may map, and its
  * 64-byte cudaIpcMemHandle; cast_peer_open maps a peer's allocation into this process with peer access enabled and
  * returns its base pointer (one open per handle and process); both are setup-time calls (they synchronise). */
