@@ -389,8 +389,9 @@ def main():
 
     # ---- (2a') where a multi-GPU step goes: [forward+backward graph | exchange | Adam graph | end-of-step barrier]
     step_split = None
-    if world > 1 and c.graph is not None and c.graph[1] is not None:
-        names = ("fwd_bwd", "exchange", "adam", "barrier")
+    if world > 1:
+        # eager launches of the same kernels, one CUDA event per segment (in the timed runs the step is one graph)
+        names = ("fwd_bwd", "exchange", "adam", "end_of_step_barrier")
         acc = torch.zeros(4, dtype=torch.float64, device=dev)
         nrep = 5
         for i in range(nrep + 2):
@@ -399,12 +400,12 @@ def main():
             c.cids.copy_(c3)
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             evs[0].record()
-            c.graph[0].replay()
+            eng.launch_fwd_bwd(c)
             evs[1].record()
             if eng.grad_allreduce is not None:
                 eng.grad_allreduce(c)
             evs[2].record()
-            c.graph[1].replay()
+            eng.adam(c)
             evs[3].record()
             if eng.after_adam is not None:
                 eng.after_adam()
@@ -413,11 +414,18 @@ def main():
             if i >= 2:
                 acc += torch.tensor([evs[j].elapsed_time(evs[j + 1]) for j in range(4)], dtype=torch.float64, device=dev)
         acc /= nrep
-        torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.MAX)
-        step_split = {n: float(v) for n, v in zip(names, acc.tolist())}
-        step_split["unit"] = "ms (max over ranks, L2 not flushed)"
-        step_split["exchange_is"] = ("all-reduce of dense gradients + owner pull of the item-table rows over NVLink"
-                                     if shard else "all-reduce of the flat gradient buffer")
+        mx = acc.clone()
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        mn = acc.clone()
+        torch.distributed.all_reduce(mn, op=torch.distributed.ReduceOp.MIN)
+        step_split = {n: {"max_ms": float(a_), "min_ms": float(b_)} for n, a_, b_ in zip(names, mx.tolist(), mn.tolist())}
+        step_split["note"] = ("eager launches (the timed step replays them as one CUDA graph), L2 not flushed; a rank "
+                              "that finishes its backward pass early waits inside `exchange` for the slowest one: "
+                              "min over ranks is the exchange itself")
+        step_split["exchange_is"] = (("flag barrier + rank-ordered sum of the dense gradients over peer memory" if
+                                      eng.exchange_capturable else "process-group all-reduce of the dense gradients") +
+                                     (" + owner pull of the item-table rows over NVLink (one staged gather + local "
+                                      "segment sums per peer, rank order)" if shard else ""))
 
     # ---- (2c) data-parallel parity ON THE BOX (world > 1): replicas bit-identical after the timed steps, and one
     # N-rank step == the same global batch processed by one rank (dropout off: ranks draw independent masks)
