@@ -18,6 +18,7 @@ SIGNATURES = {
     "cast_version": (I, []),
     "cast_last_error_string": (C.c_char_p, []),
     "cast_launch_count": (U64, []),
+    "cast_crc32c": (C.c_uint, [P, SZ, C.c_uint]),
     "cast_embed_fwd": (I, [P, P, I, I, L, I, F, P, P, F, U64, P, I, P, P, P]),
     "cast_mask_dropout": (I, [P, P, F, U64, P, I, L, I, P, P, P]),
     "cast_concat_dropout_fwd": (I, [P, I, I, L, I, F, I, F, I, U64, P, P, P]),

@@ -8,8 +8,10 @@ so reference-trained weights load into the CUDA path (`--test_model` behaviour) 
 back by the reference.
 
     vars = read_bundle(".../model.ckpt")                       # {tf name: ndarray}
-    params = to_role_names("sasrec", vars, num_blocks=2)       # {role name: ndarray}  (Adam slots are skipped)
+    params = to_role_names("cast_4", vars, num_blocks=2)       # {role name: ndarray}
     model.load_state_dict(params)
+    save_model(prefix, model, "cast_4", num_blocks=2)          # weights + Adam slots + beta powers + global_step
+    restore_model(prefix, model, "cast_4", num_blocks=2)       # ... and back (training resumes bit-exactly)
 """
 from __future__ import annotations
 
@@ -100,8 +102,7 @@ def _read_block(buf: bytes, offset: int, size: int) -> bytes:
     return buf[offset:offset + size]
 
 
-def read_bundle(prefix: str) -> Dict[str, np.ndarray]:
-    """All tensors of `<prefix>.index` / `<prefix>.data-00000-of-00001`."""
+def _index_entries(prefix: str) -> Dict[str, bytes]:
     with open(prefix + ".index", "rb") as f:
         idx = f.read()
     if struct.unpack_from("<Q", idx, len(idx) - 8)[0] != _MAGIC:
@@ -118,6 +119,23 @@ def read_bundle(prefix: str) -> Dict[str, np.ndarray]:
         bsize, _ = _varint(handle, p)
         for k, v in _block_entries(_read_block(idx, boff, bsize)):
             entries[k.decode()] = v
+    return entries
+
+
+def read_bundle_crcs(prefix: str) -> Dict[str, int]:
+    """the masked crc32c TensorFlow stored for every tensor (BundleEntryProto.crc32c, field 6)"""
+    out = {}
+    for name, raw in _index_entries(prefix).items():
+        if name:
+            e = _parse_proto(raw)
+            if 6 in e:
+                out[name] = int(e[6][0])
+    return out
+
+
+def read_bundle(prefix: str) -> Dict[str, np.ndarray]:
+    """All tensors of `<prefix>.index` / `<prefix>.data-00000-of-00001`."""
+    entries = _index_entries(prefix)
     with open(prefix + ".data-00000-of-00001", "rb") as f:
         data = f.read()
     out = {}
@@ -137,6 +155,28 @@ _CRC_TABLE = None
 
 
 def _crc32c(data: bytes) -> int:
+    lib = _crc_lib()
+    if lib is not None:
+        return int(lib.cast_crc32c(data, len(data), 0))
+    return _crc32c_py(data)
+
+
+_CRC_LIB = False
+
+
+def _crc_lib():
+    """the C library's slicing-by-8 crc32c (host code; loads without a GPU).  None if the library is not built."""
+    global _CRC_LIB
+    if _CRC_LIB is False:
+        try:
+            from . import _lib
+            _CRC_LIB = _lib.load_library()
+        except Exception:
+            _CRC_LIB = None
+    return _CRC_LIB
+
+
+def _crc32c_py(data: bytes) -> int:
     global _CRC_TABLE
     if _CRC_TABLE is None:
         t = []
@@ -173,9 +213,10 @@ def _with_trailer(block: bytes) -> bytes:
     return block + b"\x00" + struct.pack("<I", _mask_crc(_crc32c(block + b"\x00")))
 
 
-def write_bundle(prefix: str, tensors: Dict[str, np.ndarray], checksum_data: bool = False):
-    """Writes `<prefix>.index` + `<prefix>.data-00000-of-00001` readable by `read_bundle` (and by TF's loader; the
-    per-tensor crc32c field is filled only when `checksum_data` is set — pure-Python crc32c is slow on big tables)."""
+def write_bundle(prefix: str, tensors: Dict[str, np.ndarray], checksum_data: bool = True):
+    """Writes `<prefix>.index` + `<prefix>.data-00000-of-00001` in TensorFlow's tensor-bundle format: uncompressed
+    SSTable of BundleEntryProtos with the masked crc32c of every tensor (TF's BundleReader verifies it on every read;
+    tests/test_checkpoint.py checks the field byte for byte against the reference's own index)."""
     names = sorted(tensors)
     data, pairs = bytearray(), []
     header = b"\x08\x01" + b"\x1a\x02\x08\x01"          # num_shards=1, version{producer=1}
@@ -220,32 +261,127 @@ def _block_map(tf_scope: str, role: str):
     return m
 
 
+DEAD = "<dead>"   # variables the reference creates but never trains (kept at their init, written back as such)
+
+
+def _context_block_map(i: int):
+    """One block of the CAST time-context tower (`CONTEXT/timeseq_num_blocks_i`, models/cast_1.py:42-60).  The block
+    calls `normalize` three times: the first result (`self.timeseq_queries`, cast_1.py:45) is never used, so scope
+    `ln` is a dead beta/gamma pair; `ln_1` normalises the queries and `ln_2` the feed-forward input."""
+    sc, role = f"CONTEXT/timeseq_num_blocks_{i}", f"time.{i}"
+    m = {f"{sc}/ln/Variable": DEAD + "beta", f"{sc}/ln/Variable_1": DEAD + "gamma",
+         f"{sc}/ln_1/Variable": f"{role}.ln1.beta", f"{sc}/ln_1/Variable_1": f"{role}.ln1.gamma",
+         f"{sc}/ln_2/Variable": f"{role}.ln2.beta", f"{sc}/ln_2/Variable_1": f"{role}.ln2.gamma"}
+    for tf_d, r in (("dense", "q"), ("dense_1", "k"), ("dense_2", "v")):
+        m[f"{sc}/self_attention/{tf_d}/kernel"] = f"{role}.{r}.w"
+        m[f"{sc}/self_attention/{tf_d}/bias"] = f"{role}.{r}.b"
+    for tf_c, r in (("conv1d", "ffn1"), ("conv1d_1", "ffn2")):
+        m[f"{sc}/multihead_attention/{tf_c}/kernel"] = f"{role}.{r}.w"
+        m[f"{sc}/multihead_attention/{tf_c}/bias"] = f"{role}.{r}.b"
+    return m
+
+
+CKPT_MODELS = ("sasrec", "sasrec_static", "cast_1", "cast_2", "cast_3", "cast_4", "cast_5", "cast_6")
+
+
 def name_map(model: str, num_blocks: int) -> Dict[str, str]:
-    """TF variable name -> role name for the SASRec variants (models/sasrec.py scopes).  CAST checkpoints shipped with
-    the reference were written by earlier revisions of the model files, so only the SASRec family is
-    mapped by name."""
-    if model not in ("sasrec", "sasrec_static"):
-        raise ValueError("name mapping is defined for sasrec / sasrec_static")
+    """TF variable name -> role name (or DEAD...) for the models whose TensorFlow scopes are pinned by a checkpoint the
+    reference ships (saved_models/ml-1m.txt/{sasrec*, cast_1..6}_*): SASRec (models/sasrec.py) and the time-context
+    CAST variants (models/cast_1.py ... cast_6.py).  Variables are mapped BY ROLE: the context tower's extra `ln`
+    pair is dead weight in the graph, the MLP kernels follow the concat order of engine.model_plan."""
+    if model not in CKPT_MODELS:
+        raise ValueError(f"TensorFlow variable names are defined for {CKPT_MODELS}; {model} checkpoints are .npz")
     m = {"SASRec/input_embeddings/lookup_table": "item_emb", "SASRec/ln/Variable": "main.lnf.beta",
          "SASRec/ln/Variable_1": "main.lnf.gamma"}
     if model == "sasrec":
         m["SASRec/dec_pos/lookup_table"] = "pos_emb"
     for i in range(num_blocks):
         m.update(_block_map(f"SASRec/num_blocks_{i}", f"main.{i}"))
+    if model.startswith("cast_"):
+        n = int(model.split("_")[1])
+        m["CONTEXT/time_embeddings/lookup_table"] = "time_emb"
+        m["CONTEXT/ln/Variable"] = "time.lnf.beta"
+        m["CONTEXT/ln/Variable_1"] = "time.lnf.gamma"
+        for i in range(num_blocks):
+            m.update(_context_block_map(i))
+        if n >= 3:
+            m["INPUT-CONTEXT/hours_embeddings/lookup_table"] = "hours_emb"
+            m["INPUT-CONTEXT/days_embeddings/lookup_table"] = "days_emb"
+        if n >= 2:
+            m.update({"SASRec/MLP/dense/kernel": "mlp.0.w", "SASRec/MLP/dense/bias": "mlp.0.b",
+                      "SASRec/MLP/dense_1/kernel": "mlp.1.w", "SASRec/MLP/dense_1/bias": "mlp.1.b"})
     return m
+
+
+def _from_tf(a: np.ndarray) -> np.ndarray:
+    return a.reshape(a.shape[-2], a.shape[-1]) if a.ndim == 3 else a   # conv1d kernels [1,H,H] -> [H,H]
 
 
 def to_role_names(model: str, tf_vars: Dict[str, np.ndarray], num_blocks: int) -> Dict[str, np.ndarray]:
     out = {}
     for tf_name, role in name_map(model, num_blocks).items():
-        a = tf_vars[tf_name]
-        out[role] = a.reshape(a.shape[-2], a.shape[-1]) if a.ndim == 3 else a   # conv1d kernels [1,H,H] -> [H,H]
+        if not role.startswith(DEAD):
+            out[role] = _from_tf(tf_vars[tf_name])
     return out
 
 
 def to_tf_names(model: str, params: Dict[str, np.ndarray], num_blocks: int) -> Dict[str, np.ndarray]:
     out = {}
     for tf_name, role in name_map(model, num_blocks).items():
+        if role.startswith(DEAD):     # never trained: still at the initialiser (beta = 0, gamma = 1)
+            H = np.asarray(params["main.lnf.beta"]).shape[0]
+            out[tf_name] = (np.ones if role.endswith("gamma") else np.zeros)(H, np.float32)
+            continue
         a = np.asarray(params[role], dtype=np.float32)
         out[tf_name] = a[None] if "/conv1d" in tf_name and tf_name.endswith("kernel") else a
     return out
+
+
+# ------------------------------------------------------------------------------------------------ whole training state
+def save_model(prefix: str, model, model_name: str, num_blocks: int):
+    """Everything `tf.train.Saver()` writes for the reference (main.py:153-159,226-228): the variables, their Adam
+    slots `<var>/Adam` (m) and `<var>/Adam_1` (v) — for the variables that receive gradients —, `beta1_power`,
+    `beta2_power` and `global_step`, under the reference's names."""
+    eng = model.engine
+    P = {k: v.detach().cpu().numpy() for k, v in eng.P.items()}
+    out = to_tf_names(model_name, P, num_blocks)
+    m_flat, v_flat = eng.m.detach().cpu().numpy(), eng.v.detach().cpu().numpy()
+    for tf_name, role in name_map(model_name, num_blocks).items():
+        if role.startswith(DEAD):
+            continue
+        off, n = eng.offsets[role], int(np.prod(eng.P[role].shape))
+        shape = out[tf_name].shape
+        out[tf_name + "/Adam"] = m_flat[off:off + n].reshape(shape).copy()
+        out[tf_name + "/Adam_1"] = v_flat[off:off + n].reshape(shape).copy()
+    st = eng.adam_state.detach().cpu().numpy().view(np.uint8)
+    out["beta1_power"] = st[0:4].view(np.float32)[0].copy().reshape(())
+    out["beta2_power"] = st[4:8].view(np.float32)[0].copy().reshape(())
+    out["global_step"] = np.asarray(int(st[8:16].view(np.uint64)[0]), dtype=np.int32)   # tf.Variable(0) is int32
+    write_bundle(prefix, out)
+    return prefix
+
+
+def restore_model(prefix: str, model, model_name: str, num_blocks: int, optimizer: bool = True):
+    """Loads a bundle written by the reference or by `save_model`: weights by role; with `optimizer` also the Adam
+    slots, beta powers and the step counter when the bundle has them (resume = the same bits as never stopping)."""
+    import torch
+    eng = model.engine
+    tfv = read_bundle(prefix)
+    model.load_state_dict(to_role_names(model_name, tfv, num_blocks))
+    if not optimizer or "beta1_power" not in tfv:
+        return tfv
+    m_flat, v_flat = eng.m.detach().cpu().numpy().copy(), eng.v.detach().cpu().numpy().copy()
+    for tf_name, role in name_map(model_name, num_blocks).items():
+        if role.startswith(DEAD) or tf_name + "/Adam" not in tfv:
+            continue
+        off, n = eng.offsets[role], int(np.prod(eng.P[role].shape))
+        m_flat[off:off + n] = _from_tf(tfv[tf_name + "/Adam"]).reshape(-1)
+        v_flat[off:off + n] = _from_tf(tfv[tf_name + "/Adam_1"]).reshape(-1)
+    eng.m.copy_(torch.from_numpy(m_flat).to(eng.device))
+    eng.v.copy_(torch.from_numpy(v_flat).to(eng.device))
+    st = np.zeros(16, np.uint8)
+    st[0:4] = np.asarray(tfv["beta1_power"], np.float32).reshape(1).view(np.uint8)
+    st[4:8] = np.asarray(tfv["beta2_power"], np.float32).reshape(1).view(np.uint8)
+    st[8:16] = np.asarray([int(np.asarray(tfv["global_step"]).reshape(-1)[0])], np.uint64).view(np.uint8)
+    eng.adam_state.copy_(torch.from_numpy(st.view(np.int64).copy()).to(eng.device))
+    return tfv

@@ -821,13 +821,23 @@ class Engine:
                 c.presplit_pending = True
         c.reduce_jobs = []
         c.fuse_tail = self.tail_fusable()
-        self.forward(c, train=True)
-        if c.fuse_tail:
-            self.loss_tail_fused(c)
-        else:
-            self.loss_fwd_bwd(c, with_grad=True, defer_sums=True)
-        self.backward(c)
-        c.fuse_tail = False
+        try:
+            self.forward(c, train=True)
+            if c.fuse_tail:
+                self.loss_tail_fused(c)
+            else:
+                self.loss_fwd_bwd(c, with_grad=True, defer_sums=True)
+            self.backward(c)
+        finally:   # a failed launch must not leave per-step flags (or un-joined side streams) behind: contexts are reused
+            c.fuse_tail = False
+            if getattr(c, "presorted", False) or getattr(c, "presplit_pending", False):
+                main = torch.cuda.current_stream(self.device)
+                if getattr(c, "presorted", False):
+                    main.wait_stream(c.side)
+                if getattr(c, "presplit_pending", False):
+                    main.wait_stream(c.side2)
+                c.presorted = c.presplit_pending = False
+            c.reduce_jobs = []
 
     def launch_train_step(self, c):
         """Enqueue one full training step (forward, loss, backward, [all-reduce], Adam) on the current stream."""

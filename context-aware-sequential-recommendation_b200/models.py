@@ -33,27 +33,33 @@ class _Model:
 
     # ------------------------------------------------------------------ helpers
     def _stage(self, c, seq, pos, neg, time_seq, hours, days):
-        """host -> device copies of one batch into the static input buffers (pinned staging, non-blocking)."""
+        """host -> device copies of one batch into the static input buffers: pinned staging, non-blocking copies.
+        Three staging sets rotate and each remembers the event recorded after its copies, so `train_step_async` can be
+        called back to back without a batch being overwritten before its copy has run."""
         eng = self.engine
         B, T = c.B, eng.T
         key = (B, "in")
-        st = self._pinned.get(key)
-        if st is None:
+        ring = self._pinned.get(key)
+        if ring is None:
             pin = eng.device.type == "cuda"
-            st = (torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin),
-                  torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin))
-            self._pinned[key] = st
-        k3, c3 = st[0], st[1]
-        if len(st) == 2:  # numpy views of the pinned staging buffers: np.copyto has far less overhead than Tensor.copy_
-            st = (k3, c3, k3.numpy(), c3.numpy())
-            self._pinned[key] = st
-        k3n, c3n = st[2], st[3]
+            ring = {"slots": [], "next": 0}
+            for _ in range(3 if pin else 1):
+                k3 = torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin)
+                c3 = torch.zeros(3, B * T, dtype=torch.int32, pin_memory=pin)
+                # numpy views of the pinned buffers: np.copyto has far less overhead than Tensor.copy_
+                ring["slots"].append({"k3": k3, "c3": c3, "k3n": k3.numpy(), "c3n": c3.numpy(), "event": None})
+            self._pinned[key] = ring
+        st = ring["slots"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % len(ring["slots"])
+        if st["event"] is not None:
+            st["event"].synchronize()       # the copy that last used this slot has completed
+        k3n, c3n = st["k3n"], st["c3n"]
         for j, a in enumerate((seq, pos, neg)):
             if a is not None:
                 np.copyto(k3n[j], np.asarray(a).reshape(-1), casting="unsafe")
             else:
                 k3n[j].fill(0)
-        c.keys3.copy_(k3, non_blocking=True)
+        c.keys3.copy_(st["k3"], non_blocking=True)
         tables = eng.plan.tables
         need = [("time_emb", time_seq), ("hours_emb", hours), ("days_emb", days)]
         if any(t in tables for t, _ in need):
@@ -62,7 +68,10 @@ class _Model:
                     if a is None:
                         raise ValueError(f"model {self.registry_name} needs the {t[:-4]} sequence")
                     np.copyto(c3n[j], np.asarray(a).reshape(-1), casting="unsafe")
-            c.cids.copy_(c3, non_blocking=True)
+            c.cids.copy_(st["c3"], non_blocking=True)
+        if eng.device.type == "cuda":
+            st["event"] = torch.cuda.Event()
+            st["event"].record(torch.cuda.current_stream(eng.device))
 
     def _capture(self, c):
         """Capture the step as CUDA graphs: [forward+loss+backward] and [Adam]; under data parallelism the NCCL

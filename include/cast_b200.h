@@ -39,6 +39,9 @@ int cast_version(void);
 const char* cast_last_error_string(void);
 /* number of kernels this library has enqueued so far in this process (each launch site counts once). */
 unsigned long long cast_launch_count(void);
+/* crc32c (Castagnoli) of a HOST buffer, continuing from crc_in (0 to start): the tensor checksum of the reference's
+ * checkpoint format (tf.train.Saver tensor bundles, main.py:153-159,226-228). */
+unsigned int cast_crc32c(const void* data, size_t n, unsigned int crc_in);
 
 /* modules.py:148-160 `embedding` (zero-padded row 0, x sqrt(H)) + position row add (sasrec.py:39-56) + context
  * add (cast_1.py:87) + tf.layers.dropout (sasrec.py:59) + `*= mask` (sasrec.py:62).

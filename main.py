@@ -68,22 +68,34 @@ def build_parser():
 
 
 def save_checkpoint(model, args, path):
+    """reference main.py:226-228 `saver.save(sess, save_path)`: a TensorFlow tensor bundle with the reference's
+    variable names, Adam slots, beta powers and global_step (models whose TF scopes are pinned by a shipped checkpoint:
+    checkpoint.CKPT_MODELS); the role-named .npz next to it covers every model."""
     from cast_b200 import checkpoint as ck
-    sd = {k: v.numpy() for k, v in model.state_dict().items()}
-    if args.model in ("sasrec", "sasrec_static"):
-        ck.write_bundle(path, ck.to_tf_names(args.model, sd, args.num_blocks))   # reference variable names
-    np.savez(path + ".npz", **sd)
+    if args.model.lower() in ck.CKPT_MODELS:
+        ck.save_model(path, model, args.model.lower(), args.num_blocks)
+    eng = model.engine
+    np.savez(path + ".npz", **{k: v.numpy() for k, v in model.state_dict().items()},
+             **{"__adam_m": eng.m.cpu().numpy(), "__adam_v": eng.v.cpu().numpy(),
+                "__adam_state": eng.adam_state.cpu().numpy()})
     return path
 
 
 def load_checkpoint(model, args, directory):
+    """reference main.py:153-159 `saver.restore`: reads a bundle written by the reference itself or by this driver"""
+    import torch
     from cast_b200 import checkpoint as ck
     prefix = os.path.join(directory, "model.ckpt")
-    if os.path.isfile(prefix + ".npz"):
-        g = np.load(prefix + ".npz")
-        model.load_state_dict({k: g[k] for k in g.files})
-    else:
-        model.load_state_dict(ck.to_role_names(args.model, ck.read_bundle(prefix), args.num_blocks))
+    if os.path.isfile(prefix + ".index") and args.model.lower() in ck.CKPT_MODELS:
+        ck.restore_model(prefix, model, args.model.lower(), args.num_blocks)
+        return
+    g = np.load(prefix + ".npz")
+    model.load_state_dict({k: g[k] for k in g.files if not k.startswith("__")})
+    if "__adam_m" in g.files:
+        eng = model.engine
+        eng.m.copy_(torch.from_numpy(g["__adam_m"]).to(eng.device))
+        eng.v.copy_(torch.from_numpy(g["__adam_v"]).to(eng.device))
+        eng.adam_state.copy_(torch.from_numpy(g["__adam_state"]).to(eng.device))
 
 
 def run(args, device=None, lib=None, logger=None):
@@ -107,28 +119,32 @@ def run(args, device=None, lib=None, logger=None):
     print("usernum", usernum, "itemnum", itemnum)
     cc = sum(len(v) for v in train.values())
     logger.info("Average sequence length: {:.2f}".format(cc / len(train)))
-    if args.seed:
-        random.seed(args.seed)
-        np.random.seed(args.seed)
+    seed = int(args.seed or 0)
+    if world > 1:   # one seed for the whole job (--seed 0 = "unseeded": drawn once, on rank 0)
+        import torch
+        import torch.distributed as tdist
+        box = [seed if seed else int(np.random.SeedSequence().generate_state(1)[0] % (2 ** 31 - 1)) + 1]
+        tdist.broadcast_object_list(box, src=0)
+        seed = box[0]
+    if seed:        # evaluation draws its user sample and negatives from these (util.py:241-244,295): same on every rank
+        random.seed(seed)
+        np.random.seed(seed)
     kw = {} if device is None else {"device": device, "_lib": lib, "use_graph": False}
     model = cast_b200.build_model(args.model, usernum, itemnum, ratingnum, args, **kw)
     if device is None:
         cdist.attach(model.engine)
-    if world > 1:   # every rank draws a different part of the stream: rank r takes batches r, r+world, ...
-        args.batch_size_global = args.batch_size * world
-    sampler = WarpSampler(args, train, usernum, itemnum, batch_size=args.batch_size, maxlen=args.maxlen, n_workers=1)
+    # every rank draws its own batches from its own stream (seed, rank): nothing is generated to be thrown away
+    sargs = args
+    if world > 1:
+        from types import SimpleNamespace
+        sargs = SimpleNamespace(**{**vars(args), "seed": seed + 7919 * rank})
+    sampler = WarpSampler(sargs, train, usernum, itemnum, batch_size=args.batch_size, maxlen=args.maxlen, n_workers=1)
     now = datetime.now()
     files_path = os.path.join(args.model_path, os.path.basename(args.dataset),
                               "{}_{}".format(args.train_dir, now.strftime("%m-%d-%Y-%H-%M-%S")))
     save_path = os.path.join(files_path, "model.ckpt")
 
-    def next_batch():
-        b = None
-        for _ in range(rank + 1):
-            b = sampler.next_batch()
-        for _ in range(world - rank - 1):
-            sampler.next_batch()
-        return b
+    next_batch = sampler.next_batch
 
     if args.test_model:
         try:
@@ -178,12 +194,18 @@ def run(args, device=None, lib=None, logger=None):
                 logger.info("epoch:%d, time: %f(s), valid (NDCG@10: %.4f, HR@10: %.4f), test (NDCG@10: %.4f, "
                             "HR@10: %.4f)" % (epoch, T, t_valid[0], t_valid[1], t_test[0], t_test[1]))
                 if log:
-                    log.write(str(tuple(t_valid)) + " " + str(tuple(t_test)) + "\n")
+                    # the reference's line format (main.py:238): plain Python floats, not numpy reprs
+                    log.write(str(tuple(float(x) for x in t_valid)) + " " + str(tuple(float(x) for x in t_test)) + "\n")
                     log.flush()
                 t0 = time.time()
     except Exception as e:  # as the reference: close the sampler and the log, report, exit code 1
         logger.error(e)
         rc = 1
+        if world > 1:       # the other ranks are blocked in this step's exchange: fail the whole job fast
+            sampler.close()
+            if log:
+                log.close()
+            os._exit(1)
     finally:
         sampler.close()
         if log:
