@@ -57,6 +57,7 @@ SIGNATURES = {
     "cast_logits_loss_parts": (I, [L]),
     "cast_sampler_create": (P, [I, I, P, P, P, P, P, P, I, C.c_uint, P, I]),
     "cast_sampler_next": (I, [P, I, P, P, P, P, P, P, P, P]),
+    "cast_sampler_next_raw": (I, [P, I, P, P, P, P, P]),
     "cast_sampler_destroy": (None, [P]),
     "cast_time_features": (I, [P, P, P, I, I, P, I, P, P, P, P]),
     "cast_lnf_loss_parts": (I, [L]),

@@ -95,8 +95,8 @@ extern "C" void* cast_sampler_create(int usernum, int itemnum, const long* user_
 extern "C" void cast_sampler_destroy(void* h) { delete static_cast<Sampler*>(h); }
 
 // One batch of B samples, every output [B, T] int32 (left-padded with zeros), `user` [B].  Optional outputs may be null.
-extern "C" int cast_sampler_next(void* h, int B, int* user, int* seq, int* pos, int* neg, int* timeseq, int* ratings,
-                                 int* hours, int* days) {
+static int sampler_next(void* h, int B, int* user, int* seq, int* pos, int* neg, int* timeseq, int* ratings,
+                        int* hours, int* days, long long* ts_raw) {
   Sampler* s = static_cast<Sampler*>(h);
   if (!s || B <= 0 || !user || !seq || !pos || !neg) return CAST_ERR_BAD_ARG;
   const int T = s->T;
@@ -140,6 +140,11 @@ extern "C" int cast_sampler_next(void* h, int B, int* user, int* seq, int* pos, 
       memset(o, 0, sizeof(int) * T);
       if (!s->days.empty()) for (int j = 0; j < k; ++j) o[T - k + j] = s->days[lo + j];
     }
+    if (ts_raw) {   // raw timestamps of the window: the device computes bins / hours / weekdays (cast_time_features)
+      long long* o = ts_raw + (long)b * T;
+      memset(o, 0, sizeof(long long) * T);
+      if (!s->ts.empty()) for (int j = 0; j < k; ++j) o[T - k + j] = s->ts[lo + j];
+    }
     if (timeseq) {
       int* o = timeseq + (long)b * T;
       memset(o, 0, sizeof(int) * T);
@@ -159,4 +164,15 @@ extern "C" int cast_sampler_next(void* h, int B, int* user, int* seq, int* pos, 
     }
   }
   return CAST_OK;
+}
+
+extern "C" int cast_sampler_next(void* h, int B, int* user, int* seq, int* pos, int* neg, int* timeseq, int* ratings,
+                                 int* hours, int* days) {
+  return sampler_next(h, B, user, seq, pos, neg, timeseq, ratings, hours, days, nullptr);
+}
+
+/* the same stream, handing out the RAW int64 timestamps [B, T] of the window instead of host-computed time features */
+extern "C" int cast_sampler_next_raw(void* h, int B, int* user, int* seq, int* pos, int* neg, long long* ts) {
+  if (!ts) return CAST_ERR_BAD_ARG;
+  return sampler_next(h, B, user, seq, pos, neg, nullptr, nullptr, nullptr, nullptr, ts);
 }

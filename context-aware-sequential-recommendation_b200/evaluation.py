@@ -60,7 +60,7 @@ def build_candidates(dataset, args, split: str = "test", rng=None):
     lo, hi = get_delta_range(train)
     target_of = test if split == "test" else valid
     member = np.zeros(itemnum + 2, dtype=bool)
-    us, seqs, cands, tss, hrs, dys, rated = [], [], [], [], [], [], []
+    us, seqs, cands, tss, hrs, dys, rated, raws = [], [], [], [], [], [], [], []
     trunc = None
     if getattr(args, "test_model", None):
         if not getattr(args, "test_seq_len", None):
@@ -88,11 +88,14 @@ def build_candidates(dataset, args, split: str = "test", rng=None):
         member[0] = True
         neg = _draw_negatives(rng, itemnum, member)
         member[items] = False
+        tsraw = np.zeros(T, np.int64)
+        tsraw[T - k:] = t
         if trunc is not None:  # util.py:300-315 (--test_model / --test_seq_len)
             seq[:-trunc] = 0
             timeseq[:-trunc] = 0
             hours[:-trunc] = 0
             days[:-trunc] = 0
+            tsraw[:-trunc] = 0
         us.append(u)
         rated.append(np.unique(items).astype(np.int32))
         seqs.append(seq)
@@ -100,9 +103,11 @@ def build_candidates(dataset, args, split: str = "test", rng=None):
         tss.append(timeseq)
         hrs.append(hours)
         dys.append(days)
+        raws.append(tsraw)
     st = lambda a, w: np.stack(a) if a else np.zeros((0, w), np.int32)  # noqa: E731
     return {"u": np.asarray(us, np.int32), "seq": st(seqs, T), "item_idx": st(cands, 101), "timeseq": st(tss, T),
-            "hours": st(hrs, T), "days": st(dys, T), "rated": rated}
+            "hours": st(hrs, T), "days": st(dys, T), "rated": rated,
+            "tsraw": np.stack(raws) if raws else np.zeros((0, T), np.int64)}   # for the device-side feature path
 
 
 def reference_rank(logits_row: np.ndarray) -> int:
@@ -164,8 +169,13 @@ def score_users(model, cand, batch_users: int = 256, lo: int = 0, hi: Optional[i
                                               pad(cand["hours"]), pad(cand["days"]))
             ranks[s - lo:e - lo] = cgt[:n]
             continue
-        logits, cgt, ceq = model.score_candidates(pad(cand["seq"]), pad(cand["item_idx"]), pad(cand["timeseq"]),
-                                                  pad(cand["hours"]), pad(cand["days"]))
+        if getattr(model, "timefeat", None) is not None and "tsraw" in cand:
+            # time bins / hours / weekdays derived on the device from the raw event times (util.py:276-289)
+            logits, cgt, ceq = model.score_candidates(pad(cand["seq"]), pad(cand["item_idx"]),
+                                                      timestamps=pad(cand["tsraw"]))
+        else:
+            logits, cgt, ceq = model.score_candidates(pad(cand["seq"]), pad(cand["item_idx"]), pad(cand["timeseq"]),
+                                                      pad(cand["hours"]), pad(cand["days"]))
         ranks[s - lo:e - lo] = ranks_from_device(logits[:n], cgt[:n], ceq[:n])
     return ranks
 

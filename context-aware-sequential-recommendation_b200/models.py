@@ -32,6 +32,39 @@ class _Model:
         self._sums_host = None
 
     # ------------------------------------------------------------------ helpers
+    def use_device_time_features(self, bin_in_hours=48, max_bins=200, log_scale=False, min_timedelta=None,
+                                 max_timedelta=None):
+        """Derive the time-bin / hour / weekday ids on the device from raw int64 timestamps (`timestamps=` of
+        train_step / predict / score_candidates) with the dataset's bin rule — reference util.py:24-43,73-120 applied
+        per position by sampler.py:61-72 and util.py:276-289."""
+        from .timefeat import TimeFeaturizer
+        eng = self.engine
+        self.timefeat = TimeFeaturizer(eng.device, bin_in_hours, max_bins, log_scale, min_timedelta, max_timedelta,
+                                       lib=eng.lib)
+        return self
+
+    def _stage_timestamps(self, c, timestamps):
+        """raw timestamps -> c.cids on the device (after the item ids of the batch are staged)"""
+        eng = self.engine
+        if getattr(self, "timefeat", None) is None:
+            raise ValueError("timestamps= needs use_device_time_features(...) first (the dataset's bin rule)")
+        B, T = c.B, eng.T
+        key = (B, "ts")
+        st = self._pinned.get(key)
+        if st is None:
+            pin = eng.device.type == "cuda"
+            host = torch.zeros(B, T, dtype=torch.int64, pin_memory=pin)
+            st = self._pinned[key] = {"host": host, "hostn": host.numpy(),
+                                      "dev": torch.zeros(B, T, dtype=torch.int64, device=eng.device), "event": None}
+        if st["event"] is not None:
+            st["event"].synchronize()
+        np.copyto(st["hostn"], np.asarray(timestamps).reshape(B, T), casting="unsafe")
+        st["dev"].copy_(st["host"], non_blocking=True)
+        if eng.device.type == "cuda":
+            st["event"] = torch.cuda.Event()
+            st["event"].record(torch.cuda.current_stream(eng.device))
+        self.timefeat.into(st["dev"], c.keys3[0], c.cids)
+
     def _stage(self, c, seq, pos, neg, time_seq, hours, days):
         """host -> device copies of one batch into the static input buffers: pinned staging, non-blocking copies.
         Three staging sets rotate and each remembers the event recorded after its copies, so `train_step_async` can be
@@ -63,6 +96,8 @@ class _Model:
         tables = eng.plan.tables
         need = [("time_emb", time_seq), ("hours_emb", hours), ("days_emb", days)]
         if any(t in tables for t, _ in need):
+            if all(a is None for _, a in need) and getattr(self, "_ts_pending", None) is not None:
+                return      # raw timestamps follow: the device fills c.cids (_stage_timestamps)
             for j, (t, a) in enumerate(need):
                 if t in tables:
                     if a is None:
@@ -138,19 +173,29 @@ class _Model:
                       eng._stream())
 
     # ------------------------------------------------------------------ reference protocol
-    def train_step_async(self, u, seq, pos, neg, time_seq=None, hours=None, days=None):
-        """Enqueue one training step; returns the device tensor {sum loss terms, sum auc terms, sum istarget}."""
+    def _stage_all(self, c, seq, pos, neg, time_seq, hours, days, timestamps):
+        self._ts_pending = timestamps if len(self.engine.plan.tables) > 1 else None
+        try:
+            self._stage(c, seq, pos, neg, time_seq, hours, days)
+            if self._ts_pending is not None:
+                self._stage_timestamps(c, timestamps)
+        finally:
+            self._ts_pending = None
+
+    def train_step_async(self, u, seq, pos, neg, time_seq=None, hours=None, days=None, timestamps=None):
+        """Enqueue one training step; returns the device tensor {sum loss terms, sum auc terms, sum istarget}.
+        timestamps (raw int64 [B,T], 0 = padding) replaces time_seq / hours / days: see use_device_time_features."""
         eng = self.engine
         seq = np.asarray(seq)
         B = seq.shape[0]
         c = eng.ctx(B)
-        self._stage(c, seq, pos, neg, time_seq, hours, days)
+        self._stage_all(c, seq, pos, neg, time_seq, hours, days, timestamps)
         self.launch(c)
         return eng.global_sums()
 
-    def train_step(self, u, seq, pos, neg, time_seq=None, hours=None, days=None):
+    def train_step(self, u, seq, pos, neg, time_seq=None, hours=None, days=None, timestamps=None):
         """== sess.run([model.auc, model.loss, model.train_op], feed) of reference main.py:212-219."""
-        s = self.train_step_async(u, seq, pos, neg, time_seq, hours, days)
+        s = self.train_step_async(u, seq, pos, neg, time_seq, hours, days, timestamps)
         if s.device.type == "cuda":  # 12-byte read-back into pinned memory, one stream synchronisation
             if self._sums_host is None:
                 self._sums_host = torch.zeros(4, dtype=torch.float32, pin_memory=True)
@@ -161,20 +206,21 @@ class _Model:
             loss_sum, auc_sum, cnt = s[:3].tolist()
         return auc_sum / cnt, loss_sum / cnt
 
-    def forward_eval(self, seq, time_seq=None, hours=None, days=None, want_attn=False):
+    def forward_eval(self, seq, time_seq=None, hours=None, days=None, want_attn=False, timestamps=None):
         """is_training=False forward; returns the device buffer seq_emb [B*T, H] (and fills attention weights)."""
         eng = self.engine
         seq = np.asarray(seq)
         B = seq.shape[0]
         c = eng.ctx(B)
-        self._stage(c, seq, None, None, time_seq, hours, days)
+        self._stage_all(c, seq, None, None, time_seq, hours, days, timestamps)
         eng.forward(c, train=False, want_attn=want_attn)
         return c
 
-    def predict(self, sess, u, seq, item_idx, timeseq=None, input_context_seq=None, hours_seq=None, days_seq=None):
+    def predict(self, sess, u, seq, item_idx, timeseq=None, input_context_seq=None, hours_seq=None, days_seq=None,
+                timestamps=None):
         """reference models/sasrec.py:127-129 / cast_3.py:191-194: returns [test_logits [B,101], attention_weights]."""
         eng = self.engine
-        c = self.forward_eval(seq, timeseq, hours_seq, days_seq, want_attn=True)
+        c = self.forward_eval(seq, timeseq, hours_seq, days_seq, want_attn=True, timestamps=timestamps)
         B, T, H = c.B, eng.T, eng.H
         item_idx = np.asarray(item_idx, dtype=np.int32).reshape(-1)
         Cn = item_idx.shape[0]
@@ -185,11 +231,11 @@ class _Model:
         self.attention_weights = c.attn
         return [logits.cpu().numpy(), c.attn.cpu().numpy()]
 
-    def score_candidates(self, seq, cand, time_seq=None, hours=None, days=None):
+    def score_candidates(self, seq, cand, time_seq=None, hours=None, days=None, timestamps=None):
         """Batched evaluation scoring: per-user candidate lists cand [U, C] (candidate 0 = target).
         Returns (logits [U,C], count_greater [U], count_equal [U]) as numpy arrays (util.py:317-321 fused)."""
         eng = self.engine
-        c = self.forward_eval(seq, time_seq, hours, days)
+        c = self.forward_eval(seq, time_seq, hours, days, timestamps=timestamps)
         B, T, H = c.B, eng.T, eng.H
         cand_t = torch.from_numpy(np.ascontiguousarray(np.asarray(cand, dtype=np.int32))).to(eng.device)
         Cn = cand_t.shape[1]

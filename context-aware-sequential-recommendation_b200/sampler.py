@@ -40,7 +40,8 @@ class SampleStream:
 
     def __init__(self, user_train: Dict[int, Sequence], usernum: int, itemnum: int, batch_size: int, maxlen: int,
                  bin_in_hours: int, max_bins: int, log_scale: bool, min_timedelta, max_timedelta, seed: int,
-                 with_objects: bool = False):
+                 with_objects: bool = False, raw_timestamps: bool = False):
+        self.raw_timestamps = bool(raw_timestamps)
         self.train, self.usernum, self.itemnum = user_train, usernum, itemnum
         self.B, self.T = batch_size, maxlen
         self.log_scale = bool(log_scale)
@@ -102,6 +103,10 @@ class SampleStream:
         # negatives are drawn newest position first (sampler.py:44-58); item ids are >= 1 so `nxt != 0` always holds
         neg[T - k:] = self._negatives(k, ua)[::-1]
         t = ua.t[lo:n - 1]
+        if self.raw_timestamps:     # the device bins them (cast_time_features): hand out the raw seconds instead
+            tsraw = np.zeros(T, np.int64)
+            tsraw[T - k:] = t
+            return user, seq, pos, neg, timeseq * 0, ratings, hours * 0, days * 0, tsraw
         timeseq[T - k:] = timedelta_bins((t[-1] - t).astype(np.float64), self.bin_in_hours, self.max_bins,
                                          self.log_scale, self.lo, self.hi)
         orig = None
@@ -113,7 +118,8 @@ class SampleStream:
         """Same 9-tuple layout as `zip(*one_batch)` in the reference (sampler.py:78-81), as stacked arrays."""
         rows = [self.sample() for _ in range(self.B)]
         cols = list(zip(*rows))
-        out = [np.asarray(cols[0], dtype=np.int32)] + [np.stack(c) for c in cols[1:8]] + [list(cols[8])]
+        last = np.stack(cols[8]) if self.raw_timestamps else list(cols[8])
+        out = [np.asarray(cols[0], dtype=np.int32)] + [np.stack(c) for c in cols[1:8]] + [last]
         return tuple(out)
 
 
@@ -124,8 +130,10 @@ class FastSampleStream:
     to batches captured from the reference's `sample_function`)."""
 
     def __init__(self, user_train: Dict[int, Sequence], usernum: int, itemnum: int, batch_size: int, maxlen: int,
-                 bin_in_hours: int, max_bins: int, log_scale: bool, min_timedelta, max_timedelta, seed: int, lib=None):
+                 bin_in_hours: int, max_bins: int, log_scale: bool, min_timedelta, max_timedelta, seed: int, lib=None,
+                 raw_timestamps: bool = False):
         import ctypes as C
+        self.raw_timestamps = bool(raw_timestamps)
         from . import _lib
         from .data import time_bin_edges
         self.lib = lib if lib is not None else _lib.load_library()
@@ -165,8 +173,16 @@ class FastSampleStream:
     def next_batch(self):
         B, T, C = self.B, self.T, self._C
         user = np.empty(B, np.int32)
-        out = [np.empty((B, T), np.int32) for _ in range(7)]  # seq pos neg timeseq ratings hours days
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        if self.raw_timestamps:   # ninth slot = raw int64 timestamps [B,T]; the time features are left to the device
+            seq, pos, neg = (np.empty((B, T), np.int32) for _ in range(3))
+            ts = np.empty((B, T), np.int64)
+            rc = self.lib.cast_sampler_next_raw(self.h, B, p(user), p(seq), p(pos), p(neg), p(ts))
+            if rc != 0:
+                raise RuntimeError(f"cast_sampler_next_raw failed ({rc})")
+            z = np.zeros((B, T), np.int32)
+            return user, seq, pos, neg, z, z, z, z, ts
+        out = [np.empty((B, T), np.int32) for _ in range(7)]  # seq pos neg timeseq ratings hours days
         rc = self.lib.cast_sampler_next(self.h, B, p(user), *[p(a) for a in out])
         if rc != 0:
             raise RuntimeError(f"cast_sampler_next failed ({rc})")
@@ -191,7 +207,10 @@ class WarpSampler:
     spawned process and a pickling queue); the stream is the single-worker stream of the reference."""
 
     def __init__(self, args, User, usernum, itemnum, sample_func=None, batch_size=64, maxlen=10, n_workers=1,
-                 prefetch: int = 8, with_objects: bool = False):
+                 prefetch: int = 8, with_objects: bool = False, raw_timestamps: bool = False):
+        """raw_timestamps: the ninth element of a batch is the int64 [B,T] array of raw event times and the time-bin /
+        hour / weekday slots are left zero — pass it as `timestamps=` to `train_step`, which derives the three context
+        id arrays on the device (`cast_time_features`) instead of per-event host arithmetic (sampler.py:61-72)."""
         if n_workers != 1:
             raise ValueError("the reference stream is defined for n_workers=1 (main.py:148)")
         lo, hi = get_delta_range(User)
@@ -203,14 +222,16 @@ class WarpSampler:
             from ._lib import CastError
             try:
                 self.stream = FastSampleStream(User, usernum, itemnum, batch_size, maxlen, args.bin_in_hours,
-                                               args.max_bins, args.log_scale, lo, hi, seed)
+                                               args.max_bins, args.log_scale, lo, hi, seed,
+                                               raw_timestamps=raw_timestamps)
             except CastError as e:
                 import warnings
                 warnings.warn(f"native sampler unavailable ({e}); using the 45x slower Python stream")
                 self.stream = None
         if self.stream is None:
             self.stream = SampleStream(User, usernum, itemnum, batch_size, maxlen, args.bin_in_hours, args.max_bins,
-                                       args.log_scale, lo, hi, seed, with_objects=with_objects)
+                                       args.log_scale, lo, hi, seed, with_objects=with_objects,
+                                       raw_timestamps=raw_timestamps)
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, prefetch))
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)

@@ -19,6 +19,17 @@ class TimeFeaturizer:
         edges = time_bin_edges(bin_in_hours, max_bins, log_scale, min_ts, max_ts)
         self.edges = torch.from_numpy(np.ascontiguousarray(edges)).to(self.device)
 
+    def into(self, ts_dev, ids_dev, out3, stream=None):
+        """device tensors in, device tensors out, nothing allocated: ts_dev [B,T] int64, ids_dev [B*T] int32, out3
+        [3, B*T] int32 (bins | hours | weekdays — the engine's context-id buffer)"""
+        B, T = ts_dev.shape
+        if stream is None and self.device.type == "cuda":
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.cast_time_features(ts_dev.data_ptr(), None, ids_dev.data_ptr(), B, T, self.edges.data_ptr(),
+                                         int(self.edges.numel()), out3[0].data_ptr(), out3[1].data_ptr(),
+                                         out3[2].data_ptr(), stream)
+        _lib.check(self.lib, rc, "cast_time_features")
+
     def __call__(self, ts, ids, ref=None, stream=None):
         """ts [B,T] int64 seconds, ids [B,T] int32 (0 = padding), ref [B] int64 or None (= ts[:, -1]).
         Returns int32 device tensors (bins, hours, days), each [B,T]."""

@@ -259,6 +259,9 @@ void* cast_sampler_create(int usernum, int itemnum, const long* user_ptr, const 
                           const long long* edges, int n_edges);
 int cast_sampler_next(void* sampler, int B, int* user, int* seq, int* pos, int* neg, int* timeseq, int* ratings,
                       int* hours, int* days);
+/* same stream; instead of the host-computed features the RAW int64 timestamps [B,T] of each window (0 = padding), for
+ * cast_time_features on the device */
+int cast_sampler_next_raw(void* sampler, int B, int* user, int* seq, int* pos, int* neg, long long* ts);
 void cast_sampler_destroy(void* sampler);
 
 /* Time-context ids from raw timestamps on the device (reference util.py:24-43 hour / weekday, util.py:73-120

@@ -64,6 +64,8 @@ def build_parser():
     p.add_argument("--eval_every", default=20, type=int, help="epochs between checkpoint + evaluation (reference: 20)")
     p.add_argument("--eval_batch", default=256, type=int, help="users scored per device batch")
     p.add_argument("--model_path", default=os.path.abspath("saved_models"))
+    p.add_argument("--device_time_features", action="store_true", help="CAST models: the sampler and the evaluation "
+                   "hand raw timestamps to the device, which derives time bins / hours / weekdays there")
     return p
 
 
@@ -138,7 +140,19 @@ def run(args, device=None, lib=None, logger=None):
     if world > 1:
         from types import SimpleNamespace
         sargs = SimpleNamespace(**{**vars(args), "seed": seed + 7919 * rank})
-    sampler = WarpSampler(sargs, train, usernum, itemnum, batch_size=args.batch_size, maxlen=args.maxlen, n_workers=1)
+    raw_ts = bool(getattr(args, "device_time_features", False)) and len(model.engine.plan.tables) > 1
+    if raw_ts:
+        from cast_b200.data import get_delta_range
+        lo_td, hi_td = get_delta_range(train)
+        model.use_device_time_features(args.bin_in_hours, args.max_bins, args.log_scale, lo_td, hi_td)
+    sampler = WarpSampler(sargs, train, usernum, itemnum, batch_size=args.batch_size, maxlen=args.maxlen, n_workers=1,
+                          raw_timestamps=raw_ts)
+
+    def train_on(batch):
+        u, seq, pos, neg, timeseq, _, hours_seq, days_seq, last = batch
+        if raw_ts:      # ninth slot = raw int64 event times
+            return model.train_step(u, seq, pos, neg, timestamps=last)
+        return model.train_step(u, seq, pos, neg, timeseq, hours_seq, days_seq)
     now = datetime.now()
     files_path = os.path.join(args.model_path, os.path.basename(args.dataset),
                               "{}_{}".format(args.train_dir, now.strftime("%m-%d-%Y-%H-%M-%S")))
@@ -151,8 +165,7 @@ def run(args, device=None, lib=None, logger=None):
             if os.path.exists(args.test_model):
                 print("loaded saved model {}".format(args.test_model))
                 load_checkpoint(model, args, args.test_model)
-                u, seq, pos, neg, timeseq, _, hours_seq, days_seq, _ = next_batch()
-                auc, loss = model.train_step(u, seq, pos, neg, timeseq, hours_seq, days_seq)  # as main.py:167-175
+                auc, loss = train_on(next_batch())  # as main.py:167-175
                 print(auc)
                 print(loss)
                 t_test = evaluate(model, dataset, args, None, batch_users=args.eval_batch, mode=args.eval_mode)
@@ -179,8 +192,7 @@ def run(args, device=None, lib=None, logger=None):
         for epoch in range(1, args.num_epochs + 1):
             auc = loss = None
             for _ in range(num_batch):
-                u, seq, pos, neg, timeseq, _, hours_seq, days_seq, _ = next_batch()
-                auc, loss = model.train_step(u, seq, pos, neg, timeseq, hours_seq, days_seq)
+                auc, loss = train_on(next_batch())
             if auc is not None:
                 logger.info("epoch:%d TRAIN/loss %.6f TRAIN/auc %.6f" % (epoch, loss, auc))
             if epoch % args.eval_every == 0:

@@ -70,3 +70,62 @@ def test_time_features_emulated(log_scale):
 @pytest.mark.parametrize("log_scale", [False, True])
 def test_time_features_gpu(log_scale):
     run("gpu", log_scale, B=128, T=200)
+
+
+def _raw_vs_host(kind, log_scale=False):
+    """The raw-timestamp input path (sampler -> `train_step(timestamps=)` -> cast_time_features on the device ->
+    context ids; evaluation likewise) against the host-feature path on the same stream: identical context ids, hence a
+    bit-identical training step and identical ranks (reference sampler.py:61-72, util.py:276-289)."""
+    import os
+    import random
+    import cast_b200
+    from cast_b200 import evaluation as cev
+    from cast_b200.sampler import WarpSampler
+    from helpers import make_args
+    lib, dev = backend(kind)
+    here = os.path.dirname(os.path.abspath(__file__))
+    dataset = cdata.data_partition(os.path.join(here, "golden", "ref_dataset.txt"), log_scale)
+    train, valid, test, usernum, itemnum, ratingnum = dataset
+    args = make_args(hidden_units=12, maxlen=10, num_heads=1, num_blocks=1, dropout_rate=0.2, log_scale=log_scale)
+    args.test_model = args.test_seq_len = None
+    lo, hi = cdata.get_delta_range(train)
+    models, samplers = [], []
+    for raw in (False, True):
+        m = cast_b200.build_model("cast_4", usernum, itemnum, ratingnum, args, device=dev, _lib=lib, use_graph=False,
+                                  seed=5)
+        if raw:
+            m.use_device_time_features(args.bin_in_hours, args.max_bins, log_scale, lo, hi)
+        models.append(m)
+        samplers.append(WarpSampler(args, train, usernum, itemnum, batch_size=8, maxlen=10, raw_timestamps=raw))
+    try:
+        for _ in range(2):
+            bh, br = samplers[0].next_batch(), samplers[1].next_batch()
+            for j in range(4):
+                assert np.array_equal(bh[j], br[j])                       # same users, sequences, negatives
+            assert br[8].dtype == np.int64 and not br[4].any() and not br[6].any()
+            out_h = models[0].train_step(bh[0], bh[1], bh[2], bh[3], bh[4], bh[6], bh[7])
+            out_r = models[1].train_step(br[0], br[1], br[2], br[3], timestamps=br[8])
+            c_h, c_r = models[0].engine.ctx(8), models[1].engine.ctx(8)
+            assert torch.equal(c_h.cids, c_r.cids)                        # bins, hours, weekdays: bit-exact
+            assert out_h == out_r
+        assert torch.equal(models[0].engine.w, models[1].engine.w)
+    finally:
+        for s in samplers:
+            s.close()
+    res = []
+    for m in models:
+        random.seed(3)
+        np.random.seed(3)
+        res.append(cev.evaluate(m, dataset, args, None, batch_users=16))
+    assert res[0] == res[1]
+
+
+@pytest.mark.emu
+def test_raw_timestamp_path_equals_host_features_emulated():
+    _raw_vs_host("emu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_scale", [False, True])
+def test_raw_timestamp_path_equals_host_features_gpu(log_scale):
+    _raw_vs_host("gpu", log_scale)
