@@ -83,6 +83,7 @@ SIGNATURES = {
     "cast_embed_fwd_sharded": (I, [P, P, I, I, I, L, I, F, P, P, F, U64, P, I, P, P, P]),
     "cast_logits_loss_sharded": (I, [P, P, I, I, I, L, P, P, P, P, P, P, P, P, P, SZ, P]),
     "cast_score_rank_cand_sharded": (I, [P, L, P, I, I, I, L, P, I, P, P, P, P]),
+    "cast_scatter_set_chunk": (I, [I]),
     "cast_scatter_sort_sharded": (I, [P, I, L, I, I, I, P, SZ, P]),
     "cast_scatter_sorted_offsets": (I, [L, I, I, P, P]),
     "cast_scatter_apply_range": (I, [I, L, P, P, P, I, P, P, P, C.c_uint, C.c_uint, P, SZ, I, P]),

@@ -105,8 +105,10 @@ struct ScatterSrc {
   float scale[4];
 };
 
-constexpr int SEG_CHUNK = 32;  // sorted entries walked by one warp (SEG_Q per lane): short walks, many warps in flight
-constexpr int SEG_Q = SEG_CHUNK / 32;
+// sorted entries walked by one warp: 32 (one per lane: short walks, many warps in flight — sparse tables, remote rows)
+// or 64 (heavily duplicated ids: half as many chunk partials to stitch per popular row).  0 = choose per call from
+// the mean run length (entries per table row); cast_scatter_set_chunk forces one.
+static int g_seg_chunk = 0;
 // entries whose row loads are in flight together (NV = columns per lane): bounded so the staging registers stay <= 64
 
 // Stage 1: every warp walks SEG_CHUNK consecutive sorted entries, lanes own columns.  Each lane first resolves two
@@ -116,11 +118,12 @@ constexpr int SEG_Q = SEG_CHUNK / 32;
 // ("head": the run began in an earlier chunk) and/or part[w][1] ("tail": the run begins here and continues).  Stage 2
 // stitches the pieces of each crossing run in chunk order.  Work per warp is bounded by the chunk size however
 // skewed the id distribution is (popular items own thousands of entries).
-template <int NV>
+template <int NV, int SEG_CHUNK>
 __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ spay,
                                        long total, long N, ScatterSrc src, unsigned klo, unsigned khi, int H,
                                        float* __restrict__ dtable, float* __restrict__ part, int* __restrict__ pkey,
                                        int accumulate) {
+  constexpr int SEG_Q = SEG_CHUNK / 32;
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long beg = w * SEG_CHUNK;
@@ -248,7 +251,7 @@ __global__ void segment_stitch_kernel(const float* __restrict__ part, const int*
   if (w >= nchunks) return;
   const int key = pkey[w * 2 + 1];
   if (key <= 0 || (unsigned)key < klo || (unsigned)key >= khi) return;
-  constexpr int ST_U = NV <= 2 ? 8 : (NV <= 4 ? 4 : (NV <= 8 ? 2 : 1));
+  constexpr int ST_U = NV <= 2 ? 16 : (NV <= 4 ? 8 : (NV <= 8 ? 4 : 2));
   long L = 0;  // chunks w+1 .. w+L continue the run
   for (;;) {
     const long w2 = w + 1 + L + lane;
@@ -344,14 +347,14 @@ using namespace cast;
 
 // per-call scratch of the reduce half: chunk partials [nseg][2][H] followed by their keys [nseg][2]
 extern "C" size_t cast_scatter_partial_bytes(long N, int nsrc, int H) {
-  return (size_t)cdiv(N * nsrc, SEG_CHUNK) * 2 * ((size_t)H * sizeof(float) + sizeof(int));
+  return (size_t)cdiv(N * nsrc, 32) * 2 * ((size_t)H * sizeof(float) + sizeof(int));   // (sized for 32-entry chunks)
 }
 
 extern "C" size_t cast_scatter_workspace_bytes(long N, int nsrc, int V) {
   const long total = N * nsrc;
   const long nchunks = cdiv(total, RS_CHUNK);
   (void)V;
-  const long nseg = cdiv(total, SEG_CHUNK);
+  const long nseg = cdiv(total, 32);
   return (size_t)(5 * total + 256 * nchunks) * sizeof(unsigned) + (size_t)nseg * 2 * sizeof(int) + 64;
 }
 
@@ -398,6 +401,13 @@ static int scatter_sort_impl(const int* keys, int nsrc, long N, int V, int nshar
     kin = kout;
     pin = pout;
   }
+  return CAST_OK;
+}
+
+/* tuning hook: sorted entries per warp in the segment sums (32 or 64) */
+extern "C" int cast_scatter_set_chunk(int entries) {
+  if (entries != 0 && entries != 32 && entries != 64) return set_error(CAST_ERR_BAD_ARG, "scatter_set_chunk: 0, 32 or 64");
+  g_seg_chunk = entries;
   return CAST_OK;
 }
 
@@ -448,15 +458,21 @@ static int scatter_apply_impl(int nsrc, long N, const float* const* rows, const 
   // (accumulate: dtable already holds the sum of an earlier call over other sources; every row is written at most
   // once per call, so adding to it is race-free and keeps a fixed summation order)
   if (!accumulate) cudaMemsetAsync(dtable, 0, (size_t)dtable_rows * H * sizeof(float), st);
-  const long nseg = cdiv(total, SEG_CHUNK);
+  const int chunk = g_seg_chunk ? g_seg_chunk : (total >= 8 * ((long)khi - (long)klo) ? 64 : 32);
+  const long nseg = cdiv(total, chunk);
   float* part = static_cast<float*>(partial);
   int* pkey = reinterpret_cast<int*>(part + (size_t)nseg * 2 * H);
   const int wpb = 4;
   const dim3 grid((unsigned)cdiv(nseg, wpb)), block(32 * wpb);
 #define CAST_SEG(NV)                                                                                            \
   {                                                                                                             \
-    CAST_LAUNCH(segment_partial_kernel<NV>, grid, block, 0, st, kin, pin, total, N, src, klo, khi, H, dtable,   \
-                part, pkey, accumulate);                                                                        \
+    if (chunk == 32) {                                                                                          \
+      CAST_LAUNCH((segment_partial_kernel<NV, 32>), grid, block, 0, st, kin, pin, total, N, src, klo, khi, H,   \
+                  dtable, part, pkey, accumulate);                                                              \
+    } else {                                                                                                    \
+      CAST_LAUNCH((segment_partial_kernel<NV, 64>), grid, block, 0, st, kin, pin, total, N, src, klo, khi, H,   \
+                  dtable, part, pkey, accumulate);                                                              \
+    }                                                                                                           \
     if ((rc = check_launch("segment_partial"))) return rc;                                                      \
     CAST_LAUNCH(segment_stitch_kernel<NV>, grid, block, 0, st, (const float*)part, (const int*)pkey, nseg, klo, \
                 khi, H, dtable, accumulate);                                                                    \

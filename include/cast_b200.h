@@ -70,6 +70,8 @@ int cast_score_rank_cand_sharded(const float* seq_last, long ld, const float* co
  * then folds, rank by rank in rank order, the entries that belong to its rows into its dense gradient shard
  * (cast_scatter_apply_range; keys of rank r: [r*rows_per_shard, (r+1)*rows_per_shard)).  cast_scatter_sorted_offsets
  * locates the sorted arrays inside a sort workspace. */
+/* tuning hook: sorted entries walked by one warp in the segment sums (32 or 64; 0 = per call from the mean run length) */
+int cast_scatter_set_chunk(int entries);
 int cast_scatter_sort_sharded(const int* keys, int nsrc, long N, int V, int nshards, int rows_per_shard,
                               void* workspace, size_t workspace_bytes, void* stream);
 int cast_scatter_sorted_offsets(long N, int nsrc, int Vkeys, size_t* keys_offset, size_t* payload_offset);
