@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json workload (default: the "
                     "one the metric is quoted on)")
+    ap.add_argument("--model", default=None, help="override the config's model (e.g. --config c3 --model cast_4)")
     ap.add_argument("--cpu_steps", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
@@ -260,6 +261,11 @@ def main():
     ap.add_argument("--no_dp_parity", action="store_true")
     a = ap.parse_args()
     select_config(a.config)
+    if a.model:
+        global WORKLOAD
+        CFG["model"] = a.model
+        CFG["desc"] = CFG["desc"] + f" [model {a.model}]"
+        WORKLOAD = CFG["desc"]
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -145,10 +145,13 @@ def metrics_from_histogram(hist) -> tuple:
     return ndcg / n, ht / n
 
 
-def score_users(model, cand, batch_users: int = 256, lo: int = 0, hi: Optional[int] = None, mode: str = "101"):
+def score_users(model, cand, batch_users: int = 256, lo: int = 0, hi: Optional[int] = None, mode: str = "101",
+                attn_sum=None):
     """Ranks of cand rows [lo, hi) through the model's batched scoring path; fixed batch shape (tail padded).
     mode "101": the reference's target + 100 sampled negatives; mode "full": rank among every item the user has not
     rated (count of strictly greater logits; exact ties do not push the target down)."""
+    """attn_sum (optional float64 device tensor [T,T]): accumulates the first-head attention map of every scored
+    user — what the reference collects per user in --test_model mode (util.py:329-336)."""
     hi = len(cand["u"]) if hi is None else hi
     ranks = np.zeros(max(0, hi - lo), np.int64)
     B = max(1, min(batch_users, max(1, hi - lo)))
@@ -169,20 +172,25 @@ def score_users(model, cand, batch_users: int = 256, lo: int = 0, hi: Optional[i
                                               pad(cand["hours"]), pad(cand["days"]))
             ranks[s - lo:e - lo] = cgt[:n]
             continue
+        want = attn_sum is not None
         if getattr(model, "timefeat", None) is not None and "tsraw" in cand:
             # time bins / hours / weekdays derived on the device from the raw event times (util.py:276-289)
             logits, cgt, ceq = model.score_candidates(pad(cand["seq"]), pad(cand["item_idx"]),
-                                                      timestamps=pad(cand["tsraw"]))
+                                                      timestamps=pad(cand["tsraw"]), want_attn=want)
         else:
             logits, cgt, ceq = model.score_candidates(pad(cand["seq"]), pad(cand["item_idx"]), pad(cand["timeseq"]),
-                                                      pad(cand["hours"]), pad(cand["days"]))
+                                                      pad(cand["hours"]), pad(cand["days"]), want_attn=want)
+        if want:   # head 0 of user b is row b of the [h*B, T, T] stack (modules.py:208-213)
+            attn_sum += model.engine.ctx(B).attn[:n].sum(0, dtype=attn_sum.dtype)
         ranks[s - lo:e - lo] = ranks_from_device(logits[:n], cgt[:n], ceq[:n])
     return ranks
 
 
-def _evaluate(model, dataset, args, split, batch_users, rng, mode="101"):
+def _evaluate(model, dataset, args, split, batch_users, rng, mode="101", avg_attention=False):
     cand = build_candidates(dataset, args, split, rng)
     U = len(cand["u"])
+    if avg_attention:
+        return _evaluate_with_attention(model, cand, batch_users, mode)
     try:
         import torch.distributed as dist
         world = dist.get_world_size() if dist.is_initialized() else 1
@@ -206,10 +214,45 @@ def _evaluate(model, dataset, args, split, batch_users, rng, mode="101"):
     return metrics_from_histogram(h.cpu().numpy())
 
 
-def evaluate(model, dataset, args, sess=None, batch_users: int = 256, rng=None, mode: str = "101"):
+def _evaluate_with_attention(model, cand, batch_users, mode):
+    """metrics + the attention map averaged over the evaluated users (reference util.py:329-336; the reference renders
+    it to attention_weights.svg, here the [T,T] array is returned — plotting is out of scope)."""
+    import torch
+    eng = model.engine
+    U = len(cand["u"])
+    acc = torch.zeros(eng.T, eng.T, dtype=torch.float64, device=eng.device)
+    world, rank = 1, 0
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+    except Exception:  # pragma: no cover
+        pass
+    if world == 1:
+        ranks = score_users(model, cand, batch_users, mode="101", attn_sum=acc)
+        return metrics_from_ranks(ranks), (acc / max(1, U)).cpu().numpy()
+    from . import dist as cdist
+    lo, hi = cdist.shard_users(U, rank, world)
+    ranks = score_users(model, cand, batch_users, lo, hi, mode="101", attn_sum=acc)
+    hist = np.zeros(11, np.int64)
+    for r in ranks:
+        if r < 10:
+            hist[r] += 1
+    hist[10] = len(ranks)
+    on_dev = dist.get_backend() == "nccl"
+    h = torch.from_numpy(hist).to(eng.device if on_dev else "cpu")
+    cdist.reduce_rank_histogram(h)
+    a = acc if on_dev else acc.cpu()
+    dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    return metrics_from_histogram(h.cpu().numpy()), (a / max(1, U)).cpu().numpy()
+
+
+def evaluate(model, dataset, args, sess=None, batch_users: int = 256, rng=None, mode: str = "101",
+             avg_attention: bool = False):
     """Drop-in for reference util.evaluate (test split).  mode="full" ranks against the whole catalog instead of the
-    reference's 100 sampled negatives (the negatives are still drawn, so the RNG streams stay aligned)."""
-    return _evaluate(model, dataset, args, "test", batch_users, rng, mode)
+    reference's 100 sampled negatives (the negatives are still drawn, so the RNG streams stay aligned).
+    avg_attention=True (the reference's --test_model behaviour, util.py:329-336): returns ((NDCG, HR), avg_attn [T,T])."""
+    return _evaluate(model, dataset, args, "test", batch_users, rng, mode, avg_attention)
 
 
 def evaluate_valid(model, dataset, args, sess=None, batch_users: int = 256, rng=None, mode: str = "101"):

@@ -231,11 +231,12 @@ class _Model:
         self.attention_weights = c.attn
         return [logits.cpu().numpy(), c.attn.cpu().numpy()]
 
-    def score_candidates(self, seq, cand, time_seq=None, hours=None, days=None, timestamps=None):
+    def score_candidates(self, seq, cand, time_seq=None, hours=None, days=None, timestamps=None, want_attn=False):
         """Batched evaluation scoring: per-user candidate lists cand [U, C] (candidate 0 = target).
-        Returns (logits [U,C], count_greater [U], count_equal [U]) as numpy arrays (util.py:317-321 fused)."""
+        Returns (logits [U,C], count_greater [U], count_equal [U]) as numpy arrays (util.py:317-321 fused);
+        want_attn also fills the [h*U, T, T] attention stack of the model's exposed tower (ctx(U).attn)."""
         eng = self.engine
-        c = self.forward_eval(seq, time_seq, hours, days, timestamps=timestamps)
+        c = self.forward_eval(seq, time_seq, hours, days, want_attn=want_attn, timestamps=timestamps)
         B, T, H = c.B, eng.T, eng.H
         cand_t = torch.from_numpy(np.ascontiguousarray(np.asarray(cand, dtype=np.int32))).to(eng.device)
         Cn = cand_t.shape[1]

@@ -168,9 +168,13 @@ def run(args, device=None, lib=None, logger=None):
                 auc, loss = train_on(next_batch())  # as main.py:167-175
                 print(auc)
                 print(loss)
-                t_test = evaluate(model, dataset, args, None, batch_users=args.eval_batch, mode=args.eval_mode)
+                # as util.py:329-336: the attention map averaged over the evaluated users goes next to the checkpoint
+                # (the reference renders attention_weights.svg; the array is stored instead)
+                t_test, avg_attn = evaluate(model, dataset, args, None, batch_users=args.eval_batch,
+                                            avg_attention=True)
                 logger.info("test (NDCG@10: %.4f, HR@10: %.4f)" % (t_test[0], t_test[1]))
                 if rank == 0:
+                    np.save(os.path.join(args.test_model, "avg_attention_weights.npy"), avg_attn)
                     with open(os.path.join(args.test_model, "test_seq_len.txt"), "a") as f:
                         f.write("{},{},{}\n".format(args.test_seq_len, t_test[0], t_test[1]))
             else:

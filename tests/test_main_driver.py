@@ -45,9 +45,18 @@ def test_train_eval_checkpoint_cycle(tmp_path):
     line = open(os.path.join(d, "log.txt")).read().strip()
     valid, test = eval("[" + line.replace(") (", "), (") + "]")     # "(ndcg, hr) (ndcg, hr)" as the reference writes
     assert 0.0 <= valid[1] <= 1.0 and 0.0 <= test[1] <= 1.0
+    assert "np." not in line and "float64" not in line              # plain floats, the reference's log.txt format
     assert os.path.isfile(os.path.join(d, "model.ckpt.index")) and os.path.isfile(os.path.join(d, "model.ckpt.npz"))
     # --test_model: restore, one train step, evaluate with truncated sequences, append to test_seq_len.txt
     args2 = driver.build_parser().parse_args(argv + ["--test_model", d, "--test_seq_len", "3"])
     assert driver.run(args2, device=dev, lib=lib) == 0
     row = open(os.path.join(d, "test_seq_len.txt")).read().strip().split(",")
     assert row[0] == "3" and 0.0 <= float(row[2]) <= 1.0
+    # util.py:329-336: the attention map averaged over the evaluated users (rows are distributions over the keys)
+    import numpy as np
+    avg = np.load(os.path.join(d, "avg_attention_weights.npy"))
+    assert avg.shape == (8, 8) and np.allclose(avg.sum(1), 1.0, atol=1e-4)
+    # the bundle carries the whole Saver state under the reference's names
+    from cast_b200 import checkpoint as ck
+    tfv = ck.read_bundle(os.path.join(d, "model.ckpt"))
+    assert "global_step" in tfv and "SASRec/input_embeddings/lookup_table/Adam_1" in tfv and "beta2_power" in tfv
