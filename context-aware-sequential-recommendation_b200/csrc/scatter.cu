@@ -130,7 +130,7 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
   if (beg >= total) return;
   const long end = beg + SEG_CHUNK < total ? beg + SEG_CHUNK : total;
   const int cnt = (int)(end - beg);
-  constexpr int SEG_U = NV <= 8 ? 8 : (NV <= 16 ? 4 : 2);
+  constexpr int SEG_U = NV <= 2 ? 16 : (NV <= 8 ? 8 : (NV <= 16 ? 4 : 2));
   // ---- this lane's two entries
   unsigned mk[SEG_Q];
   float mf[SEG_Q];
@@ -267,18 +267,23 @@ __global__ void segment_stitch_kernel(const float* __restrict__ part, const int*
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[u][i] = 0.f;
   for (long j0 = 0; j0 < L; j0 += ST_U) {
+    // all ST_U loads of the batch are issued before the first add (the run's chunks are summed by ONE warp: the walk
+    // is a chain of L2 round trips unless the loads are in flight together); partial j goes to accumulator j mod ST_U
+    float val[ST_U][NV];
 #pragma unroll
     for (int u = 0; u < ST_U; ++u) {
       const long j = j0 + u;
-      if (j < L) {
-        const float* src = part + ((w + 1 + j) * 2 + 0) * H;
+      const float* src = part + ((w + 1 + (j < L ? j : 0)) * 2 + 0) * H;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c = lane + 32 * i;
-          if (c < H) acc[u][i] += src[c];
-        }
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        val[u][i] = (j < L && c < H) ? src[c] : 0.f;
       }
     }
+#pragma unroll
+    for (int u = 0; u < ST_U; ++u)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[u][i] += val[u][i];
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {

@@ -16,3 +16,8 @@ echo "list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"ru_ln|attn_|qkv_bwd|ffn_bwd|segment_" -s 36 -c 14 -o gpurun_out/${TAG}_prof -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full rc=$?"; tail -2 gpurun_out/${TAG}_ncu_full.log
+# only text summaries travel back (the .ncu-rep with sources exceeds the 64 MiB return limit)
+python scripts/ncu_summary.py gpurun_out/${TAG}_prof.ncu-rep > gpurun_out/${TAG}_ncu_full_summary.txt 2>&1
+python scripts/launch_summary.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.txt 2>&1
+rm -f gpurun_out/${TAG}_prof.ncu-rep
+ls -la gpurun_out | head -30
