@@ -340,7 +340,11 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     t_dev = sum(s.elapsed_time(e) for s, e in ev) / 1e3
     t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    t_dev_min = t_dev
     if world > 1:
+        tmin = t.clone()
+        torch.distributed.all_reduce(tmin, op=torch.distributed.ReduceOp.MIN)
+        t_dev_min = float(tmin.item())
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     t_dev = float(t.item())
     value = world * B * a.steps / t_dev
@@ -454,6 +458,7 @@ def main():
                                                      "owner-pull gradient)" % world if shard else ""),
                      "l2": "flushed (256 MiB write) between timed steps",
                      "timing": "per-step CUDA events on the launch stream, max over ranks",
+                     "ms_per_step_fastest_rank": t_dev_min / a.steps * 1e3,
                      "input_path": "pre-generated synthetic batches (not the reference sampler)"},
            "e2e": e2e, "gpu_launches": int(launches_per_step) * a.steps, "launches_per_step": int(launches_per_step),
            "clocks": clk}
@@ -475,7 +480,7 @@ def main():
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
-        torch.distributed.barrier()
+        cdist.quiesce(eng)
         torch.distributed.destroy_process_group()
     if dp_parity is not None and not dp_parity["ok"]:
         sys.exit(3)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "cast_block_bwd_workspace_bytes": (SZ, [L, I]),
     "cast_ffn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, F, U64, P, I, L, I, P, P, P, SZ, P]),
     "cast_qkv_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, L, I, P, P, P, SZ, P]),
+    "cast_qkv_bwd_embed": (I, [P, P, P, P, P, P, P, P, P, P, P, P, L, I, P, F, U64, P, I, P, P, P, SZ, P]),
     "cast_colsum_workspace_bytes": (SZ, [L, L]),
     "cast_colsum": (I, [P, L, L, L, P, P, SZ, P]),
     "cast_attn_set_chunk": (I, [I]),
@@ -77,6 +78,7 @@ SIGNATURES = {
     "cast_adam_init_state": (I, [P, F, F, P]),
     "cast_adam_tf_step": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, P]),
     "cast_adam_tf_range": (I, [P, P, P, P, L, F, F, F, F, P, F, L, L, P, I, P]),
+    "cast_adam_tf_step_peers": (I, [P, P, I, P, P, P, L, L, F, F, F, F, F, L, L, P, P]),
     "cast_score_rank_cand": (I, [P, L, P, I, I, L, P, I, P, P, P, P]),
     "cast_score_rank_full_workspace_bytes": (SZ, [L, I, I]),
     "cast_score_rank_full": (I, [P, L, P, I, I, L, P, P, P, P, I, P, P, P, P, SZ, P]),

@@ -242,6 +242,22 @@ struct LnBwdOut {
   float dgamma, dbeta;  // column owned by thread (tid % 64) for tid < 128: tid/64 == 0 -> dgamma, == 1 -> dbeta
 };
 
+// Optional last step on the dx rows this helper writes: the gradient of `dropout(emb) * mask` at the tower input
+// (sasrec.py:58-62), so that block 0's backward kernel emits the embedding gradient directly.
+struct LnOutFx {
+  const int* ids;  // row mask (ids[row] == 0 => 0), may be null
+  Drop drop;
+  bool on;
+};
+__device__ __forceinline__ LnOutFx ln_out_none() {
+  LnOutFx f;
+  f.ids = nullptr;
+  f.drop.k0 = f.drop.k1 = f.drop.thresh = 0u;
+  f.drop.scale = 1.f;
+  f.on = false;
+  return f;
+}
+
 template <int NWARP = FT / 32, bool COLS = true>
 __device__ __forceinline__ void f_ln_bwd_rows(const float* __restrict__ Gs, const float* __restrict__ Xr, int sxr,
                                               int sxc, const float* __restrict__ Add,
@@ -249,7 +265,7 @@ __device__ __forceinline__ void f_ln_bwd_rows(const float* __restrict__ Gs, cons
                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                               float* __restrict__ rowstat /* smem [FR][4] */, long row0,
                                               const FDims& d, float* __restrict__ dx, float& dgamma_acc,
-                                              float& dbeta_acc) {
+                                              float& dbeta_acc, const LnOutFx fx = ln_out_none()) {
   const int t = threadIdx.x;
   // (a) per-row scalars: one warp per row
   {
@@ -273,14 +289,17 @@ __device__ __forceinline__ void f_ln_bwd_rows(const float* __restrict__ Gs, cons
         rowstat[r * 4 + 3] = s2;
       }
       if (row < d.N) {
+        const float fm = (fx.on && fx.ids && fx.ids[row] == 0) ? 0.f : 1.f;
         if (c0 < d.H) {
           float o = rs * (a0 - s1 - x0 * s2);
           if (Add) o += Add[r * d.HS + c0];
+          if (fx.on) o = o * fm * drop_mul(fx.drop, (unsigned long long)(row * d.H + c0));
           dx[row * d.H + c0] = o;
         }
         if (c1 < d.H) {
           float o = rs * (a1 - s1 - x1 * s2);
           if (Add) o += Add[r * d.HS + c1];
+          if (fx.on) o = o * fm * drop_mul(fx.drop, (unsigned long long)(row * d.H + c1));
           dx[row * d.H + c1] = o;
         }
       }
@@ -447,7 +466,23 @@ struct QkvBwdArgs {
   float* dx;
   float* partial;  // [gridDim.x][2H + 3(H*H + H)]
   long ntiles;
+  // block 0 of a tower whose input is dropout(embedding) * mask: dx *= mask(out_ids) * dropout(out_rate, out_site)
+  const int* out_ids;
+  float out_rate;
+  unsigned long long seed;
+  const unsigned long long* step;
+  int out_site;
+  int out_fx;
 };
+__device__ __forceinline__ LnOutFx qkv_out_fx(const QkvBwdArgs& a) {
+  LnOutFx f = ln_out_none();
+  if (a.out_fx) {
+    f.ids = a.out_ids;
+    f.drop = make_drop(a.out_rate, a.seed, a.step, a.out_site);
+    f.on = true;
+  }
+  return f;
+}
 
 __global__ void __launch_bounds__(FT) qkv_bwd_kernel(QkvBwdArgs a, FDims d) {
   CAST_DYN_SMEM(float, sm);
@@ -463,6 +498,7 @@ __global__ void __launch_bounds__(FT) qkv_bwd_kernel(QkvBwdArgs a, FDims d) {
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int col = tx * 4;
   const bool active = col < d.HP4;
+  const LnOutFx ofx = qkv_out_fx(a);
   f_load_w_T(WqT, a.Wq, d);
   f_load_w_T(WkT, a.Wk, d);
   f_load_w_T(WvT, a.Wv, d);
@@ -513,7 +549,7 @@ __global__ void __launch_bounds__(FT) qkv_bwd_kernel(QkvBwdArgs a, FDims d) {
       }
     }
     __syncthreads();
-    f_ln_bwd_rows(Gq, XT, 1, FTS, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet);
+    f_ln_bwd_rows(Gq, XT, 1, FTS, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet, ofx);
   }
   const int H = d.H;
   float* P = a.partial + (long)blockIdx.x * (2L * H + 3L * (H * H + H));
@@ -690,10 +726,13 @@ extern "C" int cast_ffn_bwd(const float* dx, const int* ids, const float* zn, co
                                 (cudaStream_t)stream);
 }
 
-extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, const float* dres, const float* x,
-                            const float* qn, const float* mean, const float* rstd, const float* gamma, const float* Wq,
-                            const float* Wk, const float* Wv, long N, int H, float* dx, float* grads_out,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+// out_fx != 0: dx is also multiplied by the padding mask of out_ids (may be null) and by the dropout keep/scale of
+// (out_rate, seed, *step, out_site) at flat index row*H + col — the gradient of `dropout(emb) * mask` (sasrec.py:58-62)
+static int qkv_bwd_impl(const float* dQ, const float* dK, const float* dV, const float* dres, const float* x,
+                        const float* qn, const float* mean, const float* rstd, const float* gamma, const float* Wq,
+                        const float* Wk, const float* Wv, long N, int H, float* dx, float* grads_out, void* workspace,
+                        size_t workspace_bytes, int out_fx, const int* out_ids, float out_rate, unsigned long long seed,
+                        const unsigned long long* step, int out_site, void* stream) {
   if (!dQ || !dK || !dV || !dres || !x || !qn || !mean || !rstd || !gamma || !Wq || !Wk || !Wv || !dx || N <= 0)
     return set_error(CAST_ERR_BAD_ARG, "qkv_bwd");
   if (!cast_fused_supported(H)) return set_error(CAST_ERR_UNSUPPORTED, "qkv_bwd: H > 64");
@@ -702,7 +741,8 @@ extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, c
   const FDims d = fdims(N, H);
   const long ntiles = cdiv(N, FR);
   const int grid = bwd_grid(ntiles, 1);
-  QkvBwdArgs a{dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv, dx, static_cast<float*>(workspace), ntiles};
+  QkvBwdArgs a{dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv, dx, static_cast<float*>(workspace), ntiles,
+               out_ids, out_rate, seed, step, out_site, out_fx};
   if (g_fused_backend & 1) {
 #define CAST_CALL(K) launch_qkv_bwd_mma<K>(a, d, grid, (cudaStream_t)stream)
     CAST_KS_SWITCH(H, CAST_CALL)
@@ -718,4 +758,22 @@ extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, c
   const long count = 2L * H + 3L * ((long)H * H + H);
   return launch_reduce_partials(static_cast<float*>(workspace), grid, count, grads_out, count, (float*)nullptr,
                                 (cudaStream_t)stream);
+}
+
+extern "C" int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, const float* dres, const float* x,
+                            const float* qn, const float* mean, const float* rstd, const float* gamma, const float* Wq,
+                            const float* Wk, const float* Wv, long N, int H, float* dx, float* grads_out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  return qkv_bwd_impl(dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv, N, H, dx, grads_out, workspace,
+                      workspace_bytes, 0, nullptr, 0.f, 0ull, nullptr, 0, stream);
+}
+
+extern "C" int cast_qkv_bwd_embed(const float* dQ, const float* dK, const float* dV, const float* dres, const float* x,
+                                  const float* qn, const float* mean, const float* rstd, const float* gamma,
+                                  const float* Wq, const float* Wk, const float* Wv, long N, int H,
+                                  const int* mask_ids, float drop_rate, unsigned long long seed,
+                                  const unsigned long long* step, int site, float* dx, float* grads_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  return qkv_bwd_impl(dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv, N, H, dx, grads_out, workspace,
+                      workspace_bytes, 1, mask_ids, drop_rate, seed, step, site, stream);
 }

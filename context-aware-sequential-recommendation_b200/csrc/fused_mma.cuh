@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
     rm_load_tile_async<S, NW>(b + 4 * TILE, a.qn, row0, d.N, H, v4);
     cp_async_commit();
   };
+  const LnOutFx ofx = qkv_out_fx(a);
   float gWq[1][NTW][4], gWkv[2][NTW][4];
   rm_zero(gWq[0]);
   rm_zero(gWkv[0]);
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
       }
     }
     __syncthreads();
-    f_ln_bwd_rows<NW, false>(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet);
+    f_ln_bwd_rows<NW, false>(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet, ofx);
     rm_ln_cols_slice<SL, S>(Gq, X, rowstat, dgam, dbet);
   }
   float* P = a.partial + (long)blockIdx.x * (2L * H + 3L * (H * H + H));

@@ -166,6 +166,26 @@ class PeerExchange:
         return bool(self.state[1].item())
 
 
+def quiesce(engine, group=None):
+    """No rank may release its peer memory (or exit) while another rank's last optimizer pass still reads it."""
+    if engine.device.type == "cuda":
+        torch.cuda.synchronize(engine.device)
+    if dist.is_initialized():
+        dist.barrier(group=group)
+
+
+def _quiesce_at_exit(engine, group):
+    import atexit
+
+    def _at_exit():
+        try:
+            quiesce(engine, group)
+        except Exception:
+            pass
+
+    atexit.register(_at_exit)
+
+
 def use_peer_exchange(engine) -> bool:
     """peer-memory exchange unless CAST_DP_EXCHANGE=nccl (the process-group all-reduce, kept for A/B runs)"""
     return os.environ.get("CAST_DP_EXCHANGE", "peer") != "nccl"
@@ -193,11 +213,30 @@ def attach(engine, group=None, arena=None):
         engine.arena = arena
         px = engine.peer_exchange = PeerExchange(engine, arena, group)
 
-        def exchange(c):
-            px.barrier()      # every rank's gradient buffer is final
-            px.reduce()       # (Adam consumes the reduced copy)
-            px.barrier()      # everybody has read everybody: the buffers may be overwritten by the next backward pass
+        ab = os.environ.get("CAST_DP_EXCHANGE", "peer")
+        if ab == "peer3":         # A/B: separate reduction launch between two barriers (the first form of this path)
+            def exchange(c):
+                px.barrier()      # every rank's gradient buffer is final
+                px.reduce()       # (Adam consumes the reduced copy)
+                px.barrier()      # everybody has read everybody
+        else:
+            # One barrier on the critical path: every rank's gradient buffer is final => Adam sums the ranks' buffers
+            # itself (cast_adam_tf_step_peers).  The second barrier ("everybody has read everybody: the buffers may be
+            # overwritten") is only needed before the NEXT backward pass writes gradients, so it sits between the next
+            # step's forward and backward, where no rank waits for it.
+            def exchange(c):
+                px.barrier()
 
+            engine.peer_adam = (px.g_ptrs, px.world, px.g_red)
+            engine.before_backward = px.barrier
+            _quiesce_at_exit(engine, group)
+        if ab in ("none", "barrier"):   # measurement hooks only (wrong gradients): where does a multi-rank step's time go?
+            engine.peer_adam = engine.before_backward = None
+
+            def exchange(c):
+                if ab == "barrier":
+                    px.barrier()
+                engine.adam_g.copy_(engine.gbuf)
         engine.grad_allreduce = exchange
         engine.exchange_capturable = True
         if engine.device.type == "cuda":

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional
 
@@ -205,6 +206,10 @@ class Engine:
         self.adam_g = self.gbuf     # what Adam consumes: the local buffer, or the rank-ordered sum (dist.PeerExchange)
         self.exchange_capturable = False   # the exchange is plain kernel launches => the step is one CUDA graph
         self.after_adam = None      # set by dist.attach_sharded(): the barrier that ends a row-sharded step
+        self.fork_reduce = os.environ.get("CAST_FORK_REDUCE", "1") != "0"            # A/B switches (measurement)
+        self.fuse_embed_bwd = os.environ.get("CAST_FUSE_EMBED_BWD", "1") != "0"
+        self.before_backward = None  # set by dist.attach(): the barrier that lets this step overwrite the gradient buffer
+        self.peer_adam = None       # set by dist.attach(): (device pointer table, n_ranks, g_red) => Adam sums the ranks' buffers
         self.shard_ptrs = None      # ... device array of the ranks' item-table shard pointers (own + peer mappings)
 
     # ------------------------------------------------------------------ plumbing
@@ -520,8 +525,10 @@ class Engine:
         self.ln_fwd(x, tower + ".lnf", tb.out, tb.muf, tb.rsf)
         return tb.out
 
-    def tower_bwd(self, c, tower, d_out, ids):
-        """Backward of tower_fwd; parameter gradients land in self.G, returns d(loss)/d(x_in) (tb.dx_in)."""
+    def tower_bwd(self, c, tower, d_out, ids, embed_fx=None):
+        """Backward of tower_fwd; parameter gradients land in self.G, returns d(loss)/d(x_in) (tb.dx_in).
+        embed_fx = (mask ids or None, dropout rate, site, out): on the fused path block 0's kernel also applies the
+        backward of `dropout(emb) * mask` (sasrec.py:58-62) and writes the result to `out` (returned instead)."""
         tb = c.tw[tower]
         H, B, T, h = self.H, c.B, self.T, self.h
         rate = self.rate
@@ -569,11 +576,20 @@ class Engine:
                            b.y.data_ptr(), b.qn.data_ptr(), self._p(c.attn_ws),
                            c.attn_ws.numel() * 4 if c.attn_ws is not None else 0, self._stream())
                 dst = tb.dx_in if i == 0 else t[0]
-                self._call(self.lib.cast_qkv_bwd, dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), dy.data_ptr(),
-                           x_i.data_ptr(), b.qn.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
-                           P[pre + "ln1.gamma"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "k.w"].data_ptr(),
-                           P[pre + "v.w"].data_ptr(), c.N, H, dst.data_ptr(), None,
-                           b.ws_qkv.data_ptr(), b.ws_qkv.numel() * 4, self._stream())
+                if i == 0 and embed_fx is not None:
+                    fx_ids, fx_rate, fx_site, dst = embed_fx
+                    self._call(self.lib.cast_qkv_bwd_embed, dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(),
+                               dy.data_ptr(), x_i.data_ptr(), b.qn.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
+                               P[pre + "ln1.gamma"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "k.w"].data_ptr(),
+                               P[pre + "v.w"].data_ptr(), c.N, H, self._p(fx_ids), float(fx_rate), self.seed,
+                               self.step_ptr, int(fx_site), dst.data_ptr(), None, b.ws_qkv.data_ptr(),
+                               b.ws_qkv.numel() * 4, self._stream())
+                else:
+                    self._call(self.lib.cast_qkv_bwd, dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), dy.data_ptr(),
+                               x_i.data_ptr(), b.qn.data_ptr(), b.mu1.data_ptr(), b.rs1.data_ptr(),
+                               P[pre + "ln1.gamma"].data_ptr(), P[pre + "q.w"].data_ptr(), P[pre + "k.w"].data_ptr(),
+                               P[pre + "v.w"].data_ptr(), c.N, H, dst.data_ptr(), None,
+                               b.ws_qkv.data_ptr(), b.ws_qkv.numel() * 4, self._stream())
                 cnt = 2 * H + 3 * (H * H + H)
                 c.reduce_jobs.append((b.ws_qkv.data_ptr(), self.lib.cast_block_bwd_parts(c.N, 1), cnt,
                                       self.G[pre + "ln1.beta"], cnt))
@@ -737,16 +753,24 @@ class Engine:
             ds = self.merge_bwd(c, d)
             d = ds["seq"]
             dstreams.update({k: v for k, v in ds.items() if k != "seq"})
-        d = self.tower_bwd(c, "main", d, ids)
-        if plan.merge and plan.merge[3] == "pre":
+        add_time, drop, mask = plan.embed
+        pre_merge = bool(plan.merge and plan.merge[3] == "pre")
+        # the tower's input is dropout(emb) * mask: block 0's fused backward kernel applies that gradient itself
+        fuse_embed = ((drop or mask) and not pre_merge and self.use_fused and self.fuse_embed_bwd
+                      and len(c.tw["main"].blocks) > 0
+                      and bool(self.lib.cast_fused_supported(self.H)))
+        d = self.tower_bwd(c, "main", d, ids, embed_fx=(ids if mask else None, self.rate if drop else 0.0, SITE_EMBED,
+                                                        c.g0) if fuse_embed else None)
+        if pre_merge:
             if plan.merge[4]:  # `seq *= mask` after the MLP (cast_9.py:174): mlp_out is already masked => relu_bwd
                 pass           # zeroes those rows (act == 0)
             ds = self.merge_bwd(c, d)
             d = ds["seq"]
             dstreams.update({k: v for k, v in ds.items() if k != "seq"})
-        add_time, drop, mask = plan.embed
         g0 = d
-        if drop or mask:
+        if fuse_embed:
+            g0 = c.g0
+        elif drop or mask:
             self.mask_dropout(d, ids if mask else None, self.rate if drop else 0.0, SITE_EMBED, None, c.g0)
             g0 = c.g0
         if add_time:
@@ -760,14 +784,31 @@ class Engine:
                 self._call(self.lib.cast_colsum, g0.data_ptr(), c.B, th, th, self.G["pos_emb"].data_ptr(),
                            c.ws.data_ptr(), c.ws_bytes, self._stream())
         sq = float(self.H ** 0.5)
-        self.scatter(c, c.keys3, 3, [g0, c.seq_emb, c.seq_emb], [None, c.gpos, c.gneg], [sq, 1.0, 1.0], "item_emb")
+        ctx_scatter = []
         for j, (tname, key) in enumerate((("time_emb", "time"), ("hours_emb", "hours"), ("days_emb", "days"))):
             if tname not in plan.tables:
                 continue
             dk = dstreams[key]
             if key in plan.towers:
                 dk = self.tower_bwd(c, key, dk, ids)
-            self.scatter(c, c.cids[j], 1, [dk], [None], [sq], tname)
+            ctx_scatter.append((j, dk, tname))
+        # every deferred partial sum of the step is known now: its one reduction launch runs beside the embedding
+        # gradient scatters (independent outputs; a parallel branch of the captured graph), joined before the exchange
+        forked = self.fork_reduce and self.device.type == "cuda" and self.timing is None and bool(c.reduce_jobs)
+        if forked:
+            main = torch.cuda.current_stream(self.device)
+            if getattr(c, "side3", None) is None:
+                c.side3 = torch.cuda.Stream(device=self.device)
+            c.side3.wait_stream(main)
+            with torch.cuda.stream(c.side3):
+                self.flush_reduce_jobs(c)
+        try:
+            self.scatter(c, c.keys3, 3, [g0, c.seq_emb, c.seq_emb], [None, c.gpos, c.gneg], [sq, 1.0, 1.0], "item_emb")
+            for j, dk, tname in ctx_scatter:
+                self.scatter(c, c.cids[j], 1, [dk], [None], [sq], tname)
+        finally:
+            if forked:
+                torch.cuda.current_stream(self.device).wait_stream(c.side3)
         self.flush_reduce_jobs(c)
 
     def flush_reduce_jobs(self, c):
@@ -788,6 +829,13 @@ class Engine:
     def adam(self, c):
         # gradients are divided by sums[2] = sum(istarget) (global under data parallelism) inside the kernel; with a
         # row-sharded item table the flat buffers hold this rank's shard first, so the same launch updates it
+        if self.peer_adam is not None:
+            ptrs, n_ranks, g_red = self.peer_adam
+            self._call(self.lib.cast_adam_tf_step_peers, self.w.data_ptr(), ptrs.data_ptr(), n_ranks, g_red.data_ptr(),
+                       self.m.data_ptr(), self.v.data_ptr(), self.n_params, g_red.numel() - self.n_params, self.lr,
+                       self.beta1, self.beta2, self.eps, self.l2, 0, self.l2_hi if self.l2 else 0,
+                       self.adam_state.data_ptr(), self._stream())
+            return
         self._call(self.lib.cast_adam_tf_step, self.w.data_ptr(), self.adam_g.data_ptr(), self.m.data_ptr(),
                    self.v.data_ptr(), self.n_params, self.lr, self.beta1, self.beta2, self.eps,
                    self.adam_g[self.n_params + 2:].data_ptr(), self.l2, 0, self.l2_hi if self.l2 else 0,
@@ -823,6 +871,8 @@ class Engine:
         c.fuse_tail = self.tail_fusable()
         try:
             self.forward(c, train=True)
+            if self.before_backward is not None:   # peers have finished reading the previous step's gradients
+                self.before_backward()
             if c.fuse_tail:
                 self.loss_tail_fused(c)
             else:

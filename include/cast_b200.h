@@ -218,6 +218,14 @@ int cast_qkv_bwd(const float* dQ, const float* dK, const float* dV, const float*
                  const float* mean, const float* rstd, const float* gamma, const float* Wq, const float* Wk,
                  const float* Wv, long N, int H, float* dx, float* grads_out, void* workspace, size_t workspace_bytes,
                  void* stream);
+/* Block 0 of a tower whose input is dropout(embedding) * mask (sasrec.py:58-62): the same kernel, with dx also
+ * multiplied by the padding mask of mask_ids (may be NULL) and the dropout keep/scale of (drop_rate, seed, *step, site)
+ * at flat index row*H + col — i.e. cast_qkv_bwd followed by cast_mask_dropout, one launch, same bits. */
+int cast_qkv_bwd_embed(const float* dQ, const float* dK, const float* dV, const float* dres, const float* x,
+                       const float* qn, const float* mean, const float* rstd, const float* gamma, const float* Wq,
+                       const float* Wk, const float* Wv, long N, int H, const int* mask_ids, float drop_rate,
+                       unsigned long long seed, const unsigned long long* step, int site, float* dx, float* grads_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[c] = sum_r X[r*ld + c] (bias gradients; learned-position gradient = sum over the batch), deterministic. */
 size_t cast_colsum_workspace_bytes(long rows, long cols);
@@ -329,6 +337,15 @@ int cast_adam_tf_step(float* w, const float* grad, float* m, float* v, long n, f
 int cast_adam_tf_range(float* w, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
                        float eps, const float* gdenom, float l2, long l2_lo, long l2_hi, void* state, int advance,
                        void* stream);
+
+/* Data-parallel form of the same update (sasrec.py:105-121 with the global sum(istarget) as denominator): grads is a
+ * DEVICE array of n_ranks device pointers (own buffer + peer mappings, cast_peer_open), each n + tail floats = gradient
+ * numerators then [loss_sum, auc_sum, count, ...] (tail >= 3).  The update uses sum_r grads[r][i] taken in rank order
+ * (same bits on every rank) divided by sum_r count_r; the reduced n + tail floats are also left in g_red.  One launch
+ * instead of cast_peer_reduce + cast_adam_tf_step; bracket it with cast_peer_barrier like cast_peer_reduce. */
+int cast_adam_tf_step_peers(float* w, const void* const* grads, int n_ranks, float* g_red, float* m, float* v, long n,
+                            long tail, float lr, float beta1, float beta2, float eps, float l2, long l2_lo, long l2_hi,
+                            void* state, void* stream);
 
 /* sasrec.py:93-97 + util.py:318-321: logits[u,c] = seq_last[u,:] . table0[cand[u,c],:] (sequential-k, unfused
  * multiply/add so the order is reproducible), and for candidate 0 the pair (count_greater, count_equal_excl_self)

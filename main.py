@@ -229,6 +229,7 @@ def run(args, device=None, lib=None, logger=None):
     if world > 1:
         import torch.distributed as tdist
         if tdist.is_initialized():
+            cdist.quiesce(model.engine)      # no rank leaves while a peer's last optimizer pass reads its gradients
             tdist.destroy_process_group()
     if rc == 0:
         print("Done")

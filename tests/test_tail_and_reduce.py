@@ -2,6 +2,8 @@
 
 * `cast_reduce_partials_batch` -- several fixed-order partial reductions in one launch (per-CTA gradient partials of
   the fused backward kernels, LayerNorm gamma/beta partials with a pitch, batch column sums) against numpy float64;
+* `cast_adam_tf_step_peers` -- the data-parallel optimizer pass that sums the ranks' gradient buffers itself, bit for
+  bit against `cast_peer_reduce` followed by `cast_adam_tf_step` (sasrec.py:105-121 with the global count);
 * `cast_lnf_loss` -- final LayerNorm (modules.py:53-80) + logits / BCE / AUC (models/sasrec.py:87-115) + LayerNorm
   backward in one launch against the separate `cast_layernorm_fwd` -> `cast_logits_loss` -> `cast_layernorm_bwd` calls
   it replaces (same library, same inputs) and against the oracle's loss.
@@ -106,6 +108,57 @@ def run_tail(kind, N, H, V):
     loss_o = ((-torch.log(torch.sigmoid(plo) + 1e-24) - torch.log(1 - torch.sigmoid(nlo) + 1e-24)) * ist).sum()
     s = sums2.cpu().numpy()
     assert abs(s[0] - float(loss_o)) <= 1e-4 * abs(float(loss_o)) and s[2] == float(ist.sum())
+
+
+def run_adam_peers(kind, n, nranks):
+    """one launch == cast_peer_reduce + cast_adam_tf_step, same bits (buffers of `nranks` ranks in one process)"""
+    lib, dev = backend(kind)
+    st = _stream(kind, dev)
+    rng = np.random.RandomState(n + nranks)
+    tail = 4
+    gs = []
+    for r in range(nranks):
+        g = rng.randn(n + tail).astype(np.float32)
+        g[n + 2] = 100 + r      # this rank's sum(istarget)
+        gs.append(torch.from_numpy(g).to(dev))
+    ptrs = torch.tensor([g.data_ptr() for g in gs], dtype=torch.int64, device=dev)
+    w0 = torch.from_numpy(rng.randn(n).astype(np.float32)).to(dev)
+    out = []
+    for fused in (False, True):
+        w, m, v = w0.clone(), torch.zeros_like(w0), torch.zeros_like(w0)
+        state = torch.zeros(4, dtype=torch.float32, device=dev)
+        assert lib.cast_adam_init_state(state.data_ptr(), 0.9, 0.98, st) == 0
+        g_red = torch.full((n + tail,), 9.0, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            if fused:
+                rc = lib.cast_adam_tf_step_peers(w.data_ptr(), ptrs.data_ptr(), nranks, g_red.data_ptr(), m.data_ptr(),
+                                                 v.data_ptr(), n, tail, 1e-3, 0.9, 0.98, 1e-8, 1e-4, 0, min(n, 40),
+                                                 state.data_ptr(), st)
+            else:
+                rc = lib.cast_peer_reduce(ptrs.data_ptr(), nranks, n + tail, g_red.data_ptr(), st)
+                assert rc == 0, lib.cast_last_error_string()
+                rc = lib.cast_adam_tf_step(w.data_ptr(), g_red.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9,
+                                           0.98, 1e-8, g_red[n + 2:].data_ptr(), 1e-4, 0, min(n, 40),
+                                           state.data_ptr(), st)
+            assert rc == 0, lib.cast_last_error_string()
+        out.append((w.cpu(), m.cpu(), v.cpu(), g_red.cpu(), state.cpu()))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    # and the reduced count is the denominator: first-step m = (1 - beta1) * sum_r g_r / sum_r count_r, checked loosely
+    gsum = torch.stack([g.cpu() for g in gs]).double().sum(0)
+    assert abs(float(out[1][3][n + 2]) - float(gsum[n + 2])) < 1e-3
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("n,nranks", [(1003, 2), (64, 3), (5, 1), (4098, 9)])
+def test_adam_peers_emulated(n, nranks):
+    run_adam_peers("emu", n, nranks)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nranks", [(207850, 2), (1003, 8), (4098, 11), (6, 1)])
+def test_adam_peers_gpu(n, nranks):
+    run_adam_peers("gpu", n, nranks)
 
 
 @pytest.mark.emu
