@@ -190,8 +190,12 @@ def dp_parity_check(model, eng, c, dev_batches, B, world, rank, dev, shard):
     c.cids.copy_(c3)
     eng.launch_fwd_bwd(c)
     eng.grad_allreduce(c)
+    if eng.peer_adam is not None:    # the rank-ordered sum happens inside the optimizer pass, which leaves it in adam_g
+        eng.adam(c)
     torch.cuda.synchronize(dev)
     g_dp = eng.adam_g.clone()        # the exchanged gradients (what Adam consumes)
+    if eng.peer_adam is not None:
+        eng.w.copy_(saved[0]); eng.m.copy_(saved[1]); eng.v.copy_(saved[2]); eng.adam_state.copy_(saved[3])
     # the same global batch on every rank, no exchange
     gk3 = [torch.zeros_like(k3) for _ in range(world)]
     gc3 = [torch.zeros_like(c3) for _ in range(world)]

@@ -811,6 +811,21 @@ class Engine:
                 torch.cuda.current_stream(self.device).wait_stream(c.side3)
         self.flush_reduce_jobs(c)
 
+    def rank_local(self):
+        """context manager: steps launched inside touch no other rank (no barrier, exchange or peer reads) — for
+        rank-local profiling; gradients are then this rank's own and the replicas drift apart, so callers restore state"""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            saved = (self.grad_allreduce, self.after_adam, self.before_backward, self.peer_adam)
+            self.grad_allreduce = self.after_adam = self.before_backward = self.peer_adam = None
+            try:
+                yield self
+            finally:
+                self.grad_allreduce, self.after_adam, self.before_backward, self.peer_adam = saved
+        return cm()
+
     def flush_reduce_jobs(self, c):
         """One fixed-order reduction launch for the per-CTA gradient partials of every fused backward kernel."""
         jobs = c.reduce_jobs
@@ -869,9 +884,24 @@ class Engine:
                 c.presplit_pending = True
         c.reduce_jobs = []
         c.fuse_tail = self.tail_fusable()
+        bb_forked = False
+        if self.before_backward is not None and self.device.type == "cuda" and self.timing is None:
+            # "peers have finished reading the previous step's gradients": a flag round trip over NVLink that nothing in
+            # the forward pass depends on => a parallel branch of the step, joined before the first gradient write
+            main = torch.cuda.current_stream(self.device)
+            if getattr(c, "side4", None) is None:
+                c.side4 = torch.cuda.Stream(device=self.device)
+            c.side4.wait_stream(main)
+            with torch.cuda.stream(c.side4):
+                self.before_backward()
+            bb_forked = True
         try:
-            self.forward(c, train=True)
-            if self.before_backward is not None:   # peers have finished reading the previous step's gradients
+            try:
+                self.forward(c, train=True)
+            finally:
+                if bb_forked:
+                    torch.cuda.current_stream(self.device).wait_stream(c.side4)
+            if self.before_backward is not None and not bb_forked:
                 self.before_backward()
             if c.fuse_tail:
                 self.loss_tail_fused(c)

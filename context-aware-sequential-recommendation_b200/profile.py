@@ -59,17 +59,16 @@ def profile_step(model, c, steps=5):
     {name, calls_per_step, ms_per_step, share, tflops, gbs} sorted by time."""
     eng = model.engine
     B, T, H, h = c.B, eng.T, eng.H, eng.h
-    saved_allreduce, eng.grad_allreduce = eng.grad_allreduce, None  # rank-local profiling: no collective in here
-    saved_after, eng.after_adam = eng.after_adam, None
-    eng.launch_train_step(c)  # warm
-    torch.cuda.synchronize(eng.device)
-    eng.timing = []
-    for _ in range(steps):
-        eng.launch_train_step(c)
-    torch.cuda.synchronize(eng.device)
-    rec, eng.timing = eng.timing, None
-    eng.grad_allreduce = saved_allreduce
-    eng.after_adam = saved_after
+    with eng.rank_local():      # rank-local profiling: no barrier, exchange or peer read in here
+        eng.launch_train_step(c)  # warm
+        torch.cuda.synchronize(eng.device)
+        eng.timing = []
+        try:
+            for _ in range(steps):
+                eng.launch_train_step(c)
+            torch.cuda.synchronize(eng.device)
+        finally:
+            rec, eng.timing = eng.timing, None
     agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
     for name, a, e0, e1 in rec:
         ms = e0.elapsed_time(e1)
