@@ -125,6 +125,13 @@ __device__ __forceinline__ void drop_mul2(const Drop& d, unsigned long long idx,
   }
 }
 
+// the same for a caller that knows idx is even: no parity test, no branch (thresh == 0 keeps everything at scale 1)
+__device__ __forceinline__ void drop_mul2_even(const Drop& d, unsigned long long idx, float& m0, float& m1) {
+  const unsigned h = drop_hash(d, idx >> 1);
+  m0 = (h & 0xffffu) >= d.thresh ? d.scale : 0.0f;
+  m1 = (h >> 16) >= d.thresh ? d.scale : 0.0f;
+}
+
 // multiplier applied by tf.layers.dropout at element idx (0 or 1/(1-rate)); 1 when disabled
 __device__ __forceinline__ float drop_mul(const Drop& d, unsigned long long idx) {
   if (d.thresh == 0u) return 1.0f;

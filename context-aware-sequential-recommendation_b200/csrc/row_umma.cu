@@ -570,15 +570,24 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_ffn_fwd_kernel(RuLnFfnArg
       umma::fence_after_sync();
       RU_STAMP(it, 4);
       float v[16];
+      // this thread's 16 flat indices row*H + c0 + i start even or odd for the whole tile row: the pair-per-hash-word
+      // path is taken without a per-pair parity test (the odd-start loop stays out of the hot instruction stream)
+      const unsigned long long fi0 = (unsigned long long)(row * H + c0);
+      const bool fi_even = (fi0 & 1ull) == 0ull;
       if (have_cols) {  // hidden = dropout(relu(zn W1 + b1))
         umma::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+        float dm[16];
+        if (fi_even) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
+          for (int i = 0; i < 16; i += 2) drop_mul2_even(dh, fi0 + i, dm[i], dm[i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) drop_mul2(dh, fi0 + i, dm[i], dm[i + 1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
-          float m0, m1;
-          drop_mul2(dh, (unsigned long long)(row * H + c), m0, m1);
-          v[i] = (c < H) ? fmaxf(v[i] + vec[2 * 64 + c], 0.f) * m0 : 0.f;
-          v[i + 1] = (c + 1 < H) ? fmaxf(v[i + 1] + vec[2 * 64 + c + 1], 0.f) * m1 : 0.f;
+          v[i] = (c < H) ? fmaxf(v[i] + vec[2 * 64 + c], 0.f) * dm[i] : 0.f;
         }
         ru_row_store(out1, r, c0, H, v);
       } else {
@@ -595,14 +604,16 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_ffn_fwd_kernel(RuLnFfnArg
       RU_STAMP(it, 6);
       if (have_cols) {  // xout = (dropout(hidden W2 + b2) + zn) * mask
         umma::tmem_ld16(tmem + lane_base + (uint32_t)(s.NP + c0), v);
+        float dm[16];
+        if (fi_even) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const int c = c0 + i;
-          float m0, m1;
-          drop_mul2(dout, (unsigned long long)(row * H + c), m0, m1);
-          v[i] = ((v[i] + vec[3 * 64 + c]) * m0 + zn[i]) * m;
-          v[i + 1] = ((v[i + 1] + vec[3 * 64 + ((c + 1) & 63)]) * m1 + zn[i + 1]) * m;
+          for (int i = 0; i < 16; i += 2) drop_mul2_even(dout, fi0 + i, dm[i], dm[i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) drop_mul2(dout, fi0 + i, dm[i], dm[i + 1]);
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = ((v[i] + vec[3 * 64 + ((c0 + i) & 63)]) * dm[i] + zn[i]) * m;
         ru_row_store(out0, r, c0, H, v);
       }
       umma::fence_before_sync();
