@@ -64,6 +64,113 @@ __device__ __forceinline__ void rm_load_w(float* __restrict__ Ws, const float* _
   }
 }
 
+// the same through cp.async (joins the caller's next commit group: the weights arrive with the first row tile)
+template <int S>
+__device__ __forceinline__ void rm_load_w_async(float* __restrict__ Ws, const float* __restrict__ W, int H) {
+  for (int idx = threadIdx.x; idx < H * H; idx += (int)blockDim.x) {
+    const int k = idx / H, n = idx - k * H;
+    cp_async<4>(Ws + k * S + n, W + idx, true);
+  }
+}
+
+// LayerNorm backward over the FR rows of a tile, BT / FR threads per row (8 with 512 threads): thread `sub` of a row
+// owns the float4 column groups (j * TPR + sub) * 4, so that a row's threads read 128 contiguous bytes of shared memory
+// per request and write dx in row-contiguous pieces; row sums by xor shuffles inside the row's threads.
+//   a = G * gamma, xhat = (x - mu) * rs, s1 = mean(a), s2 = mean(a * xhat), dx = rs * (a - s1 - xhat * s2) (+ Add)
+// gam: gamma of this thread's columns (loaded once per kernel).  rowstat[r] = {mu, rs, s1, s2} for the column sums.
+template <int S, int BT>
+struct RmLnRows {
+  static constexpr int TPR = BT / FR, NJ = 64 / (4 * TPR);
+  static_assert(TPR == 4 || TPR == 8, "row threads");
+  float gam[NJ][4];
+  __device__ __forceinline__ void load_gamma(const float* __restrict__ gamma, int H) {
+    const int sub = threadIdx.x % TPR;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = (j * TPR + sub) * 4 + e;
+        gam[j][e] = c < H ? gamma[c] : 0.f;
+      }
+  }
+  __device__ __forceinline__ void run(const float* __restrict__ Gs, const float* __restrict__ Xr,
+                                      const float* __restrict__ Add, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, float* __restrict__ rowstat, long row0,
+                                      const FDims& d, float* __restrict__ dx, const LnOutFx& fx) const {
+    const int t = threadIdx.x, r = t / TPR, sub = t % TPR;
+    const long row = row0 + r;
+    const bool live = row < d.N;
+    const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
+    float av[NJ][4], xh[NJ][4];
+    float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c4 = (j * TPR + sub) * 4;
+      if (c4 < 8 * ((S - 4) / 8)) {   // inside the tile's (zero padded) column range
+        const float4 gq = *reinterpret_cast<const float4*>(Gs + r * S + c4);
+        const float4 xq = *reinterpret_cast<const float4*>(Xr + r * S + c4);
+        const float gg[4] = {gq.x, gq.y, gq.z, gq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool in = c4 + e < d.H;
+          av[j][e] = in ? gg[e] * gam[j][e] : 0.f;
+          xh[j][e] = in ? (xx[e] - mu) * rs : 0.f;
+          p1 += av[j][e];
+          p2 += av[j][e] * xh[j][e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) av[j][e] = xh[j][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < TPR; o <<= 1) {
+      p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+      p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+    }
+    const float s1 = p1 / (float)d.H, s2 = p2 / (float)d.H;
+    if (sub == 0) {
+      rowstat[r * 4 + 0] = mu;
+      rowstat[r * 4 + 1] = rs;
+      rowstat[r * 4 + 2] = s1;
+      rowstat[r * 4 + 3] = s2;
+    }
+    if (!live) return;
+    const float fm = (fx.on && fx.ids && fx.ids[row] == 0) ? 0.f : 1.f;
+    const bool pair = (d.H & 1) == 0 && (reinterpret_cast<uintptr_t>(dx) & 7) == 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c4 = (j * TPR + sub) * 4;
+      if (c4 >= d.H) continue;
+      float o[4];
+      float ad[4] = {0.f, 0.f, 0.f, 0.f};
+      if (Add) {
+        const float4 aq = *reinterpret_cast<const float4*>(Add + r * S + c4);
+        ad[0] = aq.x; ad[1] = aq.y; ad[2] = aq.z; ad[3] = aq.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[e] = rs * (av[j][e] - s1 - xh[j][e] * s2);
+        if (Add) o[e] += ad[e];
+      }
+      if (fx.on) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c4 + e < d.H) o[e] = o[e] * fm * drop_mul(fx.drop, (unsigned long long)(row * d.H + c4 + e));
+      }
+      float* dst = dx + row * d.H + c4;
+      if (pair) {   // H even => c4 + 1 < H whenever c4 < H, and (row * H + c4) * 4 bytes is a multiple of 8
+        *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+        if (c4 + 2 < d.H) *reinterpret_cast<float2*>(dst + 2) = make_float2(o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c4 + e < d.H) dst[e] = o[e];
+      }
+    }
+  }
+};
+
 // acc[nt] += A[16 x 8KS] * Bt^T, Bt[n][k] row-major (k contiguous), n-tiles nt < nact (warp-uniform, <= 4)
 template <int KS, int S, int NTW = 4>
 __device__ __forceinline__ void rm_mm_bt(float (&acc)[NTW][4], const float* __restrict__ As,
@@ -251,9 +358,11 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
   for (int i = t; i < 3 * TILE; i += BT) Wsm[i] = 0.f;      // weights: zero padded to [64][S]
   rm_zero_pad<8 * KS, S>(sm, 10 * FR, H);                   // K-padding columns of the ten stage tiles
   __syncthreads();
-  rm_load_w<S>(Wsm, a.Wq, H);
-  rm_load_w<S>(Wsm + TILE, a.Wk, H);
-  rm_load_w<S>(Wsm + 2 * TILE, a.Wv, H);
+  rm_load_w_async<S>(Wsm, a.Wq, H);   // (committed with the first tile's group below, or by the lone commit)
+  rm_load_w_async<S>(Wsm + TILE, a.Wk, H);
+  rm_load_w_async<S>(Wsm + 2 * TILE, a.Wv, H);
+  RmLnRows<S, BT> lnr;
+  lnr.load_gamma(a.gamma, H);
   const bool v0 = rm_vec2_ok(a.dQ, H), v1 = rm_vec2_ok(a.dK, H), v2 = rm_vec2_ok(a.dV, H), v3 = rm_vec2_ok(a.x, H),
              v4 = rm_vec2_ok(a.qn, H);
   auto issue = [&](long tile, int st) {
@@ -275,6 +384,7 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
   float vbq = 0.f, vbk = 0.f, vbv = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
   if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
+  else cp_async_commit();
   int it = 0;
   for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
     const int st = it & 1;
@@ -330,7 +440,8 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
       }
     }
     __syncthreads();
-    f_ln_bwd_rows<NW, false>(Gq, X, S, 1, Gk, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dx, dgam, dbet, ofx);
+    lnr.run(Gq, X, Gk, a.mean, a.rstd, rowstat, row0, d, a.dx, ofx);
+    __syncthreads();
     rm_ln_cols_slice<SL, S>(Gq, X, rowstat, dgam, dbet);
   }
   float* P = a.partial + (long)blockIdx.x * (2L * H + 3L * (H * H + H));
@@ -365,8 +476,10 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
   for (int i = t; i < 4 * TILE; i += BT) Gd[i] = 0.f;       // Gd, Dh and the two weight tiles
   rm_zero_pad<8 * KS, S>(sm, 8 * FR, H);                    // K-padding columns of the eight stage tiles
   __syncthreads();
-  rm_load_w<S>(W1s, a.W1, H);
-  rm_load_w<S>(W2s, a.W2, H);
+  rm_load_w_async<S>(W1s, a.W1, H);   // (committed with the first tile's group below, or by the lone commit)
+  rm_load_w_async<S>(W2s, a.W2, H);
+  RmLnRows<S, BT> lnr;
+  lnr.load_gamma(a.gamma, H);
   const bool v0 = rm_vec2_ok(a.dx, H), v1 = rm_vec2_ok(a.zn, H), v2 = rm_vec2_ok(a.h1d, H), v3 = rm_vec2_ok(a.y, H);
   auto issue = [&](long tile, int st) {
     float* b = sm + st * STAGE;
@@ -384,6 +497,15 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
   float vb1 = 0.f, vb2 = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
   if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
+  else cp_async_commit();
+  // row mask of a tile (padding positions and rows past N get 0): fetched one tile ahead by threads 0..FR-1 and handed
+  // over through shared memory (the first FR words of rowstat, free until the LayerNorm pass at the end of the tile)
+  auto row_mask = [&](long tile) -> float {
+    const long row = tile * FR + t;
+    return (t < FR && row < d.N && (!a.ids || a.ids[row] != 0)) ? 1.f : 0.f;
+  };
+  float mcur = (long)blockIdx.x < a.ntiles ? row_mask(blockIdx.x) : 0.f;
+  float* rowm = rowstat;
   int it = 0;
   for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
     const int st = it & 1;
@@ -393,12 +515,16 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
     float* Yr = Hd + TILE;
     const long row0 = tile * FR;
     __syncthreads();
+    float mnext = 0.f;
     if (tile + gridDim.x < a.ntiles) {
+      mnext = row_mask(tile + gridDim.x);
       issue(tile + gridDim.x, st ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
+    if (t < FR) rowm[t] = mcur;
+    mcur = mnext;
     __syncthreads();
     // masked / dropped upstream gradient: one (row, column pair) task per thread and pass, one dropout hash word each
     {
@@ -408,7 +534,7 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
         const int r = p / PW, c = 2 * (p - r * PW);
         const long row = row0 + r;
         const bool ok = row < d.N;
-        const float m = (ok && (!a.ids || a.ids[row] != 0)) ? 1.f : 0.f;
+        const float m = rowm[r];
         float dm2[2];
         drop_mul2(dout, (unsigned long long)(row * H + c), dm2[0], dm2[1]);
         const float g0 = Gm[r * S + c] * m;
@@ -460,7 +586,8 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
     }
     vb1 += rm_colsum_slice<SL, S>(Dh);
     __syncthreads();
-    f_ln_bwd_rows<NW, false>(Gd, Yr, S, 1, nullptr, a.gamma, a.mean, a.rstd, rowstat, row0, d, a.dy, dgam, dbet);
+    lnr.run(Gd, Yr, nullptr, a.mean, a.rstd, rowstat, row0, d, a.dy, ln_out_none());
+    __syncthreads();
     rm_ln_cols_slice<SL, S>(Gd, Yr, rowstat, dgam, dbet);
   }
   float* P = a.partial + (long)blockIdx.x * (2L * H + 2L * (H * H + H));

@@ -32,6 +32,10 @@ for ln in open(sass):
             pend = []
         line_of[int(m.group(1), 16)] = (cur_outer, cur_inner, ln.split("*/", 1)[1].strip()[:60])
 rows = list(csv.reader(open(src_csv)))
+for i in range(2, len(rows)):          # several launches in one export: keep the first
+    if rows[i] and rows[i][0] == "Kernel Name":
+        rows = rows[:i]
+        break
 hdr = rows[1]
 ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
