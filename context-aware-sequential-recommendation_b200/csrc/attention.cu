@@ -29,6 +29,7 @@ int dispatch_att_mma(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, co
                      float* pbuf, float* dbuf, const AttnDims& dm, cudaStream_t stream);
 
 int attn_mma_set_chunk(int nt);
+int attn_mma_set_kg(int kg);
 
 static int dispatch_by_width(int which, const AttnFwdArgs* fa, const AttnBwdArgs* ba, const AttnDims& dm,
                              cudaStream_t stream) {
@@ -52,6 +53,7 @@ extern "C" size_t cast_attn_bwd_workspace_bytes(int B, int T, int h) {
 }
 
 extern "C" int cast_attn_set_chunk(int columns) { return attn_mma_set_chunk(columns / 8); }
+extern "C" int cast_attn_set_kg(int key_groups) { return attn_mma_set_kg(key_groups); }
 
 extern "C" int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const float* V, long ldv,
                              const float* queries, const float* kmask, const float* qmask, int B, int T, int H, int h,

@@ -27,20 +27,37 @@ namespace cast {
 constexpr int AM_THREADS = 128;
 constexpr int AM_T = 64;  // rows per CTA (4 warps x 16)
 
+// first kept key (kmask != 0) and first query (ids != 0; 0 without ids) of the sequence, T when there is none.
+// One pass, one barrier: strided scan (a thread's first hit is its minimum), warp minimum by shuffles, one slot per
+// warp in s2[64] (first keys | first queries), every thread folds the slots.
+constexpr int AM_FIRST_SLOTS = 64;
 __device__ __forceinline__ void am_first2(const float* __restrict__ kmask_b, const int* __restrict__ ids_b, int T,
                                           int* s2, int& first_key, int& qstart) {
-  if (threadIdx.x == 0) { s2[0] = T; s2[1] = ids_b ? T : 0; }
-  __syncthreads();
-  int mk = T, mq = T;
+  int mk = T, mq = ids_b ? T : 0;
   for (int j = threadIdx.x; j < T; j += (int)blockDim.x) {
-    if (mk == T && kmask_b[j] != 0.f) mk = j;
-    if (ids_b && mq == T && ids_b[j] != 0) mq = j;
+    const float kv = kmask_b[j];
+    const int iv = ids_b ? ids_b[j] : 0;
+    if (mk == T && kv != 0.f) mk = j;
+    if (ids_b && mq == T && iv != 0) mq = j;
   }
-  if (mk < T) atomicMin(&s2[0], mk);
-  if (ids_b && mq < T) atomicMin(&s2[1], mq);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ok = __shfl_xor_sync(0xffffffffu, mk, o), oq = __shfl_xor_sync(0xffffffffu, mq, o);
+    mk = ok < mk ? ok : mk;
+    mq = oq < mq ? oq : mq;
+  }
+  const int w = threadIdx.x >> 5, nw = ((int)blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    s2[w] = mk;
+    s2[32 + w] = mq;
+  }
   __syncthreads();
   first_key = s2[0];
-  qstart = s2[1];
+  qstart = s2[32];
+  for (int i = 1; i < nw; ++i) {
+    first_key = s2[i] < first_key ? s2[i] : first_key;
+    qstart = s2[32 + i] < qstart ? s2[32 + i] : qstart;
+  }
 }
 
 // asynchronous tile load: dst[r][c] = src[(row0 + r) * ld + c] for 0 <= row0 + r < T and c < d, zero rows outside the
@@ -165,11 +182,11 @@ __device__ __forceinline__ void am_block(const AttnDims& dm, int& b, int& hh, in
 // staged chunk of 16*NT keys in halves (each keeps its own running max / sum / O), merged through shared memory at the
 // end -- the critical path of the late (long) row tiles halves.
 template <int KS, int NT, int KG>
-__global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4) ? (KG == 1 ? 4 : 2) : 1)
+__global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG <= 2) ? (KG == 1 ? 4 : 2) : 1)
 attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   CAST_DYN_SMEM(float, sm);
-  __shared__ int s_first[2];
+  __shared__ int s_first[AM_FIRST_SLOTS];
   float* Qs = sm;                         // [64][DS]
   float* Kst = Qs + AM_T * DS;            // [2][TC][DS]
   float* Vst = Kst + 2 * TC * DS;         // [2][TC][DS]
@@ -180,10 +197,14 @@ attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
   am_block(dm, b, hh, ntile, tile);
   const int q0 = am_row0(T, ntile, tile, AM_T);
   const long rowbase = (long)b * T;
+  // the query tile starts moving before the scan for the sequence's first key / first query (one round trip, not two)
+  am_load_rows_async<AM_T, DS, NW>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
   int first_key, qstart;
   am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
   const long sbase = ((long)b * dm.h + hh) * T;
   if (q0 + AM_T <= qstart) {  // every row of this tile is padding: output = residual only (block-uniform exit)
+    cp_async_commit();
+    cp_async_wait<0>();
     for (int idx = t; idx < AM_T * d; idx += NTHR) {
       const int i = q0 + idx / d, c = idx % d;
       if (i >= 0) {
@@ -211,18 +232,16 @@ attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
   const bool wuni = (r0 > qstart ? r0 : qstart) < first_key;
   const int wkend = wuni ? T : r0 + 16;
 
-  const float* Qg = a.Q + rowbase * a.ldq + hh * d;
   const float* Kg = a.K + rowbase * a.ldk + hh * d;
   const float* Vg = a.V + rowbase * a.ldv + hh * d;
-  const bool vq = am_vec2_ok(a.Q, a.ldq, d, hh), vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
+  const bool vk = am_vec2_ok(a.K, a.ldk, d, hh), vv = am_vec2_ok(a.V, a.ldv, d, hh);
   auto issue = [&](int j0, int st) {
     am_load_rows_async<TC, DS, NW>(Kst + st * TC * DS, Kg, a.ldk, j0, T, d, vk);
     am_load_rows_async<TC, DS, NW>(Vst + st * TC * DS, Vg, a.ldv, j0, T, d, vv);
     if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
     cp_async_commit();
   };
-  am_load_rows_async<AM_T, DS, NW>(Qs, Qg, a.ldq, q0, T, d, vq);
-  issue(kbeg, 0);
+  issue(kbeg, 0);   // (the query tile issued above rides in this first group)
   am_zero_pad<DP, DS>(sm, AM_T + 4 * TC, d);
 
   const Drop dr = make_drop(a.rate, a.seed, a.step, a.site);
@@ -240,13 +259,15 @@ attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
   const float* Rg = a.resid + rowbase * dm.H + hh * d;
   const bool vr = am_vec2_ok(a.resid, dm.H, d, hh);
   const int rst = nch & 1;  // stage not used by the last chunk
+  // KG > 2: the group merge below needs both K stages, so the residual tile goes to the free V stage
+  float* resS = (KG > 2 ? Vst : Kst) + rst * TC * DS;
   for (int ci = 0; ci < nch; ++ci) {
     const int j0s = kbeg + ci * TC, st = ci & 1;
-    const int j0 = j0s + kg * TW;  // this warp's half of the staged chunk
+    const int j0 = j0s + kg * TW;  // this warp's part of the staged chunk
     if (ci + 1 < nch) {
       issue(j0s + TC, st ^ 1);
     } else {
-      am_load_rows_async<TC, DS, NW>(Kst + rst * TC * DS, Rg, dm.H, q0, T, d, vr);
+      am_load_rows_async<(TC < AM_T ? TC : AM_T), DS, NW>(resS, Rg, dm.H, q0, T, d, vr);
       if (TC < AM_T) am_load_rows_async<TC, DS, NW>(Vst + rst * TC * DS, Rg, dm.H, q0 + TC, T, d, vr);
       cp_async_commit();
     }
@@ -318,34 +339,41 @@ attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
   __syncthreads();
   lA = quad_sum(lA);
   lB = quad_sum(lB);
-  if (KG == 2) {  // fold the second key group's (max, sum, O) into the first through the stage the last chunk used
-    float* mo = Kst + ((nch - 1) & 1) * TC * DS;  // [128 threads][4 * NTO]
-    float* ml = Vst + ((nch - 1) & 1) * TC * DS;  // [128 threads][4]
+  if (KG > 1) {  // fold the other key groups' (max, sum, O) into the first, in group order, through free stages
+    // KG == 2: the K / V stage the last chunk used; KG > 2: both K stages / the V stage the last chunk used
+    float* mo = KG > 2 ? Kst : Kst + ((nch - 1) & 1) * TC * DS;  // [KG - 1][128 threads][4 * NTO]
+    float* ml = Vst + ((nch - 1) & 1) * TC * DS;                  // [KG - 1][128 threads][4]
+    static_assert((KG - 1) * 128 * 4 * NTO <= (KG > 2 ? 2 : 1) * TC * DS && (KG - 1) * 128 * 4 <= TC * DS, "merge space");
     const int slot = warp * 32 + lane;
-    if (kg == 1) {
+    if (kg > 0) {
+      float* mog = mo + (kg - 1) * 128 * 4 * NTO;
 #pragma unroll
       for (int no = 0; no < NTO; ++no)
-        *reinterpret_cast<float4*>(mo + (slot * NTO + no) * 4) = make_float4(o[no][0], o[no][1], o[no][2], o[no][3]);
-      *reinterpret_cast<float4*>(ml + slot * 4) = make_float4(mA, mB, lA, lB);
+        *reinterpret_cast<float4*>(mog + (slot * NTO + no) * 4) = make_float4(o[no][0], o[no][1], o[no][2], o[no][3]);
+      *reinterpret_cast<float4*>(ml + ((kg - 1) * 128 + slot) * 4) = make_float4(mA, mB, lA, lB);
     }
     __syncthreads();
-    if (kg == 1) return;
-    const float4 st1 = *reinterpret_cast<const float4*>(ml + slot * 4);
-    const float nmA = fmaxf(mA, st1.x), nmB = fmaxf(mB, st1.y);
-    // a group that saw no chunk has max = -inf, sum = 0: its factor is exp(-inf) = 0 (nm is finite for live rows)
-    const float a0A = nmA == -INFINITY ? 0.f : __expf(mA - nmA), a1A = nmA == -INFINITY ? 0.f : __expf(st1.x - nmA);
-    const float a0B = nmB == -INFINITY ? 0.f : __expf(mB - nmB), a1B = nmB == -INFINITY ? 0.f : __expf(st1.y - nmB);
-    lA = lA * a0A + st1.z * a1A;
-    lB = lB * a0B + st1.w * a1B;
-    mA = nmA;
-    mB = nmB;
+    if (kg > 0) return;
 #pragma unroll
-    for (int no = 0; no < NTO; ++no) {
-      const float4 o1 = *reinterpret_cast<const float4*>(mo + (slot * NTO + no) * 4);
-      o[no][0] = o[no][0] * a0A + o1.x * a1A;
-      o[no][1] = o[no][1] * a0A + o1.y * a1A;
-      o[no][2] = o[no][2] * a0B + o1.z * a1B;
-      o[no][3] = o[no][3] * a0B + o1.w * a1B;
+    for (int gi = 1; gi < KG; ++gi) {
+      const float* mog = mo + (gi - 1) * 128 * 4 * NTO;
+      const float4 st1 = *reinterpret_cast<const float4*>(ml + ((gi - 1) * 128 + slot) * 4);
+      const float nmA = fmaxf(mA, st1.x), nmB = fmaxf(mB, st1.y);
+      // a group that saw no chunk has max = -inf, sum = 0: its factor is exp(-inf) = 0 (nm is finite for live rows)
+      const float a0A = nmA == -INFINITY ? 0.f : __expf(mA - nmA), a1A = nmA == -INFINITY ? 0.f : __expf(st1.x - nmA);
+      const float a0B = nmB == -INFINITY ? 0.f : __expf(mB - nmB), a1B = nmB == -INFINITY ? 0.f : __expf(st1.y - nmB);
+      lA = lA * a0A + st1.z * a1A;
+      lB = lB * a0B + st1.w * a1B;
+      mA = nmA;
+      mB = nmB;
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) {
+        const float4 o1 = *reinterpret_cast<const float4*>(mog + (slot * NTO + no) * 4);
+        o[no][0] = o[no][0] * a0A + o1.x * a1A;
+        o[no][1] = o[no][1] * a0A + o1.y * a1A;
+        o[no][2] = o[no][2] * a0B + o1.z * a1B;
+        o[no][3] = o[no][3] * a0B + o1.w * a1B;
+      }
     }
   }
 #pragma unroll
@@ -353,7 +381,7 @@ attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
     const int i = half ? iB : iA;
     if (i < 0) continue;
     const int rr = warp * 16 + g + half * 8;
-    const float* rrow = (rr < TC ? Kst + rst * TC * DS + rr * DS : Vst + rst * TC * DS + (rr - TC) * DS);
+    const float* rrow = (rr < TC ? resS + rr * DS : Vst + rst * TC * DS + (rr - TC) * DS);
     const bool live = wact && i >= qstart;
     const float l = half ? lB : lA, m = half ? mB : mA;
     const float linv = live ? 1.0f / l : 0.f;
@@ -395,7 +423,7 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
-  __shared__ int s_first[2];
+  __shared__ int s_first[AM_FIRST_SLOTS];
   float* Qs = sm;                   // [64][DS]
   float* dOs = Qs + AM_T * DS;      // [64][DS]
   float* Kst = dOs + AM_T * DS;     // [2][TC][DS]
@@ -409,9 +437,25 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   const int q0 = am_row0(T, ntile, tile, AM_T);
   const long rowbase = (long)b * T;
   const long sbase = ((long)b * dm.h + hh) * T;
+  // The tile's own rows (Q, dO and, for D_i, out and queries — parked in the second K/V stage, which the chunk loop
+  // does not touch before its first iteration) start moving before anything is known about the sequence: the scan for
+  // its first key / first query below then costs no extra round trip.
+  am_load_rows_async<AM_T, DS, NW>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
+  am_load_rows_async<AM_T, DS, NW>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
+  constexpr bool PARK = TC >= AM_T;   // a K/V stage holds a whole row tile (the 8-warp configuration)
+  float* outS = Kst + TC * DS;
+  float* resS = Vst + TC * DS;
+  if (PARK) {
+    am_load_rows_async<AM_T, DS, NW>(outS, aa.out + rowbase * dm.H + hh * d, dm.H, q0, T, d,
+                                     am_vec2_ok(aa.out, dm.H, d, hh));
+    am_load_rows_async<AM_T, DS, NW>(resS, aa.resid + rowbase * dm.H + hh * d, dm.H, q0, T, d,
+                                     am_vec2_ok(aa.resid, dm.H, d, hh));
+  }
+  cp_async_commit();
   int first_key, qstart;
   am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
   if (q0 + AM_T <= qstart) {  // padding-only tile: zero gradient
+    cp_async_wait<0>();
     for (int idx = t; idx < AM_T * d; idx += NTHR) {
       const int i = q0 + idx / d, c = idx % d;
       if (i >= 0) a.dQ[(rowbase + i) * a.lddq + hh * d + c] = 0.f;
@@ -442,37 +486,38 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
     if (t < TC) cp_async<4>(kms + st * TC + t, a.kmask + rowbase + (j0 + t < T ? j0 + t : 0), j0 + t < T);
     cp_async_commit();
   };
-  am_load_rows_async<AM_T, DS, NW>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
-  am_load_rows_async<AM_T, DS, NW>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
   if (nch > 0) issue(kbeg, 0); else cp_async_commit();
   am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
-  // D_i = dO_i . (out_i - queries_i) over this head's columns: one warp per row
-  {  // all of a warp's rows at once: the (up to) 6 loads per row are independent and stay in flight together
+  cp_async_wait<1>();   // the tile's rows have landed (the first chunk may still be in flight)
+  __syncthreads();
+  // D_i = dO_i . (out_i - queries_i) over this head's columns, from the staged rows: one warp per row
+  {
     constexpr int RW = AM_T / NW;
-    float acc[RW];
-#pragma unroll
-    for (int k = 0; k < RW; ++k) {
-      const int i = q0 + wid + k * NW;
-      acc[k] = 0.f;
-      if (i >= qstart && i >= 0) {
-        const long off = (rowbase + i) * dm.H + hh * d;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = lane + 32 * u;
-          if (c < d) acc[k] = fmaf(a.dO[off + c], aa.out[off + c] - aa.resid[off + c], acc[k]);
-        }
-      }
-    }
 #pragma unroll
     for (int k = 0; k < RW; ++k) {
       const int r = wid + k * NW, i = q0 + r;
-      const float v = warp_sum(acc[k]);
+      float acc = 0.f;
+      if (i >= qstart && i >= 0) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = lane + 32 * u;
+          if (c >= d) continue;
+          if (PARK) {
+            acc = fmaf(dOs[r * DS + c], outS[r * DS + c] - resS[r * DS + c], acc);
+          } else {
+            const long off = (rowbase + i) * dm.H + hh * d + c;
+            acc = fmaf(dOs[r * DS + c], aa.out[off] - aa.resid[off], acc);
+          }
+        }
+      }
+      const float v = warp_sum(acc);
       if (lane == 0) {
         Dsm[r] = v;
         if (i >= 0) a.rowD[sbase + i] = v;
       }
     }
   }
+  __syncthreads();      // Dsm is complete; the parked tiles may be overwritten by the second chunk
   const Drop dr = make_drop(a.rate, a.seed, a.step, a.site);
   const unsigned long long ibA = ((unsigned long long)((long)hh * dm.B + b) * T + (unsigned long long)(long)iA) * T;
   const unsigned long long ibB = ibA + 8ull * T;
@@ -563,21 +608,27 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
     __syncthreads();
   }
   cp_async_wait<0>();
-  if (KG == 2) {  // dQ = sum of the two key groups' partial products
+  if (KG > 1) {  // dQ = sum of the key groups' partial products, in group order
     __syncthreads();
-    float* mo = Kst;  // [128 threads][4 * NTO]
+    float* mo = Kst;  // [KG - 1][128 threads][4 * NTO] (both K stages are free now)
+    static_assert((KG - 1) * 128 * 4 * NTO <= 2 * TC * DS, "merge space");
     const int slot = warp * 32 + lane;
-    if (kg == 1) {
+    if (kg > 0) {
+      float* mog = mo + (kg - 1) * 128 * 4 * NTO;
 #pragma unroll
       for (int no = 0; no < NTO; ++no)
-        *reinterpret_cast<float4*>(mo + (slot * NTO + no) * 4) = make_float4(o[no][0], o[no][1], o[no][2], o[no][3]);
+        *reinterpret_cast<float4*>(mog + (slot * NTO + no) * 4) = make_float4(o[no][0], o[no][1], o[no][2], o[no][3]);
     }
     __syncthreads();
-    if (kg == 1) return;
+    if (kg > 0) return;
 #pragma unroll
-    for (int no = 0; no < NTO; ++no) {
-      const float4 o1 = *reinterpret_cast<const float4*>(mo + (slot * NTO + no) * 4);
-      o[no][0] += o1.x; o[no][1] += o1.y; o[no][2] += o1.z; o[no][3] += o1.w;
+    for (int gi = 1; gi < KG; ++gi) {
+      const float* mog = mo + (gi - 1) * 128 * 4 * NTO;
+#pragma unroll
+      for (int no = 0; no < NTO; ++no) {
+        const float4 o1 = *reinterpret_cast<const float4*>(mog + (slot * NTO + no) * 4);
+        o[no][0] += o1.x; o[no][1] += o1.y; o[no][2] += o1.z; o[no][3] += o1.w;
+      }
     }
   }
 #pragma unroll
@@ -608,7 +659,7 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
-  __shared__ int s_first[2];
+  __shared__ int s_first[AM_FIRST_SLOTS];
   float* Ks = sm;                    // [64][DS]
   float* Vs = Ks + AM_T * DS;        // [64][DS]
   float* Qst = Vs + AM_T * DS;       // [2][TC][DS]
@@ -801,7 +852,7 @@ __global__ void __launch_bounds__(AW_THREADS, 2) attn_bwd_dkv_ws_kernel(AttnBwdM
   constexpr int DP = 8 * KS, NTO = KS, TQ = AW_TQ, PS = AW_PS, NW = AW_THREADS / 32;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
-  __shared__ int s_first[2];
+  __shared__ int s_first[AM_FIRST_SLOTS];
   float* Pst = sm;                     // [2][TQ][PS]  P~ rows of the chunk's queries, columns = this tile's keys
   float* Dst = Pst + 2 * TQ * PS;      // [2][TQ][PS]  dS
   float* Qst = Dst + 2 * TQ * PS;      // [2][TQ][PS]  Q  (row stride PS: conflict-free [k][n] fragment loads)
@@ -1001,6 +1052,8 @@ __global__ void __launch_bounds__(AW_THREADS, 2) attn_bwd_dkv_ws_kernel(AttnBwdM
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
+static int g_attn_kg = 2;   // key groups per row block in the 8 x NT = 32 configuration (A/B hook: cast_attn_set_kg)
+
 template <int KS, int NT>
 static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba, const AttnDims& dm,
                       cudaStream_t stream) {
@@ -1010,6 +1063,18 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
   const dim3 grid((unsigned)(dm.B * dm.h), (unsigned)ntile);
   const size_t row = sizeof(float) * DS;
   if (which == 0) {
+    if (NT == 4 && g_attn_kg == 4) {  // 16 warps, one CTA per SM: four key groups per row block
+      constexpr int KG4 = (NT == 4) ? 4 : 1, TC4 = TC * KG4;
+      static size_t cfg4 = 48 * 1024;
+      const size_t smem = (AM_T + 4 * TC4) * row + sizeof(float) * 2 * TC4;
+      auto kf = attn_fwd_mma_kernel<KS, NT, KG4>;
+      if (smem > cfg4) {
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cfg4 = smem;
+      }
+      CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KG4), smem, stream, *fa, dm);
+      return CAST_OK;
+    }
     constexpr int KGF = (NT == 4) ? 2 : 1;  // 8 warps: two key groups per row block
     constexpr int TCF = TC * KGF;
     const size_t smem = (AM_T + 4 * TCF) * row + sizeof(float) * 2 * TCF;
@@ -1020,6 +1085,18 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
     }
     CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGF), smem, stream, *fa, dm);
   } else if (which == 1) {
+    if (NT == 4 && g_attn_kg == 4 && ba->pbuf) {
+      constexpr int KG4 = (NT == 4) ? 4 : 1, TC4 = TC * KG4;
+      static size_t cfg4 = 48 * 1024;
+      const size_t smem = (2 * AM_T + 4 * TC4) * row + sizeof(float) * (2 * TC4 + AM_T);
+      auto kf = attn_bwd_dq_mma_kernel<KS, NT, KG4, true>;
+      if (smem > cfg4) {
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cfg4 = smem;
+      }
+      CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KG4), smem, stream, *ba, dm);
+      return CAST_OK;
+    }
     constexpr int KGB = (NT == 4) ? 2 : 1;
     constexpr int TCB = TC * KGB;
     const size_t smem = (2 * AM_T + 4 * TCB) * row + sizeof(float) * (2 * TCB + AM_T);
@@ -1065,6 +1142,12 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
 }
 
 bool attn_mma_supported(const AttnDims& dm) { return dm.d >= 1 && dm.d <= 64 && (long)dm.B * dm.h < 2147483647L; }
+
+int attn_mma_set_kg(int kg) {
+  if (kg != 2 && kg != 4) return set_error(CAST_ERR_BAD_ARG, "attention (mma): key groups must be 2 or 4");
+  g_attn_kg = kg;
+  return CAST_OK;
+}
 
 static int g_chunk_tiles = 4;  // columns per streamed chunk / 8 (4 or 8); cast_attn_set_chunk (tuning hook)
 int attn_mma_set_chunk(int nt) {

@@ -245,6 +245,9 @@ int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const floa
                   float* attn_weights, float* row_max, float* row_linv, void* stream);
 /* Tuning hook: columns per streamed chunk of the tensor-core attention kernels (32 or 64; default 32). */
 int cast_attn_set_chunk(int columns);
+/* Tuning hook: warps that share one 16-row block of a 64-row attention tile, each taking a 32-key slice of every
+ * streamed chunk (forward and dQ kernels): 2 = 8 warps, two CTAs per SM (default); 4 = 16 warps, one CTA per SM. */
+int cast_attn_set_kg(int key_groups);
 /* Gradient of the attention output (without the residual branch) w.r.t. Q, K, V.  rowD: scratch [B,h,T].
  * out / queries (optional, both or neither): the forward call's `out` and `queries`; with them (and d = H/h <= 64)
  * the tensor-core kernels run and D_i = sum_j P_ij dP_ij is taken as dO_i . (out_i - queries_i).
