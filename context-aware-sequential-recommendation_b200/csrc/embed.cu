@@ -6,27 +6,80 @@
 
 namespace cast {
 
+// A warp walks rows (grid-stride); lane l owns the column pairs 2l, 2l + 64, ... of each: 8-byte loads / stores when H
+// is even and the rows are 8-byte aligned, one dropout hash word per pair, and the per-thread setup (dropout key) is
+// paid once per EMB_ROWS_PER_WARP rows instead of once per two elements.
+constexpr int EMB_ROWS_PER_WARP = 4;
 __global__ void embed_fwd_kernel(const int* __restrict__ ids, TableRef table, int V, int H, long N,
                                  int T, float scale, const float* __restrict__ pos, const float* __restrict__ add,
                                  float rate, unsigned long long seed, const unsigned long long* step, int site,
                                  const int* __restrict__ mask_ids, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= N) return;
-  const int id = ids[row];
-  const bool live = (id > 0) && (id < V);  // row 0 is the zero pad (modules.py:154-156)
-  const float m = mask_ids ? (mask_ids[row] != 0 ? 1.f : 0.f) : 1.f;
+  const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const Drop d = make_drop(rate, seed, step, site);
-  const float* trow = table.row(live ? id : 0, H);
-  const float* prow = pos ? pos + (long)(row % T) * H : nullptr;
-  const float* arow = add ? add + row * H : nullptr;
-  for (int c = lane; c < H; c += 32) {
-    float v = live ? trow[c] * scale : 0.f;
-    if (prow) v += prow[c];
-    if (arow) v += arow[c];
-    v *= drop_mul(d, (unsigned long long)(row * H + c));
-    v *= m;
-    out[row * H + c] = v;
+  const bool heven = (H & 1) == 0;
+  const bool vio = heven && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(pos) |
+                              reinterpret_cast<uintptr_t>(add)) & 7) == 0;
+#pragma unroll
+  for (int k = 0; k < EMB_ROWS_PER_WARP; ++k) {
+    const long row = warp * EMB_ROWS_PER_WARP + k;
+    if (row >= N) return;
+    const int id = ids[row];
+    const bool live = (id > 0) && (id < V);  // row 0 is the zero pad (modules.py:154-156)
+    const float m = mask_ids ? (mask_ids[row] != 0 ? 1.f : 0.f) : 1.f;
+    const float* trow = table.row(live ? id : 0, H);
+    const float* prow = pos ? pos + (long)(row % T) * H : nullptr;
+    const float* arow = add ? add + row * H : nullptr;
+    const bool vt = vio && (reinterpret_cast<uintptr_t>(trow) & 7) == 0;
+    for (int c = 2 * lane; c < H; c += 64) {
+      const bool two = c + 1 < H;
+      float v0 = 0.f, v1 = 0.f;
+      if (live) {
+        if (vt) {
+          const float2 tv = *reinterpret_cast<const float2*>(trow + c);
+          v0 = tv.x * scale;
+          v1 = tv.y * scale;
+        } else {
+          v0 = trow[c] * scale;
+          if (two) v1 = trow[c + 1] * scale;
+        }
+      }
+      if (prow) {
+        if (vio) {
+          const float2 pv = *reinterpret_cast<const float2*>(prow + c);
+          v0 += pv.x;
+          v1 += pv.y;
+        } else {
+          v0 += prow[c];
+          if (two) v1 += prow[c + 1];
+        }
+      }
+      if (arow) {
+        if (vio) {
+          const float2 av = *reinterpret_cast<const float2*>(arow + c);
+          v0 += av.x;
+          v1 += av.y;
+        } else {
+          v0 += arow[c];
+          if (two) v1 += arow[c + 1];
+        }
+      }
+      const unsigned long long idx = (unsigned long long)(row * H + c);
+      float m0, m1;
+      if ((idx & 1ull) == 0ull) {
+        drop_mul2_even(d, idx, m0, m1);
+      } else {
+        drop_mul2(d, idx, m0, m1);
+      }
+      v0 = v0 * m0 * m;
+      v1 = v1 * m1 * m;
+      if (vio) {
+        *reinterpret_cast<float2*>(out + row * H + c) = make_float2(v0, v1);
+      } else {
+        out[row * H + c] = v0;
+        if (two) out[row * H + c + 1] = v1;
+      }
+    }
   }
 }
 
@@ -127,8 +180,8 @@ extern "C" int cast_embed_fwd(const int* ids, const float* table, int V, int H, 
   if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "embed_fwd: drop_rate");
   if (N == 0) return CAST_OK;
   const int wpb = 8;
-  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, ids,
-              table_ref(table), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
+  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb * EMB_ROWS_PER_WARP)), dim3(32 * wpb), 0,
+              (cudaStream_t)stream, ids, table_ref(table), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
   return check_launch("embed_fwd");
 }
 
@@ -141,8 +194,8 @@ extern "C" int cast_embed_fwd_sharded(const int* ids, const float* const* shards
   if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "embed_fwd_sharded: drop_rate");
   if (N == 0) return CAST_OK;
   const int wpb = 8;
-  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb)), dim3(32 * wpb), 0, (cudaStream_t)stream, ids,
-              table_ref(shards, nshards), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
+  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb * EMB_ROWS_PER_WARP)), dim3(32 * wpb), 0,
+              (cudaStream_t)stream, ids, table_ref(shards, nshards), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
   return check_launch("embed_fwd_sharded");
 }
 

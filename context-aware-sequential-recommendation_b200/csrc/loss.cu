@@ -83,49 +83,119 @@ __global__ void loss_final_kernel(const float* __restrict__ partial, int nparts,
 }
 
 // Training tail in one pass (H <= 64): final LayerNorm of the main tower (modules.py:53-80) -> pos/neg logits, BCE, AUC
-// (sasrec.py:87-115) -> d(seq_emb) -> LayerNorm backward.  A warp owns a row end to end (lanes own columns c, c+32), so
-// the normalised row, its gradient and the LN-backward row sums never leave registers; per-CTA partials of the loss
-// sums and of dgamma / dbeta are left for the step's batched reduction.
-__global__ void __launch_bounds__(32 * LOSS_WARPS)
+// (sasrec.py:87-115) -> d(seq_emb) -> LayerNorm backward.  Eight threads own a row end to end (thread `sub` holds the
+// column pairs (j * 8 + sub) * 2, j < 4: a row's threads read 64 contiguous bytes per request), so the normalised row,
+// its gradient and the LN-backward row sums never leave registers and the six row sums are 3-step shuffles over 8 lanes;
+// a warp works on four rows at once.  Per-CTA partials of the loss sums and of dgamma / dbeta (fixed order over the
+// CTA's 32 row slots) are left for the step's batched reduction.
+constexpr int LNF_TPR = 8, LNF_NJ = 4, LNF_THREADS = 256, LNF_SLOTS = LNF_THREADS / LNF_TPR;
+__device__ __forceinline__ float sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+// the pair (p[c], p[c + 1]) with c even; elements at or past H (or a dead row) read as 0
+__device__ __forceinline__ void lnf_ld2(const float* __restrict__ p, int c, int H, bool on, bool vec, float& a, float& b) {
+  a = b = 0.f;
+  if (!on || c >= H) return;
+  if (vec) {   // H even => c + 1 < H
+    const float2 v = *reinterpret_cast<const float2*>(p + c);
+    a = v.x;
+    b = v.y;
+  } else {
+    a = p[c];
+    if (c + 1 < H) b = p[c + 1];
+  }
+}
+__device__ __forceinline__ void lnf_st2(float* __restrict__ p, int c, int H, bool vec, float a, float b) {
+  if (c >= H) return;
+  if (vec) {
+    *reinterpret_cast<float2*>(p + c) = make_float2(a, b);
+  } else {
+    p[c] = a;
+    if (c + 1 < H) p[c + 1] = b;
+  }
+}
+
+__global__ void __launch_bounds__(LNF_THREADS)
 lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 TableRef table, int V, int H, long N, const int* __restrict__ pos,
                 const int* __restrict__ neg, float* __restrict__ seq, float* __restrict__ pos_logits,
                 float* __restrict__ neg_logits, float* __restrict__ gpos, float* __restrict__ gneg,
                 float* __restrict__ dx, float* __restrict__ partial_loss, float* __restrict__ partial_ln) {
-  __shared__ float red[LOSS_WARPS][3];
-  __shared__ float redg[LOSS_WARPS][2][64];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float red[LNF_SLOTS][3];
+  __shared__ float redg[LNF_SLOTS][2][64];
+  const int t = threadIdx.x, slot = t / LNF_TPR, sub = t % LNF_TPR;
   const long row0 = (long)blockIdx.x * LOSS_ROWS_PER_CTA;
-  const int c0 = lane, c1 = lane + 32;
-  const bool h0 = c0 < H, h1 = c1 < H;
-  const float g0 = h0 ? gamma[c0] : 0.f, g1 = h1 ? gamma[c1] : 0.f;
-  const float b0 = h0 ? beta[c0] : 0.f, b1 = h1 ? beta[c1] : 0.f;
+  const bool heven = (H & 1) == 0;
+  const bool vx = heven && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(seq) |
+                             reinterpret_cast<uintptr_t>(dx)) & 7) == 0;
+  float gam[LNF_NJ][2], bet[LNF_NJ][2];
+#pragma unroll
+  for (int j = 0; j < LNF_NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = (j * LNF_TPR + sub) * 2 + e;
+      gam[j][e] = c < H ? gamma[c] : 0.f;
+      bet[j][e] = c < H ? beta[c] : 0.f;
+    }
   float s_loss = 0.f, s_auc = 0.f, s_cnt = 0.f;
-  float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
-  for (int r = warp; r < LOSS_ROWS_PER_CTA; r += LOSS_WARPS) {
+  float dg[LNF_NJ][2], db[LNF_NJ][2];
+#pragma unroll
+  for (int j = 0; j < LNF_NJ; ++j) dg[j][0] = dg[j][1] = db[j][0] = db[j][1] = 0.f;
+  const float invH = 1.0f / (float)H;
+  for (int r = slot; r < LOSS_ROWS_PER_CTA; r += LNF_SLOTS) {   // (no early exit: the shuffles need every lane)
     const long n = row0 + r;
-    if (n >= N) break;
-    const int pi = pos[n], ni = neg[n];
+    const bool on = n < N;
+    const long nn = on ? n : 0;
+    const int pi = on ? pos[nn] : 0, ni = on ? neg[nn] : 0;
     const bool pl = pi > 0 && pi < V, nl = ni > 0 && ni < V;
     const float* prow = table.row(pl ? pi : 0, H);
     const float* nrow = table.row(nl ? ni : 0, H);
-    const float* xr = x + n * H;
-    const float v0 = h0 ? xr[c0] : 0.f, v1 = h1 ? xr[c1] : 0.f;
-    const float p0 = (pl && h0) ? prow[c0] : 0.f, p1 = (pl && h1) ? prow[c1] : 0.f;
-    const float q0 = (nl && h0) ? nrow[c0] : 0.f, q1 = (nl && h1) ? nrow[c1] : 0.f;
+    const bool vt = heven && ((reinterpret_cast<uintptr_t>(prow) | reinterpret_cast<uintptr_t>(nrow)) & 7) == 0;
+    const float* xr = x + nn * H;
+    float v[LNF_NJ][2], p[LNF_NJ][2], q[LNF_NJ][2];
+#pragma unroll
+    for (int j = 0; j < LNF_NJ; ++j) {
+      const int c = (j * LNF_TPR + sub) * 2;
+      lnf_ld2(xr, c, H, on, vx, v[j][0], v[j][1]);
+      lnf_ld2(prow, c, H, pl, vt, p[j][0], p[j][1]);
+      lnf_ld2(nrow, c, H, nl, vt, q[j][0], q[j][1]);
+    }
     // ---- LayerNorm (biased variance, eps inside the sqrt)
-    const float mean = warp_sum(v0 + v1) / (float)H;
-    const float d0 = h0 ? v0 - mean : 0.f, d1 = h1 ? v1 - mean : 0.f;
-    const float var = warp_sum(d0 * d0 + d1 * d1) / (float)H;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < LNF_NJ; ++j) acc += v[j][0] + v[j][1];
+    const float mean = sum8(acc) * invH;
+    float xh[LNF_NJ][2], y[LNF_NJ][2];
+    acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < LNF_NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = (j * LNF_TPR + sub) * 2 + e;
+        xh[j][e] = c < H ? v[j][e] - mean : 0.f;
+        acc = fmaf(xh[j][e], xh[j][e], acc);
+      }
+    const float var = sum8(acc) * invH;
     const float stdv = sqrtf(var + eps);
     const float rs = 1.0f / stdv;
-    const float xh0 = d0 * rs, xh1 = d1 * rs;
-    const float y0 = h0 ? g0 * xh0 + b0 : 0.f, y1 = h1 ? g1 * xh1 + b1 : 0.f;
-    if (h0) seq[n * H + c0] = y0;
-    if (h1) seq[n * H + c1] = y1;
+    float adp = 0.f, adn = 0.f;
+#pragma unroll
+    for (int j = 0; j < LNF_NJ; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = (j * LNF_TPR + sub) * 2 + e;
+        xh[j][e] *= rs;
+        y[j][e] = c < H ? fmaf(gam[j][e], xh[j][e], bet[j][e]) : 0.f;
+        adp = fmaf(p[j][e], y[j][e], adp);
+        adn = fmaf(q[j][e], y[j][e], adn);
+      }
+      if (on) lnf_st2(seq + nn * H, (j * LNF_TPR + sub) * 2, H, vx, y[j][0], y[j][1]);
+    }
     // ---- logits, loss terms, logit gradients (same expressions as logits_loss_kernel)
-    const float dp = warp_sum(fmaf(p1, y1, p0 * y0));
-    const float dn = warp_sum(fmaf(q1, y1, q0 * y0));
+    const float dp = sum8(adp), dn = sum8(adn);
     const float ist = pi != 0 ? 1.f : 0.f;
     const float sp = 1.0f / (1.0f + expf(-dp));
     const float sn = 1.0f / (1.0f + expf(-dn));
@@ -134,7 +204,7 @@ lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
     const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
     const float gp = -ist * sp * (1.0f - sp) / (sp + 1e-24f);
     const float gn = ist * sn * (1.0f - sn) / (1.0f - sn + 1e-24f);
-    if (lane == 0) {
+    if (sub == 0 && on) {
       if (pos_logits) pos_logits[n] = dp;
       if (neg_logits) neg_logits[n] = dn;
       gpos[n] = gp;
@@ -144,37 +214,56 @@ lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
       s_cnt += ist;
     }
     // ---- d(seq_emb) and LayerNorm backward of the row
-    const float e0 = fmaf(gn, q0, gp * p0), e1 = fmaf(gn, q1, gp * p1);
-    const float a0 = e0 * g0, a1 = e1 * g1;
-    const float s1 = warp_sum(a0 + a1) / (float)H;
-    const float s2 = warp_sum(a0 * xh0 + a1 * xh1) / (float)H;
-    if (h0) dx[n * H + c0] = rs * (a0 - s1 - xh0 * s2);
-    if (h1) dx[n * H + c1] = rs * (a1 - s1 - xh1 * s2);
-    dg0 = fmaf(e0, xh0, dg0);
-    dg1 = fmaf(e1, xh1, dg1);
-    db0 += e0;
-    db1 += e1;
+    float ev[LNF_NJ][2], av[LNF_NJ][2];
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LNF_NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        ev[j][e] = fmaf(gn, q[j][e], gp * p[j][e]);
+        av[j][e] = ev[j][e] * gam[j][e];
+        a1 += av[j][e];
+        a2 = fmaf(av[j][e], xh[j][e], a2);
+      }
+    const float s1 = sum8(a1) * invH, s2 = sum8(a2) * invH;
+#pragma unroll
+    for (int j = 0; j < LNF_NJ; ++j) {
+      if (on)
+        lnf_st2(dx + nn * H, (j * LNF_TPR + sub) * 2, H, vx, rs * (av[j][0] - s1 - xh[j][0] * s2),
+                rs * (av[j][1] - s1 - xh[j][1] * s2));
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (on) {
+          dg[j][e] = fmaf(ev[j][e], xh[j][e], dg[j][e]);
+          db[j][e] += ev[j][e];
+        }
+      }
+    }
   }
-  if (lane == 0) {
-    red[warp][0] = s_loss;
-    red[warp][1] = s_auc;
-    red[warp][2] = s_cnt;
+  if (sub == 0) {
+    red[slot][0] = s_loss;
+    red[slot][1] = s_auc;
+    red[slot][2] = s_cnt;
   }
-  redg[warp][0][c0] = dg0;
-  redg[warp][0][c1] = dg1;
-  redg[warp][1][c0] = db0;
-  redg[warp][1][c1] = db1;
+#pragma unroll
+  for (int j = 0; j < LNF_NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = (j * LNF_TPR + sub) * 2 + e;
+      redg[slot][0][c] = dg[j][e];
+      redg[slot][1][c] = db[j][e];
+    }
   __syncthreads();
   if (threadIdx.x < 3) {
     float s = 0.f;
-    for (int w = 0; w < LOSS_WARPS; ++w) s += red[w][threadIdx.x];
+    for (int w = 0; w < LNF_SLOTS; ++w) s += red[w][threadIdx.x];
     partial_loss[(long)blockIdx.x * 3 + threadIdx.x] = s;
   }
-  if (threadIdx.x < 128) {  // fixed-order fold over the warps: threads 0..63 -> dgamma[c], 64..127 -> dbeta[c]
+  if (threadIdx.x < 128) {  // fixed-order fold over the row slots: threads 0..63 -> dgamma[c], 64..127 -> dbeta[c]
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
     if (c < H) {
       float s = 0.f;
-      for (int w = 0; w < LOSS_WARPS; ++w) s += redg[w][which][c];
+      for (int w = 0; w < LNF_SLOTS; ++w) s += redg[w][which][c];
       partial_ln[(long)blockIdx.x * 2 * H + which * H + c] = s;
     }
   }
@@ -200,7 +289,7 @@ extern "C" int cast_lnf_loss(const float* x, const float* gamma, const float* be
     return set_error(CAST_ERR_WORKSPACE, "lnf_loss: workspace too small");
   const int ncta = (int)cdiv(N, LOSS_ROWS_PER_CTA);
   float* pl = static_cast<float*>(workspace);
-  CAST_LAUNCH(lnf_loss_kernel, dim3(ncta), dim3(32 * LOSS_WARPS), 0, (cudaStream_t)stream, x, gamma, beta, eps,
+  CAST_LAUNCH(lnf_loss_kernel, dim3(ncta), dim3(LNF_THREADS), 0, (cudaStream_t)stream, x, gamma, beta, eps,
               table_ref(table), V, H, N, pos, neg, seq_emb, pos_logits, neg_logits, gpos, gneg, dx, pl, pl + (size_t)ncta * 3);
   return check_launch("lnf_loss");
 }
