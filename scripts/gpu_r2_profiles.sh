@@ -14,7 +14,7 @@ $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 500 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"ru_ln|attn_|qkv_bwd|ffn_bwd|segment_" -s 36 -c 14 -o gpurun_out/${TAG}_prof -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"ru_ln|attn_|qkv_bwd|ffn_bwd|segment_|lnf_loss|embed_fwd" -s 40 -c 16 -o gpurun_out/${TAG}_prof -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full rc=$?"; tail -2 gpurun_out/${TAG}_ncu_full.log
 # only text summaries travel back (the .ncu-rep with sources exceeds the 64 MiB return limit)
 python scripts/ncu_summary.py gpurun_out/${TAG}_prof.ncu-rep > gpurun_out/${TAG}_ncu_full_summary.txt 2>&1
