@@ -7,7 +7,7 @@ deterministic sparse embedding gradient + (all-reduce) + TF-Adam.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch_size B] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` = whole-job sequences/s with inputs resident in HBM (CUDA-graph replay, CUDA
-events, max over ranks, L2 flushed between timed steps); `e2e` = the same through `SASRec.train_step` with HOST
+events, max over ranks, L2 flushed between timed steps); `e2e` = the same through `SASRec.train_step(sync=False)` with HOST
 numpy batches (pinned staging + H2D + D2H of the loss inside the timed region); `roofline` = the dominant kernel
 timed with CUDA events on the launch stream; `cpu_baseline` = the CPU oracle (PyTorch restatement of the reference
 graph, `oracle/`) on the box's host cores over a bounded sample.  `--impl reference` times that CPU arm alone.
@@ -404,10 +404,12 @@ def main():
         model.train_step(None, *batches[i % len(batches)])
     barrier()
     t0 = time.perf_counter()
-    for i in range(a.steps):
-        model.train_step(None, *batches[i % len(batches)])
+    for i in range(a.steps):   # every step: pinned staging + H2D of its batch, the step, D2H of its {loss, auc, count};
+        model.train_step(None, *batches[i % len(batches)], sync=False)   # the host reads step i-1's while step i runs
+    e2e_last = model.last_metrics()
     torch.cuda.synchronize(dev)
     t_e2e = time.perf_counter() - t0
+    assert e2e_last is not None and np.isfinite(e2e_last[1])
     t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

@@ -193,18 +193,42 @@ class _Model:
         self.launch(c)
         return eng.global_sums()
 
-    def train_step(self, u, seq, pos, neg, time_seq=None, hours=None, days=None, timestamps=None):
-        """== sess.run([model.auc, model.loss, model.train_op], feed) of reference main.py:212-219."""
+    def train_step(self, u, seq, pos, neg, time_seq=None, hours=None, days=None, timestamps=None, sync=True):
+        """== sess.run([model.auc, model.loss, model.train_op], feed) of reference main.py:212-219.
+        sync=False (a training loop that only logs now and then, like the reference's once-per-epoch print): the step's
+        {loss, auc, count} sums are still copied to pinned host memory, but the call returns without waiting for them —
+        it hands back the (auc, loss) of the PREVIOUS step (None on the first call), so the host prepares batch i+1
+        while the GPU runs step i.  `last_metrics()` waits for and returns the newest step's values."""
         s = self.train_step_async(u, seq, pos, neg, time_seq, hours, days, timestamps)
-        if s.device.type == "cuda":  # 12-byte read-back into pinned memory, one stream synchronisation
-            if self._sums_host is None:
-                self._sums_host = torch.zeros(4, dtype=torch.float32, pin_memory=True)
-            self._sums_host.copy_(s[:4], non_blocking=True)
-            torch.cuda.current_stream(s.device).synchronize()
-            loss_sum, auc_sum, cnt = self._sums_host[:3].tolist()
-        else:
+        if s.device.type != "cuda":
             loss_sum, auc_sum, cnt = s[:3].tolist()
+            self._lag = None
+            self._lag_cpu = (auc_sum / cnt, loss_sum / cnt)
+            return self._lag_cpu
+        if self._sums_host is None:   # 12-byte read-backs into two alternating pinned slots
+            self._sums_host = torch.zeros(2, 4, dtype=torch.float32, pin_memory=True)
+            self._sums_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._lag = None
+            self._sums_i = 0
+        slot = self._sums_i & 1
+        self._sums_i += 1
+        prev, self._lag = self._lag, slot
+        self._sums_host[slot].copy_(s[:4], non_blocking=True)
+        self._sums_ev[slot].record(torch.cuda.current_stream(s.device))
+        if sync:
+            return self.last_metrics()
+        return self._read_metrics(prev) if prev is not None else None
+
+    def _read_metrics(self, slot):
+        self._sums_ev[slot].synchronize()
+        loss_sum, auc_sum, cnt = self._sums_host[slot][:3].tolist()
         return auc_sum / cnt, loss_sum / cnt
+
+    def last_metrics(self):
+        """(auc, loss) of the most recent train_step call (waits for it)."""
+        if getattr(self, "_lag", None) is None:
+            return getattr(self, "_lag_cpu", None)
+        return self._read_metrics(self._lag)
 
     def forward_eval(self, seq, time_seq=None, hours=None, days=None, want_attn=False, timestamps=None):
         """is_training=False forward; returns the device buffer seq_emb [B*T, H] (and fills attention weights)."""

@@ -148,11 +148,11 @@ def run(args, device=None, lib=None, logger=None):
     sampler = WarpSampler(sargs, train, usernum, itemnum, batch_size=args.batch_size, maxlen=args.maxlen, n_workers=1,
                           raw_timestamps=raw_ts)
 
-    def train_on(batch):
+    def train_on(batch, sync=True):
         u, seq, pos, neg, timeseq, _, hours_seq, days_seq, last = batch
         if raw_ts:      # ninth slot = raw int64 event times
-            return model.train_step(u, seq, pos, neg, timestamps=last)
-        return model.train_step(u, seq, pos, neg, timeseq, hours_seq, days_seq)
+            return model.train_step(u, seq, pos, neg, timestamps=last, sync=sync)
+        return model.train_step(u, seq, pos, neg, timeseq, hours_seq, days_seq, sync=sync)
     now = datetime.now()
     files_path = os.path.join(args.model_path, os.path.basename(args.dataset),
                               "{}_{}".format(args.train_dir, now.strftime("%m-%d-%Y-%H-%M-%S")))
@@ -195,8 +195,10 @@ def run(args, device=None, lib=None, logger=None):
     try:
         for epoch in range(1, args.num_epochs + 1):
             auc = loss = None
-            for _ in range(num_batch):
-                auc, loss = train_on(next_batch())
+            for _ in range(num_batch):   # the epoch's last (auc, loss) is what gets logged: nothing waits in between
+                train_on(next_batch(), sync=False)
+            if num_batch > 0:
+                auc, loss = model.last_metrics()
             if auc is not None:
                 logger.info("epoch:%d TRAIN/loss %.6f TRAIN/auc %.6f" % (epoch, loss, auc))
             if epoch % args.eval_every == 0:
