@@ -30,7 +30,7 @@ def _work(name, a, B, T, H, h):
         return 4.0 * a[12] * a[13] * a[13], 4.0 * 4 * a[12] * a[13]
     if name == "cast_ffn_bwd":      # 2 dgrad + 2 wgrad  (a[14]=N, a[15]=H)
         return 8.0 * a[14] * a[15] * a[15], 4.0 * 5 * a[14] * a[15]
-    if name == "cast_qkv_bwd":      # 3 dgrad + 3 wgrad  (a[12]=N, a[13]=H)
+    if name in ("cast_qkv_bwd", "cast_qkv_bwd_embed"):      # 3 dgrad + 3 wgrad  (a[12]=N, a[13]=H in both forms)
         return 12.0 * a[12] * a[13] * a[13], 4.0 * 7 * a[12] * a[13]
     if name in ("cast_layernorm_fwd",):
         return 8.0 * a[3] * a[4], 4.0 * 2 * a[3] * a[4]
@@ -101,7 +101,7 @@ def load_peaks(root):
     return d
 
 
-COMPUTE_BOUND = ("cast_attn_fwd", "cast_attn_bwd", "cast_gemm", "cast_qkv_bwd", "cast_ffn_bwd", "cast_ln_qkv_fwd",
+COMPUTE_BOUND = ("cast_attn_fwd", "cast_attn_bwd", "cast_gemm", "cast_qkv_bwd", "cast_qkv_bwd_embed", "cast_ffn_bwd", "cast_ln_qkv_fwd",
                  "cast_ln_ffn_fwd", "cast_rowk_ln_qkv_fwd", "cast_rowk_ln_ffn_fwd")
 
 

@@ -20,7 +20,7 @@ for n in (1, 2, 4, 8):
                  "dp_parity": d.get("dp_parity"), "eval": d.get("eval"), "hbm_per_gpu": d.get("hbm_per_gpu"),
                  "notes": d.get("notes"), "clocks": d.get("clocks")})
 out = {"workload": json.loads(lines[-1])["config"]["workload"] if rows else None, "scaling": "weak (per-GPU batch 128)",
-       "how": "bash scripts/gpu_c5_scale.sh N on one 8xB200 node (gpurun --gpus 2 / 8), bench.py --config " + cfg,
+       "how": f"CFG={cfg} bash scripts/gpu_c5_scale.sh N on one 8xB200 node (gpurun --gpus N), bench.py --config {cfg}",
        "runs": rows}
 with open(os.path.join(root, "profiles", f"scale_{cfg}.json"), "w") as f:
     json.dump(out, f, indent=1)
