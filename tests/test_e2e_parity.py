@@ -168,6 +168,25 @@ def test_multi_step_training_tracks_oracle():
 
 
 @pytest.mark.gpu
+def test_train_step_without_waiting_returns_the_previous_steps_metrics():
+    """train_step(sync=False): same training (bit-equal weights), every step's (auc, loss) still read — one call later."""
+    import cast_b200
+    args = make_args(hidden_units=50, maxlen=50, num_heads=1, num_blocks=2, dropout_rate=0.2)
+    a = cast_b200.SASRec(80, 300, args, use_graph=True)
+    b = cast_b200.SASRec(80, 300, args, use_graph=True)
+    b.engine.load_parameters({k: v.detach().cpu().clone() for k, v in a.engine.P.items()})
+    waited, lagged = [], []
+    for step in range(6):
+        gb = golden_batch(idx=step % 3)
+        waited.append(a.train_step(gb["u"], gb["seq"], gb["pos"], gb["neg"]))
+        lagged.append(b.train_step(gb["u"], gb["seq"], gb["pos"], gb["neg"], sync=False))
+    assert lagged[0] is None
+    assert lagged[1:] == waited[:-1]
+    assert b.last_metrics() == waited[-1]
+    assert torch.equal(a.engine.w, b.engine.w)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("model", ["sasrec", "cast_1", "cast_7"])
 def test_predict_matches_oracle(model):
     """models/sasrec.py:127-129 protocol: test_logits [B,101] within 1e-4, attention_weights [h*B,T,T] within 1e-5."""

@@ -4,6 +4,8 @@
   the fused backward kernels, LayerNorm gamma/beta partials with a pitch, batch column sums) against numpy float64;
 * `cast_adam_tf_step_peers` -- the data-parallel optimizer pass that sums the ranks' gradient buffers itself, bit for
   bit against `cast_peer_reduce` followed by `cast_adam_tf_step` (sasrec.py:105-121 with the global count);
+* `cast_qkv_bwd_embed` -- block 0's backward kernel that also applies the gradient of `dropout(emb) * mask`
+  (sasrec.py:58-62), bit for bit against `cast_qkv_bwd` followed by `cast_mask_dropout`;
 * `cast_lnf_loss` -- final LayerNorm (modules.py:53-80) + logits / BCE / AUC (models/sasrec.py:87-115) + LayerNorm
   backward in one launch against the separate `cast_layernorm_fwd` -> `cast_logits_loss` -> `cast_layernorm_bwd` calls
   it replaces (same library, same inputs) and against the oracle's loss.
@@ -159,6 +161,49 @@ def test_adam_peers_emulated(n, nranks):
 @pytest.mark.parametrize("n,nranks", [(207850, 2), (1003, 8), (4098, 11), (6, 1)])
 def test_adam_peers_gpu(n, nranks):
     run_adam_peers("gpu", n, nranks)
+
+
+def run_qkv_bwd_embed(kind, N, H, rate, with_ids):
+    lib, dev = backend(kind)
+    st = _stream(kind, dev)
+    rng = np.random.RandomState(N + H)
+    t = lambda *sh: torch.from_numpy(rng.randn(*sh).astype(np.float32)).to(dev)  # noqa: E731
+    dQ, dK, dV, dres, x, qn = (t(N, H) for _ in range(6))
+    mean, rstd = t(N), torch.from_numpy((0.5 + rng.rand(N)).astype(np.float32)).to(dev)
+    gamma, Wq, Wk, Wv = t(H), t(H, H), t(H, H), t(H, H)
+    ids = torch.from_numpy((rng.rand(N) > 0.3).astype(np.int32) * rng.randint(1, 99, N).astype(np.int32)).to(dev)
+    step = torch.tensor([5], dtype=torch.int64, device=dev)
+    wsb = lib.cast_block_bwd_workspace_bytes(N, H)
+    ws_a = torch.zeros(wsb // 4 + 4, dtype=torch.float32, device=dev)
+    ws_b = torch.zeros_like(ws_a)
+    dx_a = torch.full((N, H), 7.0, dtype=torch.float32, device=dev)
+    ref = torch.full((N, H), 8.0, dtype=torch.float32, device=dev)
+    dx_b = torch.full((N, H), 9.0, dtype=torch.float32, device=dev)
+    args = [v.data_ptr() for v in (dQ, dK, dV, dres, x, qn, mean, rstd, gamma, Wq, Wk, Wv)]
+    rc = lib.cast_qkv_bwd(*args, N, H, dx_a.data_ptr(), None, ws_a.data_ptr(), wsb, st)
+    assert rc == 0, lib.cast_last_error_string()
+    idp = ids.data_ptr() if with_ids else None
+    rc = lib.cast_mask_dropout(dx_a.data_ptr(), idp, rate, 1234, step.data_ptr(), 3, N, H, None, ref.data_ptr(), st)
+    assert rc == 0, lib.cast_last_error_string()
+    rc = lib.cast_qkv_bwd_embed(*args, N, H, idp, rate, 1234, step.data_ptr(), 3, dx_b.data_ptr(), None,
+                                ws_b.data_ptr(), wsb, st)
+    assert rc == 0, lib.cast_last_error_string()
+    assert torch.equal(ref.cpu(), dx_b.cpu())
+    assert torch.equal(ws_a.cpu(), ws_b.cpu())       # the weight / bias / LayerNorm partials do not depend on it
+    if rate > 0:
+        assert float((dx_b == 0).float().mean()) > 0.5 * rate
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("N,H,rate,with_ids", [(150, 20, 0.25, True), (70, 7, 0.0, True), (64, 50, 0.5, False)])
+def test_qkv_bwd_embed_emulated(N, H, rate, with_ids):
+    run_qkv_bwd_embed("emu", N, H, rate, with_ids)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,rate,with_ids", [(25600, 50, 0.2, True), (999, 64, 0.3, False), (130, 33, 0.0, True)])
+def test_qkv_bwd_embed_gpu(N, H, rate, with_ids):
+    run_qkv_bwd_embed("gpu", N, H, rate, with_ids)
 
 
 @pytest.mark.emu
