@@ -150,9 +150,16 @@ __global__ void colsum_kernel(const float* __restrict__ X, long rows, long cols,
   if (c >= cols) return;
   const long r0 = (long)blockIdx.y * rlen;
   const long r1 = (r0 + rlen < rows) ? r0 + rlen : rows;
-  float s = 0.f;
-  for (long r = r0; r < r1; ++r) s += X[r * ld + c];
-  partial[(long)blockIdx.y * cols + c] = s;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four interleaved chains: the loads of 8 rows are in flight together
+  long r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    const float v0 = X[r * ld + c], v1 = X[(r + 1) * ld + c], v2 = X[(r + 2) * ld + c], v3 = X[(r + 3) * ld + c];
+    const float v4 = X[(r + 4) * ld + c], v5 = X[(r + 5) * ld + c], v6 = X[(r + 6) * ld + c], v7 = X[(r + 7) * ld + c];
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+  }
+  for (; r < r1; ++r) a0 += X[r * ld + c];
+  partial[(long)blockIdx.y * cols + c] = (a0 + a1) + (a2 + a3);
 }
 
 }  // namespace cast

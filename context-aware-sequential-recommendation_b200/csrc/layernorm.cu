@@ -74,35 +74,64 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
   float dg[NV], db[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) dg[i] = db[i] = 0.f;
-  for (int r = warp; r < LN_ROWS_PER_CTA; r += LN_WARPS) {
-    const long row = row0 + r;
-    if (row >= N) break;  // warp-uniform
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float g[NV], xh[NV];
-    float s1 = 0.f, s2 = 0.f;
+  // RB rows of a warp are in flight together (their loads are independent; one row at a time left the kernel
+  // latency-bound at the small N of the short-sequence configs); rows are still accumulated in ascending order
+  constexpr int RB = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
+  for (int r0 = warp; r0 < LN_ROWS_PER_CTA; r0 += LN_WARPS * RB) {
+    float g[RB][NV], xh[RB][NV], dv[RB][NV];
+    float mean[RB], rstd[RB], s1[RB], s2[RB];
+    bool on[RB];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      g[i] = xh[i] = 0.f;
-      if (c < H) {
-        const float d = dy[row * H + c];
-        xh[i] = (x[row * H + c] - mean) * rstd;
-        g[i] = d * gamma[c];
-        s1 += g[i];
-        s2 += g[i] * xh[i];
-        dg[i] += d * xh[i];
-        db[i] += d;
+    for (int k = 0; k < RB; ++k) {
+      const int r = r0 + k * LN_WARPS;
+      const long row = row0 + r;
+      on[k] = r < LN_ROWS_PER_CTA && row < N;  // warp-uniform
+      mean[k] = on[k] ? mean_in[row] : 0.f;
+      rstd[k] = on[k] ? rstd_in[row] : 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        const bool in = on[k] && c < H;
+        dv[k][i] = in ? dy[row * H + c] : 0.f;
+        xh[k][i] = in ? x[row * H + c] : 0.f;
       }
     }
-    s1 = warp_sum(s1) / (float)H;
-    s2 = warp_sum(s2) / (float)H;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < H) {
-        float o = rstd * (g[i] - s1 - xh[i] * s2);
-        if (dx_add) o += dx_add[row * H + c];
-        dx[row * H + c] = o;
+    for (int k = 0; k < RB; ++k) {
+      s1[k] = s2[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        g[k][i] = 0.f;
+        if (on[k] && c < H) {
+          xh[k][i] = (xh[k][i] - mean[k]) * rstd[k];
+          g[k][i] = dv[k][i] * gamma[c];
+          s1[k] += g[k][i];
+          s2[k] += g[k][i] * xh[k][i];
+          dg[i] += dv[k][i] * xh[k][i];
+          db[i] += dv[k][i];
+        } else {
+          xh[k][i] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      s1[k] = warp_sum(s1[k]) / (float)H;
+      s2[k] = warp_sum(s2[k]) / (float)H;
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      if (!on[k]) continue;
+      const long row = row0 + r0 + k * LN_WARPS;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < H) {
+          float o = rstd[k] * (g[k][i] - s1[k] - xh[k][i] * s2[k]);
+          if (dx_add) o += dx_add[row * H + c];
+          dx[row * H + c] = o;
+        }
       }
     }
   }
