@@ -190,7 +190,7 @@ class Engine:
         self.sinus = torch.from_numpy(sinusoid_table(self.H, self.T)).to(self.device)
         self.init_parameters(self.seed or 42)
         self._call(self.lib.cast_adam_init_state, self.adam_state.data_ptr(), self.beta1, self.beta2, self._stream())
-        self._ctx: Dict[int, SimpleNamespace] = {}
+        self._ctx: Dict[tuple, SimpleNamespace] = {}
         # tcgen05 row kernels (csrc/row_umma.cu): per-block weight operand images, rebuilt once per forward pass
         self.use_rowk = bool(self.lib.cast_rowk_supported(self.H))
         self.rowk_block: Dict[str, int] = {}
@@ -301,7 +301,8 @@ class Engine:
 
     # ------------------------------------------------------------------ buffers
     def ctx(self, B: int) -> SimpleNamespace:
-        c = self._ctx.get(B)
+        key = (B, bool(self.use_fused))   # the per-block workspaces differ between the fused and the unfused path
+        c = self._ctx.get(key)
         if c is not None:
             return c
         H, T, h, dev = self.H, self.T, self.h, self.device
@@ -370,7 +371,7 @@ class Engine:
         c.spart_bytes = spb
         c.attn = None
         c.graph = None
-        self._ctx[B] = c
+        self._ctx[key] = c
         return c
 
     # ------------------------------------------------------------------ op wrappers
