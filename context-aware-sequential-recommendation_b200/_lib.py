@@ -51,6 +51,7 @@ SIGNATURES = {
     "cast_colsum_workspace_bytes": (SZ, [L, L]),
     "cast_colsum": (I, [P, L, L, L, P, P, SZ, P]),
     "cast_attn_set_chunk": (I, [I]),
+    "cast_set_pdl": (I, [I]),
     "cast_attn_set_kg": (I, [I]),
     "cast_fused_set_backend": (I, [I]),
     "cast_block_bwd_parts": (I, [L, I]),
@@ -134,6 +135,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib = bind(C.CDLL(p))
     if os.environ.get("CAST_ATTN_CHUNK"):  # tuning hook (32 or 64 columns per streamed attention chunk)
         check(lib, lib.cast_attn_set_chunk(int(os.environ["CAST_ATTN_CHUNK"])), "cast_attn_set_chunk")
+    if os.environ.get("CAST_PDL"):         # A/B hook: 0 = ordinary launches instead of programmatic dependent launch
+        check(lib, lib.cast_set_pdl(int(os.environ["CAST_PDL"])), "cast_set_pdl")
     if os.environ.get("CAST_ATTN_KG"):     # tuning hook (2 or 4 key groups per row block of the attention kernels)
         check(lib, lib.cast_attn_set_kg(int(os.environ["CAST_ATTN_KG"])), "cast_attn_set_kg")
     if os.environ.get("CAST_FUSED_BACKEND"):  # A/B hook: 0 = FFMA row kernels, 1 = tensor-core row kernels

@@ -34,6 +34,8 @@ __global__ void adam_step_kernel(float* __restrict__ w, const float* __restrict_
                                  float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
                                  const float* __restrict__ gdenom, float l2, long l2_lo, long l2_hi,
                                  const AdamState* __restrict__ st) {
+  cast_pdl_wait();
+  cast_pdl_trigger();
   const float gs = gdenom ? 1.0f / *gdenom : 1.0f;
   const float lr_t = lr * sqrtf(1.0f - st->b2p) / (1.0f - st->b1p);
   const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
@@ -51,6 +53,8 @@ __global__ void adam_step_vec4_kernel(float4* __restrict__ w, const float4* __re
                                       float4* __restrict__ v, long n4, float lr, float b1, float b2, float eps,
                                       const float* __restrict__ gdenom, float l2, long l2_lo, long l2_hi,
                                       const AdamState* __restrict__ st) {
+  cast_pdl_wait();
+  cast_pdl_trigger();
   const float gs = gdenom ? 1.0f / *gdenom : 1.0f;
   const float lr_t = lr * sqrtf(1.0f - st->b2p) / (1.0f - st->b1p);
   const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
@@ -80,6 +84,8 @@ __global__ void adam_step_peers_kernel(float* __restrict__ w, const float* const
                                        long np, long tail, float lr, float b1, float b2, float eps, float l2,
                                        long l2_lo, long l2_hi, const AdamState* __restrict__ st) {
   __shared__ float s_count;
+  cast_pdl_wait();
+  cast_pdl_trigger();
   if (threadIdx.x == 0) {
     float c = g[0][np + 2];
     for (int r = 1; r < n; ++r) c += g[r][np + 2];
@@ -145,6 +151,8 @@ __global__ void adam_step_peers_kernel(float* __restrict__ w, const float* const
 }
 
 __global__ void adam_advance_kernel(AdamState* st, float b1, float b2) {
+  cast_pdl_wait();
+  cast_pdl_trigger();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->b1p *= b1;
     st->b2p *= b2;
@@ -174,19 +182,19 @@ extern "C" int cast_adam_tf_range(float* w, const float* grad, float* m, float* 
   if (vec) {
     long g = cdiv(n / 4, 256);
     if (g > 148 * 8) g = 148 * 8;
-    CAST_LAUNCH(adam_step_vec4_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream,
+    CAST_LAUNCH_DEP(adam_step_vec4_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream,
                 reinterpret_cast<float4*>(w), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(m),
                 reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps, gdenom, l2, l2_lo, l2_hi,
                 static_cast<const AdamState*>(state));
   } else {
     long g = cdiv(n, 256);
     if (g > 148 * 8) g = 148 * 8;
-    CAST_LAUNCH(adam_step_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, w, grad, m, v, n, lr, beta1,
+    CAST_LAUNCH_DEP(adam_step_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, w, grad, m, v, n, lr, beta1,
                 beta2, eps, gdenom, l2, l2_lo, l2_hi, static_cast<const AdamState*>(state));
   }
   if ((rc = check_launch("adam_step"))) return rc;
   if (advance) {
-    CAST_LAUNCH(adam_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, static_cast<AdamState*>(state),
+    CAST_LAUNCH_DEP(adam_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, static_cast<AdamState*>(state),
                 beta1, beta2);
     return check_launch("adam_advance");
   }
@@ -212,12 +220,12 @@ extern "C" int cast_adam_tf_step_peers(float* w, const void* const* grads, int n
     return set_error(CAST_ERR_BAD_ARG, "adam_tf_step_peers: buffers must be 16-byte aligned");
   long g = cdiv(cdiv(n + tail, 4), 256);
   if (g > 148 * 8) g = 148 * 8;
-  CAST_LAUNCH(adam_step_peers_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, w,
+  CAST_LAUNCH_DEP(adam_step_peers_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, w,
               reinterpret_cast<const float* const*>(grads), n_ranks, g_red, m, v, n, tail, lr, beta1, beta2, eps, l2,
               l2_lo, l2_hi, static_cast<const AdamState*>(state));
   int rc;
   if ((rc = check_launch("adam_step_peers"))) return rc;
-  CAST_LAUNCH(adam_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, static_cast<AdamState*>(state), beta1,
+  CAST_LAUNCH_DEP(adam_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, static_cast<AdamState*>(state), beta1,
               beta2);
   return check_launch("adam_advance");
 }

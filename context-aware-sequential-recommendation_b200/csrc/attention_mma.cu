@@ -184,6 +184,10 @@ __device__ __forceinline__ void am_block(const AttnDims& dm, int& b, int& hh, in
 template <int KS, int NT, int KG>
 __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG <= 2) ? (KG == 1 ? 4 : 2) : 1)
 attn_fwd_mma_kernel(AttnFwdArgs a, AttnDims dm) {
+  cast_pdl_wait();
+  // every CTA signals at once: the next kernel of the chain (a row kernel: weights, shared-memory set-up, tensor-memory
+  // allocation before its own wait) may take the SMs this grid leaves idle in its long tail
+  cast_pdl_trigger();
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   CAST_DYN_SMEM(float, sm);
   __shared__ int s_first[AM_FIRST_SLOTS];
@@ -420,6 +424,10 @@ struct AttnBwdMmaArgs {
 // reaches all T keys, are walked over the whole key range like in the forward pass)
 template <int KS, int NT, int KG, bool ST>
 __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 2) ? 2 : 1) attn_bwd_dq_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  cast_pdl_wait();
+  // every CTA signals at once: the next kernel of the chain (a row kernel: weights, shared-memory set-up, tensor-memory
+  // allocation before its own wait) may take the SMs this grid leaves idle in its long tail
+  cast_pdl_trigger();
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
@@ -656,6 +664,7 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 template <int KS, int NT, int KG>
 __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 2) ? 2 : 1) attn_bwd_dkv_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  cast_pdl_wait();
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
@@ -849,6 +858,10 @@ constexpr int AW_TQ = 32, AW_PS = 72, AW_THREADS = 256;
 
 template <int KS>
 __global__ void __launch_bounds__(AW_THREADS, 2) attn_bwd_dkv_ws_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
+  cast_pdl_wait();
+  // every CTA signals at once: the next kernel of the chain (a row kernel: weights, shared-memory set-up, tensor-memory
+  // allocation before its own wait) may take the SMs this grid leaves idle in its long tail
+  cast_pdl_trigger();
   constexpr int DP = 8 * KS, NTO = KS, TQ = AW_TQ, PS = AW_PS, NW = AW_THREADS / 32;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
@@ -1072,7 +1085,7 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
         cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cfg4 = smem;
       }
-      CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KG4), smem, stream, *fa, dm);
+      CAST_LAUNCH_DEP(kf, grid, dim3(AM_THREADS * KG4), smem, stream, *fa, dm);
       return CAST_OK;
     }
     constexpr int KGF = (NT == 4) ? 2 : 1;  // 8 warps: two key groups per row block
@@ -1083,7 +1096,7 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg[0] = smem;
     }
-    CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGF), smem, stream, *fa, dm);
+    CAST_LAUNCH_DEP(kf, grid, dim3(AM_THREADS * KGF), smem, stream, *fa, dm);
   } else if (which == 1) {
     if (NT == 4 && g_attn_kg == 4 && ba->pbuf) {
       constexpr int KG4 = (NT == 4) ? 4 : 1, TC4 = TC * KG4;
@@ -1094,7 +1107,7 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
         cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cfg4 = smem;
       }
-      CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KG4), smem, stream, *ba, dm);
+      CAST_LAUNCH_DEP(kf, grid, dim3(AM_THREADS * KG4), smem, stream, *ba, dm);
       return CAST_OK;
     }
     constexpr int KGB = (NT == 4) ? 2 : 1;
@@ -1107,7 +1120,7 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
         cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cfgs = smem;
       }
-      CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
+      CAST_LAUNCH_DEP(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
       return CAST_OK;
     }
     auto kf = attn_bwd_dq_mma_kernel<KS, NT, KGB, false>;
@@ -1115,7 +1128,7 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg[1] = smem;
     }
-    CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
+    CAST_LAUNCH_DEP(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
   } else {
     if (ba->pbuf) {
       static size_t cfgw = 48 * 1024;
@@ -1125,7 +1138,7 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
         cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
         cfgw = smemw;
       }
-      CAST_LAUNCH(kw, grid, dim3(AW_THREADS), smemw, stream, *ba, dm);
+      CAST_LAUNCH_DEP(kw, grid, dim3(AW_THREADS), smemw, stream, *ba, dm);
       return CAST_OK;
     }
     constexpr int KGB = (NT == 4) ? 2 : 1;
@@ -1136,7 +1149,7 @@ static int launch_mma(int which, const AttnFwdArgs* fa, const AttnBwdMmaArgs* ba
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg[2] = smem;
     }
-    CAST_LAUNCH(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
+    CAST_LAUNCH_DEP(kf, grid, dim3(AM_THREADS * KGB), smem, stream, *ba, dm);
   }
   return CAST_OK;
 }

@@ -7,6 +7,9 @@ namespace cast {
 
 static thread_local char g_err[256] = "";
 static unsigned long long g_launches = 0;  // kernels enqueued through this library (host-side counter)
+#ifndef CAST_EMU
+int g_pdl = 1;   // programmatic dependent launch of the step's main-chain kernels (cast_rt.cuh), cast_set_pdl()
+#endif
 
 int set_error(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s (code %d)", msg ? msg : "error", code);
@@ -26,6 +29,14 @@ int check_launch(const char* what) {
 }  // namespace cast
 
 extern "C" int cast_version(void) { return CAST_ABI_VERSION; }
+extern "C" int cast_set_pdl(int on) {
+#ifndef CAST_EMU
+  cast::g_pdl = on ? 1 : 0;
+#else
+  (void)on;
+#endif
+  return CAST_OK;
+}
 extern "C" const char* cast_last_error_string(void) { return cast::g_err; }
 extern "C" unsigned long long cast_launch_count(void) { return __atomic_load_n(&cast::g_launches, __ATOMIC_RELAXED); }
 

@@ -19,6 +19,43 @@
   type* name = reinterpret_cast<type*>(name##_raw_smem)
 #endif
 
+// Programmatic dependent launch for the kernels of the training step's main chain: the next kernel's CTAs may be
+// scheduled while the previous kernel drains (its launch latency and whatever it does before cast_pdl_wait() overlap
+// the tail); every kernel launched this way calls cast_pdl_wait() before its first global-memory access, so the
+// stream order of all data is unchanged.  cast_set_pdl(0) (env CAST_PDL=0) launches them the ordinary way.
+#ifdef CAST_EMU
+#define CAST_LAUNCH_DEP(kernel, grid, block, smem, stream, ...) CAST_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
+static inline void cast_pdl_wait() {}
+static inline void cast_pdl_trigger() {}
+#else
+namespace cast {
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+static inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  if (!g_pdl) {
+    kernel<<<grid, block, smem, stream>>>(KArgs(args)...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace cast
+#define CAST_LAUNCH_DEP(kernel, grid, block, smem, stream, ...) \
+  cast::launch_dep(kernel, grid, block, smem, stream, __VA_ARGS__)
+__device__ __forceinline__ void cast_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void cast_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 #include "../../include/cast_b200.h"
 
 #define CAST_NEG_FILL (-4294967296.0f)  // float32(-2**32+1), modules.py:227,239

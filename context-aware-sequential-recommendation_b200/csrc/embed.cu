@@ -14,6 +14,8 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, TableRef table, in
                                  int T, float scale, const float* __restrict__ pos, const float* __restrict__ add,
                                  float rate, unsigned long long seed, const unsigned long long* step, int site,
                                  const int* __restrict__ mask_ids, float* __restrict__ out) {
+  cast_pdl_wait();
+  cast_pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const Drop d = make_drop(rate, seed, step, site);
@@ -180,7 +182,7 @@ extern "C" int cast_embed_fwd(const int* ids, const float* table, int V, int H, 
   if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "embed_fwd: drop_rate");
   if (N == 0) return CAST_OK;
   const int wpb = 8;
-  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb * EMB_ROWS_PER_WARP)), dim3(32 * wpb), 0,
+  CAST_LAUNCH_DEP(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb * EMB_ROWS_PER_WARP)), dim3(32 * wpb), 0,
               (cudaStream_t)stream, ids, table_ref(table), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
   return check_launch("embed_fwd");
 }
@@ -194,7 +196,7 @@ extern "C" int cast_embed_fwd_sharded(const int* ids, const float* const* shards
   if (drop_rate < 0.f || drop_rate >= 1.f) return set_error(CAST_ERR_BAD_ARG, "embed_fwd_sharded: drop_rate");
   if (N == 0) return CAST_OK;
   const int wpb = 8;
-  CAST_LAUNCH(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb * EMB_ROWS_PER_WARP)), dim3(32 * wpb), 0,
+  CAST_LAUNCH_DEP(embed_fwd_kernel, dim3((unsigned)cdiv(N, wpb * EMB_ROWS_PER_WARP)), dim3(32 * wpb), 0,
               (cudaStream_t)stream, ids, table_ref(shards, nshards), V, H, N, T, scale, pos, add, drop_rate, seed, step, site, mask_ids, out);
   return check_launch("embed_fwd_sharded");
 }

@@ -605,7 +605,7 @@ static void launch_qkv_bwd_mma(const QkvBwdArgs& a, FDims d, int grid, cudaStrea
   const size_t smem = qkv_bwd_mma_smem<KS>();
   auto kf = qkv_bwd_mma_kernel<KS, RM_BWD_NG>;
   CAST_FUSED_SMEM(kf, smem)
-  CAST_LAUNCH(kf, dim3(grid), dim3(128 * RM_BWD_NG), smem, stream, a, d);
+  CAST_LAUNCH_DEP(kf, dim3(grid), dim3(128 * RM_BWD_NG), smem, stream, a, d);
 }
 template <int KS>
 static void launch_ffn_bwd_mma(const FfnBwdArgs& a, FDims d, int grid, cudaStream_t stream) {
@@ -613,7 +613,7 @@ static void launch_ffn_bwd_mma(const FfnBwdArgs& a, FDims d, int grid, cudaStrea
   const size_t smem = ffn_bwd_mma_smem<KS>();
   auto kf = ffn_bwd_mma_kernel<KS, RM_BWD_NG>;
   CAST_FUSED_SMEM(kf, smem)
-  CAST_LAUNCH(kf, dim3(grid), dim3(128 * RM_BWD_NG), smem, stream, a, d);
+  CAST_LAUNCH_DEP(kf, dim3(grid), dim3(128 * RM_BWD_NG), smem, stream, a, d);
 }
 template <int KS>
 static void launch_ln_qkv_fwd_mma(const LnQkvArgs& a, FDims d, cudaStream_t stream) {

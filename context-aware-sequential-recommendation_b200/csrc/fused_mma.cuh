@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
   constexpr int SL = BT / 64;  // row slices of the column sums
   float vbq = 0.f, vbk = 0.f, vbv = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
+  cast_pdl_wait();   // (weights and gamma, requested above, are not the previous kernel's output; the row tiles are)
   if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
   else cp_async_commit();
   int it = 0;
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
   constexpr int SL = BT / 64;  // row slices of the column sums
   float vb1 = 0.f, vb2 = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
+  cast_pdl_wait();   // (weights and gamma, requested above, are not the previous kernel's output; the row tiles are)
   if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
   else cp_async_commit();
   // row mask of a tile (padding positions and rows past N get 0): fetched one tile ahead by threads 0..FR-1 and handed

@@ -202,6 +202,8 @@ struct ReduceJobs {
 };
 __global__ void __launch_bounds__(RP_COLS * RP_GROUPS) reduce_partials_batch_kernel(ReduceJobs jobs) {
   __shared__ float red[RP_GROUPS][RP_COLS];
+  cast_pdl_wait();
+  cast_pdl_trigger();
   const int job = blockIdx.y;
   const float* __restrict__ partial = jobs.partial[job];
   float* __restrict__ out = jobs.out[job];
@@ -269,7 +271,7 @@ extern "C" int cast_reduce_partials_batch(int njobs, const float* const* partial
     }
     long g = cdiv(maxc, RP_COLS);
     if (g > 2368) g = 2368;
-    CAST_LAUNCH(reduce_partials_batch_kernel, dim3((unsigned)g, (unsigned)n), dim3(RP_COLS * RP_GROUPS), 0,
+    CAST_LAUNCH_DEP(reduce_partials_batch_kernel, dim3((unsigned)g, (unsigned)n), dim3(RP_COLS * RP_GROUPS), 0,
                 (cudaStream_t)stream, jobs);
   }
   return check_launch("reduce_partials_batch");

@@ -126,6 +126,8 @@ lnf_loss_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
                 float* __restrict__ dx, float* __restrict__ partial_loss, float* __restrict__ partial_ln) {
   __shared__ float red[LNF_SLOTS][3];
   __shared__ float redg[LNF_SLOTS][2][64];
+  cast_pdl_wait();
+  cast_pdl_trigger();
   const int t = threadIdx.x, slot = t / LNF_TPR, sub = t % LNF_TPR;
   const long row0 = (long)blockIdx.x * LOSS_ROWS_PER_CTA;
   const bool heven = (H & 1) == 0;
@@ -289,7 +291,7 @@ extern "C" int cast_lnf_loss(const float* x, const float* gamma, const float* be
     return set_error(CAST_ERR_WORKSPACE, "lnf_loss: workspace too small");
   const int ncta = (int)cdiv(N, LOSS_ROWS_PER_CTA);
   float* pl = static_cast<float*>(workspace);
-  CAST_LAUNCH(lnf_loss_kernel, dim3(ncta), dim3(LNF_THREADS), 0, (cudaStream_t)stream, x, gamma, beta, eps,
+  CAST_LAUNCH_DEP(lnf_loss_kernel, dim3(ncta), dim3(LNF_THREADS), 0, (cudaStream_t)stream, x, gamma, beta, eps,
               table_ref(table), V, H, N, pos, neg, seq_emb, pos_logits, neg_logits, gpos, gneg, dx, pl, pl + (size_t)ncta * 3);
   return check_launch("lnf_loss");
 }

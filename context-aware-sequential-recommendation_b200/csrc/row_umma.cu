@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_qkv_fwd_kernel(RuLnQkvArg
       umma::mbar_arrive_expect_tx(&bars[0], (uint32_t)(s.img1 + s.img2));
       umma::bulk_g2s(wq, a.img + ru_img_offset(s, 0), (uint32_t)s.img1, &bars[0]);
       umma::bulk_g2s(wkv, a.img + ru_img_offset(s, 1), (uint32_t)s.img2, &bars[0]);
+      cast_pdl_wait();
       ru_wait(&bars[0], 0);
       for (int it = 0; it < rg.ntiles; ++it) {
         const uint32_t par = (uint32_t)(it & 1);
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_qkv_fwd_kernel(RuLnQkvArg
       const long left = rg.hi - (rg.lo + (long)it * RU_ROWS);
       return left < RU_ROWS ? left : (long)RU_ROWS;
     };
+    cast_pdl_wait();   // weights, LayerNorm parameters and biases above do not come from the previous kernel; x does
     if (rg.ntiles > 0) ru_tile_load_async(tin, a.x + rg.lo * H, rows_of(0) * H, ntot);
     const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
     for (int it = 0; it < rg.ntiles; ++it) {
@@ -516,6 +518,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_ffn_fwd_kernel(RuLnFfnArg
     if ((t & 31) == 0 && rg.ntiles > 0) {
       umma::mbar_arrive_expect_tx(&bars[0], (uint32_t)(2 * s.img1));
       umma::bulk_g2s(w1, a.img + ru_img_offset(s, 2), (uint32_t)(2 * s.img1), &bars[0]);  // W1T and W2T are adjacent
+      cast_pdl_wait();
       ru_wait(&bars[0], 0);
       for (int it = 0; it < rg.ntiles; ++it) {
         const uint32_t par = (uint32_t)(it & 1);
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_ln_ffn_fwd_kernel(RuLnFfnArg
       const long left = rg.hi - (rg.lo + (long)it * RU_ROWS);
       return left < RU_ROWS ? left : (long)RU_ROWS;
     };
+    cast_pdl_wait();   // weights, LayerNorm parameters and biases above do not come from the previous kernel; y does
     if (rg.ntiles > 0) ru_tile_load_async(tin, a.y + rg.lo * H, rows_of(0) * H, ntot);
     const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
     const Drop dh = make_drop(a.rate, a.seed, a.step, a.site_h);
@@ -705,7 +709,7 @@ extern "C" int cast_rowk_ln_qkv_fwd(const float* x, const float* gamma, const fl
                 kmask, qmask, N, rpc, H};
   const size_t smem = ru_ln_qkv_smem(s);
   CAST_RU_SMEM(ru_ln_qkv_fwd_kernel, smem)
-  CAST_LAUNCH(ru_ln_qkv_fwd_kernel, dim3(grid), dim3(RU_THREADS), smem, (cudaStream_t)stream, a);
+  CAST_LAUNCH_DEP(ru_ln_qkv_fwd_kernel, dim3(grid), dim3(RU_THREADS), smem, (cudaStream_t)stream, a);
   return check_launch("rowk_ln_qkv_fwd");
 }
 
@@ -726,7 +730,7 @@ extern "C" int cast_rowk_ln_ffn_fwd(const float* y, const float* gamma, const fl
                 site_hidden, site_out, zn, h1d, xout, mean, rstd, N, rpc, H};
   const size_t smem = ru_ln_ffn_smem(s);
   CAST_RU_SMEM(ru_ln_ffn_fwd_kernel, smem)
-  CAST_LAUNCH(ru_ln_ffn_fwd_kernel, dim3(grid), dim3(RU_THREADS), smem, (cudaStream_t)stream, a);
+  CAST_LAUNCH_DEP(ru_ln_ffn_fwd_kernel, dim3(grid), dim3(RU_THREADS), smem, (cudaStream_t)stream, a);
   return check_launch("rowk_ln_ffn_fwd");
 }
 

@@ -124,6 +124,8 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
                                        float* __restrict__ dtable, float* __restrict__ part, int* __restrict__ pkey,
                                        int accumulate) {
   constexpr int SEG_Q = SEG_CHUNK / 32;
+  cast_pdl_wait();
+  cast_pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long beg = w * SEG_CHUNK;
@@ -246,6 +248,8 @@ __global__ void segment_partial_kernel(const unsigned* __restrict__ skeys, const
 template <int NV>
 __global__ void segment_stitch_kernel(const float* __restrict__ part, const int* __restrict__ pkey, long nchunks,
                                       unsigned klo, unsigned khi, int H, float* __restrict__ dtable, int accumulate) {
+  cast_pdl_wait();
+  cast_pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nchunks) return;
@@ -472,14 +476,14 @@ static int scatter_apply_impl(int nsrc, long N, const float* const* rows, const 
 #define CAST_SEG(NV)                                                                                            \
   {                                                                                                             \
     if (chunk == 32) {                                                                                          \
-      CAST_LAUNCH((segment_partial_kernel<NV, 32>), grid, block, 0, st, kin, pin, total, N, src, klo, khi, H,   \
+      CAST_LAUNCH_DEP((segment_partial_kernel<NV, 32>), grid, block, 0, st, kin, pin, total, N, src, klo, khi, H,   \
                   dtable, part, pkey, accumulate);                                                              \
     } else {                                                                                                    \
-      CAST_LAUNCH((segment_partial_kernel<NV, 64>), grid, block, 0, st, kin, pin, total, N, src, klo, khi, H,   \
+      CAST_LAUNCH_DEP((segment_partial_kernel<NV, 64>), grid, block, 0, st, kin, pin, total, N, src, klo, khi, H,   \
                   dtable, part, pkey, accumulate);                                                              \
     }                                                                                                           \
     if ((rc = check_launch("segment_partial"))) return rc;                                                      \
-    CAST_LAUNCH(segment_stitch_kernel<NV>, grid, block, 0, st, (const float*)part, (const int*)pkey, nseg, klo, \
+    CAST_LAUNCH_DEP(segment_stitch_kernel<NV>, grid, block, 0, st, (const float*)part, (const int*)pkey, nseg, klo, \
                 khi, H, dtable, accumulate);                                                                    \
   }
   if (H <= 64) CAST_SEG(2)

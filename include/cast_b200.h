@@ -244,6 +244,10 @@ int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const floa
                   unsigned long long seed, const unsigned long long* step, int site, const int* skip_ids, float* out,
                   float* attn_weights, float* row_max, float* row_linv, void* stream);
 /* Tuning hook: columns per streamed chunk of the tensor-core attention kernels (32 or 64; default 32). */
+/* Programmatic dependent launch of the training step's main-chain kernels (default on): the next kernel's CTAs may be
+ * scheduled while the previous kernel drains; every such kernel waits (griddepcontrol.wait) before its first access to
+ * data the previous kernel produces, so results do not change.  0 = ordinary stream-ordered launches (A/B hook). */
+int cast_set_pdl(int on);
 int cast_attn_set_chunk(int columns);
 /* Tuning hook: warps that share one 16-row block of a 64-row attention tile, each taking a 32-key slice of every
  * streamed chunk (forward and dQ kernels): 2 = 8 warps, two CTAs per SM (default); 4 = 16 warps, one CTA per SM. */
