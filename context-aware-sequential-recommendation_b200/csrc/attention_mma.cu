@@ -424,10 +424,6 @@ struct AttnBwdMmaArgs {
 // reaches all T keys, are walked over the whole key range like in the forward pass)
 template <int KS, int NT, int KG, bool ST>
 __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 2) ? 2 : 1) attn_bwd_dq_mma_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
-  cast_pdl_wait();
-  // every CTA signals at once: the next kernel of the chain (a row kernel: weights, shared-memory set-up, tensor-memory
-  // allocation before its own wait) may take the SMs this grid leaves idle in its long tail
-  cast_pdl_trigger();
   constexpr int DP = 8 * KS, DS = DP + 4, NTO = KS, TW = 8 * NT, TC = TW * KG, NTHR = AM_THREADS * KG, NW = 4 * KG;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
@@ -448,8 +444,9 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   // The tile's own rows (Q, dO and, for D_i, out and queries — parked in the second K/V stage, which the chunk loop
   // does not touch before its first iteration) start moving before anything is known about the sequence: the scan for
   // its first key / first query below then costs no extra round trip.
+  // Of this kernel's inputs only dO is produced by the kernel before it in the chain (the FFN backward kernel): the
+  // query tile, out / queries, the sequence scan and the first K/V chunk are requested before the wait on that kernel.
   am_load_rows_async<AM_T, DS, NW>(Qs, a.Q + rowbase * a.ldq + hh * d, a.ldq, q0, T, d, am_vec2_ok(a.Q, a.ldq, d, hh));
-  am_load_rows_async<AM_T, DS, NW>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
   constexpr bool PARK = TC >= AM_T;   // a K/V stage holds a whole row tile (the 8-warp configuration)
   float* outS = Kst + TC * DS;
   float* resS = Vst + TC * DS;
@@ -464,6 +461,7 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
   if (q0 + AM_T <= qstart) {  // padding-only tile: zero gradient
     cp_async_wait<0>();
+    cast_pdl_wait();
     for (int idx = t; idx < AM_T * d; idx += NTHR) {
       const int i = q0 + idx / d, c = idx % d;
       if (i >= 0) a.dQ[(rowbase + i) * a.lddq + hh * d + c] = 0.f;
@@ -496,7 +494,13 @@ __global__ void __launch_bounds__(AM_THREADS * KG, (KS <= 7 && NT == 4 && KG == 
   };
   if (nch > 0) issue(kbeg, 0); else cp_async_commit();
   am_zero_pad<DP, DS>(sm, 2 * AM_T + 4 * TC, d);
-  cp_async_wait<1>();   // the tile's rows have landed (the first chunk may still be in flight)
+  cast_pdl_wait();
+  // every CTA signals at once (after its own wait, so that whatever precedes the previous kernel is complete when a
+  // dependent starts): the dK/dV kernel may take the SMs this grid leaves idle in its long tail
+  cast_pdl_trigger();
+  am_load_rows_async<AM_T, DS, NW>(dOs, a.dO + rowbase * dm.H + hh * d, dm.H, q0, T, d, am_vec2_ok(a.dO, dm.H, d, hh));
+  cp_async_commit();
+  cp_async_wait<0>();   // the tile's rows and the first chunk have landed
   __syncthreads();
   // D_i = dO_i . (out_i - queries_i) over this head's columns, from the staged rows: one warp per row
   {
@@ -858,10 +862,6 @@ constexpr int AW_TQ = 32, AW_PS = 72, AW_THREADS = 256;
 
 template <int KS>
 __global__ void __launch_bounds__(AW_THREADS, 2) attn_bwd_dkv_ws_kernel(AttnBwdMmaArgs aa, AttnDims dm) {
-  cast_pdl_wait();
-  // every CTA signals at once: the next kernel of the chain (a row kernel: weights, shared-memory set-up, tensor-memory
-  // allocation before its own wait) may take the SMs this grid leaves idle in its long tail
-  cast_pdl_trigger();
   constexpr int DP = 8 * KS, NTO = KS, TQ = AW_TQ, PS = AW_PS, NW = AW_THREADS / 32;
   const AttnBwdArgs& a = aa.b;
   CAST_DYN_SMEM(float, sm);
@@ -879,6 +879,10 @@ __global__ void __launch_bounds__(AW_THREADS, 2) attn_bwd_dkv_ws_kernel(AttnBwdM
   int first_key, qstart;
   am_first2(a.kmask + rowbase, a.skip_ids ? a.skip_ids + rowbase : nullptr, T, s_first, first_key, qstart);
   const bool has_uniform = qstart < first_key;
+  // Up to here only forward-pass data was read (key mask, ids): the scan ran while the dQ kernel, whose P~ / dS tiles
+  // this kernel consumes, may still be draining.  Nothing is written and no dQ-kernel output is read before the wait.
+  cast_pdl_wait();
+  cast_pdl_trigger();   // (after the wait: whatever precedes the dQ kernel is complete when a dependent starts)
   if (k0 + AM_T <= first_key && !has_uniform) {
     for (int idx = t; idx < AM_T * d; idx += AW_THREADS) {
       const int j = k0 + idx / d, c = idx % d;

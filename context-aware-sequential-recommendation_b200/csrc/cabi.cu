@@ -8,7 +8,7 @@ namespace cast {
 static thread_local char g_err[256] = "";
 static unsigned long long g_launches = 0;  // kernels enqueued through this library (host-side counter)
 #ifndef CAST_EMU
-int g_pdl = 1;   // programmatic dependent launch of the step's main-chain kernels (cast_rt.cuh), cast_set_pdl()
+int g_pdl = 0;   // programmatic dependent launch of the step's main-chain kernels (cast_rt.cuh); cast_set_pdl(1) by the engine
 #endif
 
 int set_error(int code, const char* msg) {

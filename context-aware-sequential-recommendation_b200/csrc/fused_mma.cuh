@@ -383,9 +383,23 @@ __global__ void __launch_bounds__(128 * NG, 1) qkv_bwd_mma_kernel(QkvBwdArgs a, 
   constexpr int SL = BT / 64;  // row slices of the column sums
   float vbq = 0.f, vbk = 0.f, vbv = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
-  cast_pdl_wait();   // (weights and gamma, requested above, are not the previous kernel's output; the row tiles are)
-  if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
-  else cp_async_commit();
+  // The kernel before this one in the chain is the attention dK/dV kernel: of the first tile only dK and dV are its
+  // output (dQ, x, LN(x), the weights and gamma were complete before it started), so everything else is requested
+  // before the wait and arrives while that kernel drains.
+  if ((long)blockIdx.x < a.ntiles) {
+    const long row0 = (long)blockIdx.x * FR;
+    rm_load_tile_async<S, NW>(sm, a.dQ, row0, d.N, H, v0);
+    rm_load_tile_async<S, NW>(sm + 3 * TILE, a.x, row0, d.N, H, v3);
+    rm_load_tile_async<S, NW>(sm + 4 * TILE, a.qn, row0, d.N, H, v4);
+  }
+  cp_async_commit();
+  cast_pdl_wait();
+  if ((long)blockIdx.x < a.ntiles) {
+    const long row0 = (long)blockIdx.x * FR;
+    rm_load_tile_async<S, NW>(sm + TILE, a.dK, row0, d.N, H, v1);
+    rm_load_tile_async<S, NW>(sm + 2 * TILE, a.dV, row0, d.N, H, v2);
+  }
+  cp_async_commit();
   int it = 0;
   for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
     const int st = it & 1;
@@ -498,6 +512,7 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
   float vb1 = 0.f, vb2 = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
   cast_pdl_wait();   // (weights and gamma, requested above, are not the previous kernel's output; the row tiles are)
+  cast_pdl_trigger();  // the attention dQ kernel that follows has a long prologue that does not depend on this kernel
   if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
   else cp_async_commit();
   // row mask of a tile (padding positions and rows past N get 0): fetched one tile ahead by threads 0..FR-1 and handed

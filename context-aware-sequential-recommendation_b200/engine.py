@@ -206,6 +206,11 @@ class Engine:
         self.adam_g = self.gbuf     # what Adam consumes: the local buffer, or the rank-ordered sum (dist.PeerExchange)
         self.exchange_capturable = False   # the exchange is plain kernel launches => the step is one CUDA graph
         self.after_adam = None      # set by dist.attach_sharded(): the barrier that ends a row-sharded step
+        # the step's kernels form a chain whose operands obey include/cast_b200.h's cast_set_pdl contract (weights are
+        # last written by the optimizer pass of the previous step, images on a joined side stream, activations of the
+        # forward pass long before the backward kernels that re-read them): programmatic dependent launch is safe here
+        if self.device.type == "cuda":
+            self.lib.cast_set_pdl(0 if os.environ.get("CAST_PDL", "1") == "0" else 1)
         self.fork_reduce = os.environ.get("CAST_FORK_REDUCE", "1") != "0"            # A/B switches (measurement)
         self.fuse_embed_bwd = os.environ.get("CAST_FUSE_EMBED_BWD", "1") != "0"
         self.before_backward = None  # set by dist.attach(): the barrier that lets this step overwrite the gradient buffer

@@ -244,9 +244,14 @@ int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const floa
                   unsigned long long seed, const unsigned long long* step, int site, const int* skip_ids, float* out,
                   float* attn_weights, float* row_max, float* row_linv, void* stream);
 /* Tuning hook: columns per streamed chunk of the tensor-core attention kernels (32 or 64; default 32). */
-/* Programmatic dependent launch of the training step's main-chain kernels (default on): the next kernel's CTAs may be
- * scheduled while the previous kernel drains; every such kernel waits (griddepcontrol.wait) before its first access to
- * data the previous kernel produces, so results do not change.  0 = ordinary stream-ordered launches (A/B hook). */
+/* Programmatic dependent launch of the training step's main-chain kernels.  Off (0, the default): ordinary
+ * stream-ordered launches, any operand may come from the immediately preceding launch.  On (1, what engine.py sets):
+ * the next kernel's CTAs may be scheduled while the previous kernel drains, and a kernel reads a few operands BEFORE it
+ * waits (griddepcontrol.wait) for that previous kernel — the caller promises that those operands were complete earlier:
+ *   - weights, biases, LayerNorm gamma / beta and the pre-split weight images of every row kernel;
+ *   - cast_qkv_bwd(_embed): dQ, x, qn (only dK, dV and dres may be outputs of the immediately preceding launch);
+ *   - cast_attn_bwd with out / queries: every input except dO (Q, K, V, out, queries, masks, row_max, row_linv, skip_ids).
+ * Everything else is read, and everything is written, after the wait, so results do not change. */
 int cast_set_pdl(int on);
 int cast_attn_set_chunk(int columns);
 /* Tuning hook: warps that share one 16-row block of a 64-row attention tile, each taking a 32-key slice of every

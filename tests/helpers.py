@@ -36,7 +36,9 @@ def emu_lib():
 def backend(kind):
     """kind = 'gpu' -> (cuda lib, cuda device); kind = 'emu' -> (emulated lib, cpu)."""
     if kind == "gpu":
-        return castlib.load_library(), torch.device("cuda", 0)
+        lib = castlib.load_library()
+        lib.cast_set_pdl(0)   # ABI-level tests feed kernels operands made by the launch just before: plain stream order
+        return lib, torch.device("cuda", 0)
     return emu_lib(), torch.device("cpu")
 
 
