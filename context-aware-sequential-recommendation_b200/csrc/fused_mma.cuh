@@ -511,10 +511,19 @@ __global__ void __launch_bounds__(128 * NG, 1) ffn_bwd_mma_kernel(FfnBwdArgs a, 
   constexpr int SL = BT / 64;  // row slices of the column sums
   float vb1 = 0.f, vb2 = 0.f;  // bias gradients, dgamma, dbeta: this thread's (column, row slice) partials
   float dgam = 0.f, dbet = 0.f;
-  cast_pdl_wait();   // (weights and gamma, requested above, are not the previous kernel's output; the row tiles are)
+  // Of the first tile only dx is the previous kernel's output (the loss tail or the block above's qkv backward kernel);
+  // LN(y), the hidden activations and y are forward-pass data: requested before the wait, with the weights and gamma.
+  if ((long)blockIdx.x < a.ntiles) {
+    const long row0 = (long)blockIdx.x * FR;
+    rm_load_tile_async<S, NW>(sm + TILE, a.zn, row0, d.N, H, v1);
+    rm_load_tile_async<S, NW>(sm + 2 * TILE, a.h1d, row0, d.N, H, v2);
+    rm_load_tile_async<S, NW>(sm + 3 * TILE, a.y, row0, d.N, H, v3);
+  }
+  cp_async_commit();
+  cast_pdl_wait();
   cast_pdl_trigger();  // the attention dQ kernel that follows has a long prologue that does not depend on this kernel
-  if ((long)blockIdx.x < a.ntiles) issue(blockIdx.x, 0);
-  else cp_async_commit();
+  if ((long)blockIdx.x < a.ntiles) rm_load_tile_async<S, NW>(sm, a.dx, (long)blockIdx.x * FR, d.N, H, v0);
+  cp_async_commit();
   // row mask of a tile (padding positions and rows past N get 0): fetched one tile ahead by threads 0..FR-1 and handed
   // over through shared memory (the first FR words of rowstat, free until the LayerNorm pass at the end of the tile)
   auto row_mask = [&](long tile) -> float {

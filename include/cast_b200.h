@@ -250,6 +250,7 @@ int cast_attn_fwd(const float* Q, long ldq, const float* K, long ldk, const floa
  * waits (griddepcontrol.wait) for that previous kernel — the caller promises that those operands were complete earlier:
  *   - weights, biases, LayerNorm gamma / beta and the pre-split weight images of every row kernel;
  *   - cast_qkv_bwd(_embed): dQ, x, qn (only dK, dV and dres may be outputs of the immediately preceding launch);
+ *   - cast_ffn_bwd: zn, h1d, y (only dx may be);
  *   - cast_attn_bwd with out / queries: every input except dO (Q, K, V, out, queries, masks, row_max, row_linv, skip_ids).
  * Everything else is read, and everything is written, after the wait, so results do not change. */
 int cast_set_pdl(int on);
