@@ -121,19 +121,26 @@ class ClockSampler:
         except Exception:
             self.nvml = None
 
-    def _poll(self):
+    def sample_now(self):
+        """one NVML reading from the calling thread (the timed loop calls it half-way: at least one sample is inside the
+        region however short it is)"""
         nv = self.nvml
-        while not self.stop_flag.is_set():
+        if nv is None:
+            return
+        try:
+            mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
             try:
-                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.rows.append((mhz, mask))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
             except Exception:
-                pass
-            time.sleep(0.004)
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.rows.append((mhz, mask))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self.stop_flag.is_set():
+            self.sample_now()
+            time.sleep(0.002)
 
     def start(self):
         if self.nvml is not None:
@@ -391,6 +398,8 @@ def main():
         ev[i][0].record()
         device_step(i)
         ev[i][1].record()
+        if rank == 0 and i == a.steps // 2:
+            clocks.sample_now()
     barrier()
     clk = clocks.stop() if rank == 0 else None
     t_dev = sum(s.elapsed_time(e) for s, e in ev) / 1e3
